@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: training tokens/s of the NLPScratch Transformer step on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|...]
+
+A "step" is one full-sequence training step (forward, softmax-CE, backward, [all-reduce], global-norm
+clip, Adam) over one batch of synthetic token ids.  Default workload = BASELINE.json configs[3]
+("c4": 6 layers, d_model 512, 8 heads, ff 2048, seq 512, batch 64 per GPU, vocab 8192), the
+configuration the metric is quoted on; weak scaling (per-GPU batch fixed).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident tokens/s; `e2e` = the same metric through
+the public API with pinned-host -> device copies of x,y and a device -> host read of the loss inside
+every timed step.  `--impl reference` times the reference's CPU algorithm (the NumPy oracle port;
+the reference itself is not on the GPU box) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (L, E, h, F, S, B/gpu, V)
+    "c4": (6, 512, 8, 2048, 512, 64, 8192),
+    "c4-32k": (6, 512, 8, 2048, 512, 64, 32768),
+    "c5": (12, 768, 12, 3072, 2048, 8, 8192),
+    "c3": (3, 256, 8, 1024, 320, 16, 32768),
+    "c2": (3, 256, 8, 1024, 320, 16, 574),
+    "tiny": (2, 64, 2, 128, 32, 4, 120),
+}
+METRIC = "train tokens/s"
+
+
+def flops_per_token(L, E, F, S, V):
+    return L * (24.0 * E * E + 12.0 * E * F + 6.0 * S * E) + 6.0 * E * V
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_burst": p["bf16_tflops"], "bf16_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc, self.lines, self.index = None, [], index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args, wl):
+    """The reference's CPU algorithm (oracle port) on the host cores, bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.transformer_oracle import OracleTransformer, full_sequence_step
+    L, E, h, F, S, B, V = wl
+    sample_B = 1 if L * E * S > 1_000_000 else min(B, 4)
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    np.random.seed(0)
+    model = OracleTransformer(V, E, h, F, L, S, dropout_p=0.1)
+    rng = np.random.default_rng(1234)
+    x = rng.integers(1, V, (sample_B, S)).astype(np.int32)
+    y = rng.integers(1, V, (sample_B, S)).astype(np.int32)
+    budget = 240.0
+    t_start = time.perf_counter()
+    for _ in range(args.warmup):
+        full_sequence_step(model, x, y, lr=1e-4, clip=1.0)
+        if time.perf_counter() - t_start > budget / 3:
+            break
+    done, t0 = 0, time.perf_counter()
+    for _ in range(args.steps):
+        full_sequence_step(model, x, y, lr=1e-4, clip=1.0)
+        done += 1
+        if time.perf_counter() - t_start > budget:
+            break
+    dt = time.perf_counter() - t0
+    tok_s = done * sample_B * S / dt
+    sample = "oracle port (NumPy, f64 activations like the reference under numpy>=2), batch %d x seq %d, %d steps" % (
+        sample_B, S, done)
+    line = {"impl": "reference", "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.workload, wl, 1, "reference CPU path"),
+            "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, wl, n_gpus, note):
+    L, E, h, F, S, B, V = wl
+    return {"workload": "%s: %dL d_model %d heads %d ff %d seq %d vocab %d batch %d/GPU full-sequence LM step (%s)" % (
+        name, L, E, h, F, S, V, B, note), "layers": L, "d_model": E, "heads": h, "ff": F, "seq_len": S, "vocab": V,
+        "batch_per_gpu": B, "global_batch": B * n_gpus, "parallelism": "dp%d" % n_gpus,
+        "l2": "per-step working set (activations, GBs) exceeds the 126 MB L2; no explicit flush"}
+
+
+def cpu_baseline_sample(wl, seconds=20.0):
+    from oracle.transformer_oracle import OracleTransformer, full_sequence_step
+    L, E, h, F, S, B, V = wl
+    sample_B = 1 if L * E * S > 1_000_000 else min(B, 4)
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    np.random.seed(0)
+    model = OracleTransformer(V, E, h, F, L, S, dropout_p=0.1)
+    rng = np.random.default_rng(1234)
+    x = rng.integers(1, V, (sample_B, S)).astype(np.int32)
+    y = rng.integers(1, V, (sample_B, S)).astype(np.int32)
+    t0, done = time.perf_counter(), 0
+    while done < 1 or (time.perf_counter() - t0 < seconds and done < 8):
+        full_sequence_step(model, x, y, lr=1e-4, clip=1.0)
+        done += 1
+    dt = time.perf_counter() - t0
+    return {"value": done * sample_B * S / dt, "unit": "tokens/s", "cores": threads, "kind": "port",
+            "sample": "oracle port, batch %d x seq %d, %d steps in %.1f s (f64 activations, OpenBLAS)" % (
+                sample_B, S, done, dt)}
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from nlpscratch_b200 import Transformer, _lib
+    from nlpscratch_b200.array import DeviceArray
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    L, E, h, F, S, B, V = wl
+    np.random.seed(1234)
+    model = Transformer(V, E, h, F, L, S, dropout_p=args.dropout, precision=args.precision, device=local)
+    dp = None
+    if distributed:
+        from nlpscratch_b200.dp import DataParallel
+        dp = DataParallel(model)
+        dp.broadcast_parameters(0)
+    rng = np.random.default_rng(1234 + rank)
+    nbatches = 4
+    xs = [rng.integers(1, V, (B, S)).astype(np.int32) for _ in range(nbatches)]
+    ys = [rng.integers(1, V, (B, S)).astype(np.int32) for _ in range(nbatches)]
+    xd = [DeviceArray.from_host(a) for a in xs]
+    yd = [DeviceArray.from_host(a) for a in ys]
+    lr, clip = 1e-4, 1.0
+
+    def step(i):
+        if dp is not None:
+            return dp.train_step(xd[i % nbatches], yd[i % nbatches], lr, clip)
+        return model.train_step(xd[i % nbatches], yd[i % nbatches], lr, clip)
+
+    def fence():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        loss = step(i)
+    fence()
+    first_loss = float(loss) if args.warmup else None
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    model.launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    ev0.record()
+    for i in range(args.steps):
+        loss = step(i)
+    ev1.record()
+    fence()
+    ms = ev0.elapsed_time(ev1)
+    launches = model.launch_count() + (dp.launches if dp else 0)
+    clocks = sampler.stop() if rank == 0 else None
+    last_loss = float(loss)
+    if distributed:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    tokens = B * S * world * args.steps
+    value = tokens / (ms * 1e-3)
+
+    # ---- end to end: pinned host -> device copies of x,y and a loss read-back inside every step ----
+    pin = []
+    for a in xs + ys:
+        p = C.c_void_p()
+        _lib.call("nlps_host_alloc_pinned", C.byref(p), C.c_size_t(a.nbytes))
+        C.memmove(p.value, a.ctypes.data, a.nbytes)
+        pin.append(p)
+    x_in, y_in = DeviceArray.empty((B, S), np.int32), DeviceArray.empty((B, S), np.int32)
+    x_in.bounds = y_in.bounds = (1, V - 1)
+    nbytes = xs[0].nbytes
+
+    def e2e_step(i):
+        _lib.call("nlps_memcpy_h2d", _lib.vp(x_in.ptr), pin[i % nbatches], C.c_size_t(nbytes), _lib.stream_ptr())
+        _lib.call("nlps_memcpy_h2d", _lib.vp(y_in.ptr), pin[nbatches + i % nbatches], C.c_size_t(nbytes), _lib.stream_ptr())
+        l = dp.train_step(x_in, y_in, lr, clip) if dp is not None else model.train_step(x_in, y_in, lr, clip)
+        return float(l)                              # device -> host read of the step's loss (synchronises)
+
+    for i in range(min(3, args.warmup)):
+        e2e_step(i)
+    fence()
+    e_steps = max(3, args.steps // 2)
+    t0 = time.perf_counter()
+    ev0.record()
+    for i in range(e_steps):
+        e2e_step(i)
+    ev1.record()
+    fence()
+    e_ms = ev0.elapsed_time(ev1)
+    if distributed:
+        t = torch.tensor([e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t.item())
+    e2e_value = B * S * world * e_steps / (e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM), timed alone with CUDA events ----------
+    roof = None
+    if rank == 0:
+        roof = gemm_roofline(torch, _lib, B * S, E, F, args.precision)
+        fpt = flops_per_token(L, E, F, S, V)
+        peaks = measured_peaks()
+        tf32_peak = peaks["bf16_sustained"] / 2.0
+        roof["step"] = {"algorithmic_tflop_per_step_per_gpu": fpt * B * S / 1e12,
+                        "achieved_tflops_per_gpu": fpt * value / world / 1e12,
+                        "frac_of_tf32_peak": fpt * value / world / 1e12 / tf32_peak,
+                        "tf32_peak_tflops": tf32_peak,
+                        "peak_note": "TF32 dense = 1/2 of the %s sustained BF16 peak in MEASURED_PEAKS.json" % peaks["source"]}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_sample(wl)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"tf32": "tf32", "fp32": "fp32", "tf32x3": "tf32x3"}[args.precision],
+            "data": "synthetic", "config": workload_config(args.workload, wl, world,
+                                                           "dropout %.2f, Adam lr 1e-4, clip 1.0" % args.dropout),
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": int(2 * nbytes),
+                    "d2h_bytes_per_step": 4, "steps": e_steps},
+            "roofline": roof, "cpu_baseline": cpu, "loss_first": first_loss, "loss_last": last_loss}
+    print(json.dumps(line), flush=True)
+
+
+def gemm_roofline(torch, _lib, N, E, F, precision):
+    """FFN up-projection GEMM (N,E)x(E,F), the most frequent shape of the step, timed alone."""
+    from nlpscratch_b200.array import DeviceArray, b200np
+    prec = _lib.PREC[precision]
+    a = DeviceArray.from_host(np.random.default_rng(0).standard_normal((N, E)).astype(np.float32))
+    b = DeviceArray.from_host(np.random.default_rng(1).standard_normal((E, F)).astype(np.float32))
+    c = DeviceArray.empty((N, F), np.float32)
+    stream = C.c_void_p(0)
+
+    def launch():
+        _lib.call("nlps_gemm", stream, C.c_int(prec), C.c_int(N), C.c_int(F), C.c_int(E), _lib.vp(a.ptr),
+                  C.c_int64(E), C.c_int(0), _lib.vp(b.ptr), C.c_int64(F), C.c_int(0), _lib.vp(c.ptr), C.c_int64(F),
+                  None, C.c_int(0), None, C.c_int64(0), None, C.c_int64(0), C.c_int(0))
+    for _ in range(5):
+        launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * N * E * F
+    peaks = measured_peaks()
+    peak = peaks["bf16_burst"] / 2.0
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32) %dx%dx%d" % (N, F, E),
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "ms_per_launch": ms, "peak_note": "TF32 dense = 1/2 of the %s burst BF16 peak" % peaks["source"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "tf32x3"])
+    ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

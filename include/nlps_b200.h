@@ -1,0 +1,211 @@
+/*
+ * nlps_b200.h -- C ABI of libnlps_b200.so: the B200 (sm_100a) training step of the
+ * NLPScratch next-word Transformer.
+ *
+ * The reference (hydrogendeuteride/NLPScratch) is pure Python and has no FFI; its
+ * boundary for this path is the duck-typed model object that
+ * utils/train.py::train_transformer drives (utils/train.py:104-140).  Every entry point
+ * below names the reference method (file:line under the reference tree) whose arithmetic
+ * it replaces.  nlpscratch_b200/transformer.py binds them with ctypes and re-exposes the
+ * reference's own method names, so the reference's loop runs unmodified on top.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named d_* is DEVICE memory, h_* is HOST memory.
+ *   - every function returns 0 on success, non-zero on failure; nlps_last_error() returns
+ *     a thread-local message.  There is NO CPU fallback: without a CUDA device every
+ *     compute entry point fails with a message.
+ *   - a model handle owns one CUDA stream of work order (nlps_set_stream); calls on one
+ *     handle are not thread-safe; launches are asynchronous unless stated otherwise.
+ *   - float tensors are fp32 row-major; token ids are int32; PAD id is 0.
+ */
+#ifndef NLPS_B200_H_
+#define NLPS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLPS_ABI_VERSION 1
+
+/* arithmetic mode of the dense contractions */
+enum {
+  NLPS_PREC_FP32 = 0,   /* CUDA-core FP32 FMA everywhere: the <=1e-4 "FP32-faithful" mode      */
+  NLPS_PREC_TF32 = 1,   /* tcgen05 kind::tf32 tensor-core GEMMs, FP32 accumulate in TMEM       */
+  NLPS_PREC_TF32X3 = 2  /* 3xTF32 split (hi*hi + lo*hi + hi*lo) on tcgen05: FP32-level error   */
+};
+
+/* parameter tensor ids (Transformer.__init__, Transformer/transformer.py:34-63) */
+enum {
+  NLPS_P_We = 0, NLPS_P_Wq, NLPS_P_Wk, NLPS_P_Wv, NLPS_P_Wo, NLPS_P_W1, NLPS_P_W2, NLPS_P_b1,
+  NLPS_P_b2, NLPS_P_W_vocab, NLPS_P_b_vocab, NLPS_P_ln1_gamma, NLPS_P_ln1_beta,
+  NLPS_P_ln2_gamma, NLPS_P_ln2_beta, NLPS_P_COUNT
+};
+/* which flat buffer a view points into */
+enum { NLPS_BUF_PARAM = 0, NLPS_BUF_GRAD = 1, NLPS_BUF_ADAM_M = 2, NLPS_BUF_ADAM_V = 3 };
+
+typedef struct nlps_model nlps_model;   /* opaque */
+typedef struct nlps_cache nlps_cache;   /* opaque: activations of ONE forward call */
+
+/* Transformer(vocab_size, embed_dim, num_heads, ff_dim, num_layers, max_len, ..., dropout_p,
+ * use_adam) -- transformer.py:9-21 */
+typedef struct nlps_config {
+  int32_t vocab_size, embed_dim, num_heads, ff_dim, num_layers, max_len;
+  float dropout_p;
+  int32_t use_adam;
+  int32_t precision;     /* NLPS_PREC_* */
+  uint64_t seed;         /* dropout Philox key */
+} nlps_config;
+
+/* strided view of one parameter tensor (or its grad / Adam moment) inside a flat buffer.
+ * Wq/Wk/Wv are column blocks of one packed (E,3E) matrix per layer, hence the strides. */
+typedef struct nlps_view {
+  void* d_ptr;
+  int32_t ndim;
+  int64_t shape[3];
+  int64_t stride[3];     /* in elements */
+} nlps_view;
+
+/* ---- library --------------------------------------------------------------------- */
+int nlps_abi_version(void);
+const char* nlps_last_error(void);
+int nlps_device_count(int* count);                 /* 0 devices is not an error here        */
+int nlps_device_info(int device, char* name_out, size_t name_cap, int* sm_count, int* cc_major,
+                     int* cc_minor, size_t* total_mem);
+
+/* ---- raw device memory for the host-side array shim (replaces the numpy/cupy array
+ *      module the reference picks at transformer.py:11-12) ------------------------------- */
+int nlps_malloc(void** d_ptr, size_t bytes);
+int nlps_free(void* d_ptr);
+int nlps_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);   /* async if pinned */
+int nlps_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);   /* synchronises    */
+int nlps_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream);
+int nlps_memset(void* d_dst, int value, size_t bytes, void* stream);
+int nlps_stream_sync(void* stream);
+int nlps_host_alloc_pinned(void** h_ptr, size_t bytes);
+int nlps_host_free_pinned(void* h_ptr);
+
+/* ---- model lifetime ------------------------------------------------------------------ */
+int nlps_create(const nlps_config* cfg, int device, nlps_model** out);
+int nlps_destroy(nlps_model* m);
+int nlps_set_stream(nlps_model* m, void* cuda_stream);       /* cudaStream_t; NULL = default */
+int nlps_set_precision(nlps_model* m, int precision);
+int nlps_set_training(nlps_model* m, int training);          /* train()/eval(), transformer.py:96-100 */
+int nlps_set_dropout(nlps_model* m, float p, uint64_t seed);
+int nlps_sync(nlps_model* m);
+
+/* flat buffers: [W_vocab b_vocab | layer L-1 ... layer 0 | We] -- backward-completion order,
+ * so that data-parallel buckets become ready front to back. */
+int nlps_flat_size(const nlps_model* m, int64_t* n_floats);
+int nlps_flat_ptr(nlps_model* m, int which_buf, void** d_ptr);
+int nlps_param_view(nlps_model* m, int which_buf, int param_id, nlps_view* out);
+int nlps_pe_ptr(nlps_model* m, void** d_ptr);                /* (max_len,E), transformer.py:609-615 */
+int nlps_num_buckets(const nlps_model* m, int* n);
+int nlps_bucket_range(const nlps_model* m, int bucket, int64_t* first_float, int64_t* n_floats);
+int nlps_stream_wait_bucket(nlps_model* m, int bucket, void* other_stream);  /* grads of bucket final */
+int nlps_wait_stream(nlps_model* m, void* other_stream);     /* model stream waits for other_stream */
+
+/* ---- the step --------------------------------------------------------------------------- */
+/* Transformer.forward, transformer.py:110-199.  d_x: (B,S) int32 with row stride x_row_stride
+ * (the driver passes the slice xb[:, :s_max], utils/train.py:110).  hidden_only!=0 returns the
+ * (B,S,E) final hidden state (return_hidden_only=True), else (B,S,V) logits with row stride
+ * ld_out >= V.  d_out may be NULL to keep the result only inside the cache. */
+int nlps_cache_create(nlps_model* m, int B, int S, nlps_cache** out);
+int nlps_cache_release(nlps_model* m, nlps_cache* c);
+int nlps_forward(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t x_row_stride,
+                 int hidden_only, float* d_out, int64_t ld_out);
+int nlps_cache_hidden_ptr(nlps_cache* c, void** d_h_final);  /* (B*S,E), cache['H_final'] */
+int nlps_cache_logits_ptr(nlps_cache* c, void** d_logits, int64_t* ld);
+int nlps_logits_ld(const nlps_model* m, int64_t* ld);        /* padded row stride of (N,V) buffers */
+
+/* Transformer.calculate_loss_dlogits, transformer.py:515-549.  rows = B*S (or B for the
+ * last-token path).  d_dlogits may alias d_logits.  grad_scale multiplies dlogits on top of the
+ * reference's 1/rows (1/world_size under data parallelism, else 1).  d_loss: one float. */
+int nlps_loss_dlogits(nlps_model* m, const float* d_logits, int64_t ld_logits, const int32_t* d_y,
+                      int64_t rows, float grad_scale, float* d_loss, float* d_dlogits, int64_t ld_dlogits);
+
+/* Transformer.backward, transformer.py:327-459.  Fills the flat grad buffer. */
+int nlps_backward(nlps_model* m, nlps_cache* c, const float* d_dlogits, int64_t ld_dlogits);
+/* Transformer.backward_last_token, transformer.py:201-325. */
+int nlps_backward_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_t_index,
+                             const float* d_dlogits_last, int64_t ld_dlogits);
+
+/* clip_grads, utils/function.py:27-38, over the whole flat grad buffer.  The scale factor stays
+ * on the device; *h_norm_out (optional) forces a synchronising read-back of the norm. */
+int nlps_clip(nlps_model* m, float max_norm, float* h_norm_out);
+/* Transformer.step / _adam_update, transformer.py:461-509.  use_clip_scale!=0 multiplies the
+ * gradients by the factor the last nlps_clip_compute left on the device (fused clip). */
+int nlps_clip_compute(nlps_model* m, float max_norm);
+int nlps_step(nlps_model* m, float lr, int use_clip_scale);
+int nlps_adam_t(nlps_model* m, int64_t* t, int set, int64_t value);
+
+/* Fused whole step for the full-sequence objective (transformer.py:635-641 with the clip of
+ * utils/train.py:122-129): forward, loss, backward; then, unless defer_update!=0 (data parallel:
+ * the caller all-reduces the flat grad buffer first and then calls nlps_clip_compute/nlps_step),
+ * clip and step.  max_norm<=0 disables the clip.  d_loss: one float on the device. */
+int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t x_row_stride,
+                    const int32_t* d_y, float lr, float max_norm, float grad_scale,
+                    int defer_update, float* d_loss);
+int nlps_launch_count(nlps_model* m, int64_t* launches, int reset);  /* kernels launched so far */
+
+/* ---- stand-alone operators (tests, the array shim and the benchmarks call these) --------- */
+/* C[M,N] = op(A)[M,K] * op(B)[K,N] (+bias[N]) (relu) (*gate>0) (+residual) ; trans flags say the
+ * operand is stored transposed (A as [K,M], B as [N,K]).  precision = NLPS_PREC_*.  */
+int nlps_gemm(void* stream, int precision, int M, int N, int K,
+              const float* d_A, int64_t lda, int trans_a,
+              const float* d_B, int64_t ldb, int trans_b,
+              float* d_C, int64_t ldc,
+              const float* d_bias, int relu,
+              const float* d_gate, int64_t ldg,
+              const float* d_residual, int64_t ldr,
+              int accumulate);
+/* causal + key-padding attention over packed (B*S,3E) Q|K|V rows (transformer.py:131-141),
+ * fully-masked rows attend to all keys (additive -1e9 semantics, transformer.py:585-606). */
+int nlps_attention_forward(void* stream, int precision, int B, int S, int h, int d,
+                           const float* d_qkv, const int32_t* d_x, float* d_ctx, float* d_lse);
+int nlps_attention_backward(void* stream, int precision, int B, int S, int h, int d,
+                            const float* d_qkv, const int32_t* d_x, const float* d_ctx,
+                            const float* d_lse, const float* d_dctx, float* d_dqkv);
+/* layer_norm_affine_forward/backward, utils/function.py:90-124 (eps 1e-6 inside the sqrt). */
+int nlps_layernorm_forward(void* stream, int64_t rows, int E, const float* d_x, const float* d_gamma,
+                           const float* d_beta, float* d_y, float* d_mean, float* d_rstd);
+int nlps_layernorm_backward(void* stream, int64_t rows, int E, const float* d_dy, const float* d_x,
+                            const float* d_mean, const float* d_rstd, const float* d_gamma,
+                            float* d_dx, float* d_dgamma, float* d_dbeta);
+/* We[x] + pe[:S] (transformer.py:114) and its scatter-add gradient (transformer.py:453-457),
+ * summed in ascending token position per vocabulary row: deterministic. */
+int nlps_embed_forward(void* stream, int B, int S, int E, int V, const int32_t* d_x,
+                       int64_t x_row_stride, const float* d_We, const float* d_pe, float* d_out,
+                       int32_t* d_x_flat, int32_t* d_err_flag);
+int nlps_embed_backward(void* stream, int64_t N, int E, int V, const int32_t* d_x_flat,
+                        const float* d_dh, float* d_dWe);
+int nlps_colsum(void* stream, int64_t rows, int cols, const float* d_x, int64_t ld, float* d_out);
+int nlps_sumsq(void* stream, int64_t n, const float* d_x, float* d_out);
+
+/* ---- element-wise / indexing helpers behind the array shim (model.np, utils/train.py:46-116) */
+int nlps_strided_copy(void* stream, int elem_size, int ndim, const int64_t* shape,
+                      const void* d_src, const int64_t* src_stride, void* d_dst, const int64_t* dst_stride);
+int nlps_gather_rows(void* stream, int elem_size, int64_t n_out, int64_t row_elems, const void* d_src,
+                     int64_t src_row_stride, const int32_t* d_index, int64_t n_src, void* d_dst);
+int nlps_gather_last(void* stream, int B, int S, int E, const float* d_h, const int32_t* d_t, float* d_out);
+int nlps_count_nonzero_rows(void* stream, int64_t rows, int64_t cols, const int32_t* d_x,
+                            int64_t row_stride, int32_t* d_out);
+/* op: 0 add 1 sub 2 mul 3 div 4 max ; b_mode: 0 scalar, 1 same shape, 2 row vector (cols) */
+int nlps_binary_f32(void* stream, int op, int64_t n, int64_t cols, const float* d_a, const float* d_b,
+                    float b_scalar, int b_mode, float* d_out);
+int nlps_binary_i32(void* stream, int op, int64_t n, const int32_t* d_a, const int32_t* d_b,
+                    int32_t b_scalar, int b_mode, int32_t* d_out);
+/* op: 0 exp 1 sqrt 2 square 3 log 4 neg */
+int nlps_unary_f32(void* stream, int op, int64_t n, const float* d_a, float* d_out);
+/* op: 0 sum 1 max 2 sum of squares ; result is one element on the device */
+int nlps_reduce_f32(void* stream, int op, int64_t n, const float* d_a, float* d_out);
+int nlps_reduce_i32(void* stream, int op, int64_t n, const int32_t* d_a, int32_t* d_out);
+int nlps_compare_ne_i32(void* stream, int64_t n, const int32_t* d_a, int32_t value, int32_t* d_out);
+int nlps_cast_i32_f32(void* stream, int64_t n, const int32_t* d_a, float* d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* NLPS_B200_H_ */

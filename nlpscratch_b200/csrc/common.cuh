@@ -1,0 +1,209 @@
+// Shared helpers for libnlps_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+
+namespace nlps {
+
+// ---- error plumbing -------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+void count_launch(int n = 1);         // every kernel launch of ours goes through this counter
+long long launch_count(bool reset);
+
+#define NLPS_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::nlps::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 1;                                                                           \
+    }                                                                                     \
+  } while (0)
+
+#define NLPS_TRY(expr)                \
+  do {                                \
+    int _s = (expr);                  \
+    if (_s != 0) return _s;           \
+  } while (0)
+
+#define NLPS_REQUIRE(cond, ...)       \
+  do {                                \
+    if (!(cond)) {                    \
+      ::nlps::set_error(__VA_ARGS__); \
+      return 2;                       \
+    }                                 \
+  } while (0)
+
+// check the launch itself (not the execution): cheap, no sync
+#define NLPS_LAUNCH_CHECK()                                                                \
+  do {                                                                                     \
+    ::nlps::count_launch();                                                                \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess) {                                                               \
+      ::nlps::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 1;                                                                            \
+    }                                                                                      \
+  } while (0)
+
+constexpr int kNumSMs = 148;           // B200
+constexpr float kLnEps = 1e-6f;        // transformer.py:150,161
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// ---- device helpers -------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Philox4x32-10 (Salmon et al. 2011).  counter = (idx4, stream, step, 0); key = seed.
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                            uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+struct DropoutParams {
+  float p;             // drop probability; <=0 disables
+  float inv_keep;      // 1/(1-p)
+  uint32_t threshold;  // keep iff rand32 < threshold  (threshold = keep * 2^32, saturated)
+  uint32_t seed_lo, seed_hi;
+  uint32_t stream;     // (layer*2 + which)
+  uint32_t step;       // forward-call counter so that every step draws fresh masks
+};
+
+// keep-mask of 4 consecutive elements idx4*4 .. idx4*4+3  (inverted dropout, transformer.py:102-108)
+__device__ __forceinline__ uint4 dropout_rand4(const DropoutParams& d, uint64_t idx4) {
+  return philox4x32((uint32_t)idx4, (uint32_t)(idx4 >> 32), d.stream, d.step, d.seed_lo, d.seed_hi);
+}
+__device__ __forceinline__ float dropout_one(const DropoutParams& d, uint64_t idx, float v) {
+  const uint4 r = dropout_rand4(d, idx >> 2);
+  const uint32_t lane = (uint32_t)(idx & 3);
+  const uint32_t rv = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
+  return rv < d.threshold ? v * d.inv_keep : 0.f;
+}
+
+inline DropoutParams make_dropout(float p, uint64_t seed, uint32_t stream, uint32_t step) {
+  DropoutParams d{};
+  d.p = p;
+  if (p > 0.f) {
+    const double keep = 1.0 - (double)p;
+    d.inv_keep = (float)(1.0 / keep);
+    double t = keep * 4294967296.0;
+    d.threshold = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+  } else {
+    d.inv_keep = 1.f;
+    d.threshold = 0xFFFFFFFFu;
+  }
+  d.seed_lo = (uint32_t)seed;
+  d.seed_hi = (uint32_t)(seed >> 32);
+  d.stream = stream;
+  d.step = step;
+  return d;
+}
+
+// ---- GEMM argument block shared by the tcgen05 and the CUDA-core implementations -------
+struct GemmArgs {
+  int M = 0, N = 0, K = 0;
+  const float* A = nullptr; int64_t lda = 0; bool trans_a = false;   // trans_a: stored [K,M]
+  const float* B = nullptr; int64_t ldb = 0; bool trans_b = false;   // trans_b: stored [N,K]
+  float* C = nullptr; int64_t ldc = 0;
+  const float* bias = nullptr;      // [N], added first
+  bool relu = false;                // then max(0,.)
+  const float* gate = nullptr; int64_t ldg = 0;       // then *= (gate > 0)       (ReLU backward)
+  DropoutParams drop = {0.f, 1.f, 0xFFFFFFFFu, 0, 0, 0, 0};   // then inverted dropout
+  const float* residual = nullptr; int64_t ldr = 0;   // then += residual
+  bool accumulate = false;          // finally C += result instead of C = result
+};
+
+// bias -> relu -> gate -> dropout -> residual, identical in every GEMM implementation
+__device__ __forceinline__ float gemm_epilogue_one(const GemmArgs& g, float acc, int row, int col) {
+  if (g.bias) acc += g.bias[col];
+  if (g.relu) acc = fmaxf(acc, 0.f);
+  if (g.gate) acc = g.gate[(int64_t)row * g.ldg + col] > 0.f ? acc : 0.f;
+  if (g.drop.p > 0.f) acc = dropout_one(g.drop, (uint64_t)row * (uint64_t)g.N + (uint64_t)col, acc);
+  if (g.residual) acc += g.residual[(int64_t)row * g.ldr + col];
+  return acc;
+}
+
+int gemm_fp32(cudaStream_t st, const GemmArgs& g);       // gemm_simt.cu
+int gemm_tf32(cudaStream_t st, const GemmArgs& g);       // gemm_tcgen05.cu  (1xTF32)
+int gemm_tf32x3(cudaStream_t st, const GemmArgs& g);     // 3-pass split, FP32-level error
+bool gemm_tf32_supported(const GemmArgs& g);
+int gemm_dispatch(cudaStream_t st, int precision, const GemmArgs& g);
+
+// attention.cu
+int attention_forward(cudaStream_t st, int precision, int B, int S, int h, int d, const float* qkv,
+                      const int32_t* x, const int32_t* first_nonpad, float* ctx, float* lse);
+int attention_backward(cudaStream_t st, int precision, int B, int S, int h, int d, const float* qkv,
+                       const int32_t* x, const int32_t* first_nonpad, const float* ctx, const float* lse,
+                       const float* dctx, float* delta_scratch, float* dqkv);
+int first_nonpad(cudaStream_t st, int B, int S, const int32_t* x, int32_t* out);
+
+// rowwise.cu
+int layernorm_forward(cudaStream_t st, int64_t rows, int E, const float* x, const float* gamma,
+                      const float* beta, float* y, float* mean, float* rstd);
+int layernorm_backward(cudaStream_t st, int64_t rows, int E, const float* dy, const float* x,
+                       const float* mean, const float* rstd, const float* gamma, float* dx,
+                       float* dx_dropped, const DropoutParams* drop,
+                       float* dgamma, float* dbeta, float* partial_scratch);
+size_t layernorm_backward_scratch_floats(int E);
+int softmax_xent(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
+                 float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss_scratch);
+int colsum(cudaStream_t st, int64_t rows, int cols, const float* x, int64_t ld, float* out, float* scratch);
+size_t colsum_scratch_floats(int cols);
+int sumsq(cudaStream_t st, int64_t n, const float* x, float* out, float* scratch);
+size_t sumsq_scratch_floats();
+
+// embed.cu
+int embed_forward(cudaStream_t st, int B, int S, int E, int V, const int32_t* x, int64_t xs,
+                  const float* We, const float* pe, float* out, int32_t* x_flat, int32_t* err_flag);
+int embed_backward(cudaStream_t st, int64_t N, int E, int V, const int32_t* x_flat, const float* dh,
+                   float* dWe, int32_t* scratch_i32);
+size_t embed_backward_scratch_ints(int64_t N, int V);
+int scatter_rows(cudaStream_t st, int B, int S, int E, const int32_t* t, const float* rows, float* out);
+
+// optimizer.cu
+int clip_scale_from_sumsq(cudaStream_t st, const float* sumsq, float max_norm, float* scale_out, float* norm_out);
+int scale_inplace(cudaStream_t st, int64_t n, float* x, const float* scale_dev);
+int adam_update(cudaStream_t st, int64_t n, float* p, const float* g, float* m, float* v, float lr,
+                float b1, float b2, float one_minus_b1, float one_minus_b2, float eps, float bc1, float bc2,
+                const float* clip_scale_dev);
+int sgd_update(cudaStream_t st, int64_t n, float* p, const float* g, float lr, const float* clip_scale_dev);
+
+}  // namespace nlps
+
+namespace nlps {
+// array_ops.cu
+int strided_copy(cudaStream_t st, int elem_size, int ndim, const int64_t* shape, const void* src,
+                 const int64_t* sstr, void* dst, const int64_t* dstr);
+int gather_rows(cudaStream_t st, int elem_size, int64_t n_out, int64_t row_elems, const void* src, int64_t src_stride,
+                const int32_t* index, int64_t n_src, void* dst);
+int gather_last(cudaStream_t st, int B, int S, int E, const float* h, const int32_t* t, float* out);
+int count_nonzero_rows(cudaStream_t st, int64_t rows, int64_t cols, const int32_t* x, int64_t stride, int32_t* out);
+int binary_f32(cudaStream_t st, int op, int64_t n, int64_t cols, const float* a, const float* b, float bs, int mode, float* out);
+int binary_i32(cudaStream_t st, int op, int64_t n, const int32_t* a, const int32_t* b, int32_t bs, int mode, int32_t* out);
+int unary_f32(cudaStream_t st, int op, int64_t n, const float* a, float* out);
+int reduce_f32(cudaStream_t st, int op, int64_t n, const float* a, float* out);
+int reduce_i32(cudaStream_t st, int op, int64_t n, const int32_t* a, int32_t* out);
+int compare_ne_i32(cudaStream_t st, int64_t n, const int32_t* a, int32_t value, int32_t* out);
+int cast_i32_f32(cudaStream_t st, int64_t n, const int32_t* a, float* out);
+}  // namespace nlps

@@ -1,0 +1,534 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = op(A)[M,K] * op(B)[K,N]  with fused epilogue.
+//
+//   * operands are FP32 in HBM, fed by TMA (SWIZZLE_128B boxes, 128 B = 32 floats wide) into a
+//     4..6 stage shared-memory ring; `tcgen05.mma.cta_group::1.kind::tf32` (M=128, N=128|256, K=8)
+//     accumulates FP32 in TMEM; two accumulator buffers let the epilogue of tile i overlap the
+//     MMAs of tile i+1.
+//   * both operand majors are native: a row-major [rows,K] operand is K-major, a row-major
+//     [K,rows] operand is MN-major (instruction-descriptor transpose bits), so forward (X@W),
+//     dgrad (dY@W^T) and wgrad (X^T@dY) all read the tensors where they lie -- no transposes.
+//   * warp roles: warp0 = TMA producer, warp1 = TMEM owner + single-thread MMA issuer,
+//     warps2-5 = epilogue (tcgen05.ld 32x32b -> smem transpose -> coalesced float4 stores with
+//     bias / ReLU / ReLU-gate / Philox dropout / residual fused).
+//   * persistent: grid = min(#work items, #SMs); work item = (split-K slice, n tile, m tile),
+//     m fastest so concurrent CTAs share the B tile in L2.  Small-MN/large-K products (weight
+//     gradients) are split along K into a workspace and reduced in a fixed order (deterministic).
+#include "common.cuh"
+#include <cuda.h>
+#include <algorithm>
+
+namespace nlps {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                 // floats per k-block = one 128-byte swizzle span
+constexpr int UMMA_K = 8;              // kind::tf32: 32 bytes of K per instruction
+constexpr int kThreads = 192;
+constexpr int kEpiStageFloats = 32 * 36;   // per epilogue warp: 32 rows x (32+4) floats
+constexpr uint32_t kSpinLimit = 1u << 27;  // a lost barrier traps instead of hanging the GPU
+
+template <int BN>
+struct TileCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 4;
+  static constexpr int kBBytes = BN * BK * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kEpiBytes = 4 * kEpiStageFloats * 4;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
+//   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct KernelArgs {
+  GemmArgs g;
+  int num_m_tiles, num_n_tiles, splits, kblocks_total, kblocks_per_split;
+  float* ws;            // split-K workspace [splits][M][ws_ld] or null
+  int64_t ws_ld;
+  int vec_ok;           // float4 epilogue allowed (alignment of C / residual / gate / N)
+};
+
+// ---- epilogue store of one 32x32 fp32 block, coalesced ---------------------------------
+__device__ __forceinline__ void store_block(const KernelArgs& ka, float* stg, int lane, int row0, int col0,
+                                            int split) {
+  const GemmArgs& g = ka.g;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3);
+    const int c4 = (lane & 7) * 4;
+    const int row = row0 + r, col = col0 + c4;
+    if (row >= g.M || col >= g.N) continue;
+    float4 v = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
+    if (ka.ws != nullptr) {      // split-K partial: raw accumulators, epilogue runs in the reducer
+      float* dst = ka.ws + ((int64_t)split * g.M + row) * ka.ws_ld + col;
+      *reinterpret_cast<float4*>(dst) = v;   // ws_ld is a multiple of 4 and padded
+      continue;
+    }
+    if (ka.vec_ok && col + 3 < g.N) {
+      if (g.bias) {
+        const float4 b = *reinterpret_cast<const float4*>(g.bias + col);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      if (g.gate) {
+        const float4 t = *reinterpret_cast<const float4*>(g.gate + (int64_t)row * g.ldg + col);
+        v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f;
+        v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
+      }
+      if (g.drop.p > 0.f) {
+        const uint64_t idx = (uint64_t)row * (uint64_t)g.N + (uint64_t)col;   // multiple of 4 here
+        const uint4 rnd = dropout_rand4(g.drop, idx >> 2);
+        v.x = rnd.x < g.drop.threshold ? v.x * g.drop.inv_keep : 0.f;
+        v.y = rnd.y < g.drop.threshold ? v.y * g.drop.inv_keep : 0.f;
+        v.z = rnd.z < g.drop.threshold ? v.z * g.drop.inv_keep : 0.f;
+        v.w = rnd.w < g.drop.threshold ? v.w * g.drop.inv_keep : 0.f;
+      }
+      if (g.residual) {
+        const float4 t = *reinterpret_cast<const float4*>(g.residual + (int64_t)row * g.ldr + col);
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+      }
+      float4* dst = reinterpret_cast<float4*>(g.C + (int64_t)row * g.ldc + col);
+      if (g.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+      *dst = v;
+    } else {
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (col + j >= g.N) break;
+        float o = gemm_epilogue_one(g, vv[j], row, col + j);
+        float* dst = g.C + (int64_t)row * g.ldc + col + j;
+        if (g.accumulate) o += *dst;
+        *dst = o;
+      }
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const KernelArgs ka) {
+  using Cfg = TileCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;            // SWIZZLE_128B atoms need 1024-B alignment
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t epi_base = base + Cfg::kStages * Cfg::kStageBytes;
+  float* epi_ptr = reinterpret_cast<float*>(base_ptr + Cfg::kStages * Cfg::kStageBytes);
+  const uint32_t bar_base = epi_base + Cfg::kEpiBytes;
+  // barrier layout (8 B each): full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::kStages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::kStages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::kStages * Cfg::kStageBytes + Cfg::kEpiBytes +
+                                           8 * (2 * Cfg::kStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GemmArgs& g = ka.g;
+  const int tiles = ka.num_m_tiles * ka.num_n_tiles;
+  const int items = tiles * ka.splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int split = item / tiles;
+        const int t = item - split * tiles;
+        const int m0 = (t % ka.num_m_tiles) * BM;
+        const int n0 = (t / ka.num_m_tiles) * BN;
+        const int kb0 = split * ka.kblocks_per_split;
+        const int kb1 = min(ka.kblocks_total, kb0 + ka.kblocks_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = base + stage * Cfg::kStageBytes;
+          const uint32_t b_dst = a_dst + Cfg::kABytes;
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          const int k0 = kb * BK;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_dst + j * 4096, &map_a, full_bar(stage), m0 + 32 * j, k0);
+          } else {
+            tma_load_2d(a_dst, &map_a, full_bar(stage), k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_dst + j * 4096, &map_b, full_bar(stage), n0 + 32 * j, k0);
+          } else {
+            tma_load_2d(b_dst, &map_b, full_bar(stage), k0, n0);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bits4-5=1), A=B=tf32 (2 at bits 7-9 / 10-12), majors, N>>3, M>>4
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                 ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0; int local = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++local) {
+        const int split = item / tiles;
+        const int kb0 = split * ka.kblocks_per_split;
+        const int kb1 = min(ka.kblocks_total, kb0 + ka.kblocks_per_split);
+        const int buf = local & 1;
+        const uint32_t aphase = (uint32_t)(local >> 1) & 1u;
+        mbar_wait(tempty_bar(buf), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_src = base + stage * Cfg::kStageBytes;
+          const uint32_t b_src = a_src + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: rows of 128 B, 8-row groups 1024 B apart, +32 B per K=8 step.
+            // MN-major: 32-float column slabs of (BK x 128 B) = 4096 B (LBO), +1024 B per K=8 step.
+            const uint64_t ad = A_MN ? make_desc(a_src + k * 1024, 4096, 1024) : make_desc(a_src + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? make_desc(b_src + k * 1024, 4096, 1024) : make_desc(b_src + k * 32, 16, 1024);
+            umma_tf32(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));        // smem slot free once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(tfull_bar(buf));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    float* stg = epi_ptr + (warp - 2) * kEpiStageFloats;
+    int local = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++local) {
+      const int split = item / tiles;
+      const int t = item - split * tiles;
+      const int m0 = (t % ka.num_m_tiles) * BM;
+      const int n0 = (t / ka.num_m_tiles) * BN;
+      const int buf = local & 1;
+      const uint32_t aphase = (uint32_t)(local >> 1) & 1u;
+      mbar_wait(tfull_bar(buf), aphase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+      const bool rows_live = (m0 + q * 32) < g.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const bool live = rows_live && (n0 + c * 32) < g.N;     // warp-uniform
+        if (live) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(stg + lane * 36 + i * 4) =
+                make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                            __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          __syncwarp();
+          if (c == BN / 32 - 1 || (n0 + (c + 1) * 32) >= g.N) {
+            // last TMEM read of this buffer done: hand it back before the global stores
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+          }
+          store_block(ka, stg, lane, m0 + q * 32, n0 + c * 32, split);
+          __syncwarp();
+        }
+      }
+      if (!rows_live) {
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(tempty_bar(buf));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---- split-K reducer (fixed summation order => deterministic) --------------------------
+__global__ void splitk_reduce_kernel(const KernelArgs ka) {
+  const GemmArgs& g = ka.g;
+  const int64_t total = (int64_t)g.M * g.N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / g.N), col = (int)(i - (int64_t)row * g.N);
+    float acc = 0.f;
+    for (int s = 0; s < ka.splits; ++s) acc += ka.ws[((int64_t)s * g.M + row) * ka.ws_ld + col];
+    float o = gemm_epilogue_one(g, acc, row, col);
+    float* dst = g.C + (int64_t)row * g.ldc + col;
+    if (g.accumulate) o += *dst;
+    *dst = o;
+  }
+}
+
+// hi = round-to-nearest TF32 of x (low 13 mantissa bits zero), lo = x - hi (exact in FP32)
+__global__ void split_hi_lo_kernel(const float* __restrict__ src, int64_t ld, int rows, int cols, int64_t ldo,
+                                   float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t total = (int64_t)rows * ldo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ldo), c = (int)(i - (int64_t)r * ldo);
+    float x = c < cols ? src[(int64_t)r * ld + c] : 0.f;
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+    const float h = __uint_as_float(hb);
+    hi[i] = h;
+    lo[i] = x - h;
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: dim0 = contiguous (inner) extent, dim1 = rows with stride ld floats.
+int make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, int64_t ld, uint32_t box_inner,
+             uint32_t box_outer, bool round_tf32) {
+  EncodeTiledFn fn = encode_fn();
+  NLPS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NLPS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%lld)",
+               (int)r, (unsigned long long)inner, (unsigned long long)outer, (long long)ld);
+  return 0;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <int BN>
+int launch(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const KernelArgs& ka, int grid) {
+  using Cfg = TileCfg<BN>;
+  const bool amn = ka.g.trans_a, bmn = !ka.g.trans_b;
+#define NLPS_GEMM_CASE(AM, BMN)                                                                              \
+  {                                                                                                          \
+    auto kern = gemm_tf32_kernel<BN, AM, BMN>;                                                               \
+    static bool attr_set = false;                                                                            \
+    if (!attr_set) {                                                                                         \
+      NLPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));   \
+      attr_set = true;                                                                                       \
+    }                                                                                                        \
+    kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, ka);                                               \
+  }
+  if (amn && bmn) NLPS_GEMM_CASE(true, true)
+  else if (amn) NLPS_GEMM_CASE(true, false)
+  else if (bmn) NLPS_GEMM_CASE(false, true)
+  else NLPS_GEMM_CASE(false, false)
+#undef NLPS_GEMM_CASE
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+
+int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
+  if (g.M <= 0 || g.N <= 0) return 0;
+  NLPS_REQUIRE(g.K > 0, "gemm_tf32: K must be positive");
+  NLPS_REQUIRE(gemm_tf32_supported(g), "gemm_tf32: operands not TMA-addressable (need 16-B aligned bases, ld %% 4 == 0)");
+  // tile shape: wide tiles when there is enough work to fill the machine
+  const int64_t tiles256 = ceil_div(g.M, BM) * ceil_div(g.N, 256);
+  const int BN = (g.N > 128 && tiles256 >= 96) ? 256 : 128;
+  KernelArgs ka{};
+  ka.g = g;
+  ka.num_m_tiles = (int)ceil_div(g.M, BM);
+  ka.num_n_tiles = (int)ceil_div(g.N, BN);
+  ka.kblocks_total = (int)ceil_div(g.K, BK);
+  const int tiles = ka.num_m_tiles * ka.num_n_tiles;
+  int splits = 1;
+  if (tiles < 64 && ka.kblocks_total >= 64) {            // weight-gradient shaped: few tiles, long K
+    splits = (int)std::min<int64_t>(std::min<int64_t>(ceil_div(kNumSMs, tiles), ka.kblocks_total / 16), 32);
+    if (splits < 1) splits = 1;
+  }
+  ka.kblocks_per_split = (int)ceil_div(ka.kblocks_total, splits);
+  splits = (int)ceil_div(ka.kblocks_total, ka.kblocks_per_split);
+  ka.splits = splits;
+  ka.vec_ok = (aligned16(g.C) && g.ldc % 4 == 0 && (!g.bias || aligned16(g.bias)) &&
+               (!g.residual || (aligned16(g.residual) && g.ldr % 4 == 0)) &&
+               (!g.gate || (aligned16(g.gate) && g.ldg % 4 == 0)) && (g.drop.p <= 0.f || g.N % 4 == 0)) ? 1 : 0;
+  ka.ws = nullptr;
+  ka.ws_ld = round_up(g.N, 4);
+  if (splits > 1) {
+    NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ka.ws), (size_t)splits * g.M * ka.ws_ld * sizeof(float), st));
+  }
+  CUtensorMap ma, mb;
+  if (g.trans_a) NLPS_TRY(make_map(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K, g.lda, 32, BK, round_tf32));
+  else NLPS_TRY(make_map(&ma, g.A, (uint64_t)g.K, (uint64_t)g.M, g.lda, BK, BM, round_tf32));
+  if (g.trans_b) NLPS_TRY(make_map(&mb, g.B, (uint64_t)g.K, (uint64_t)g.N, g.ldb, BK, (uint32_t)BN, round_tf32));
+  else NLPS_TRY(make_map(&mb, g.B, (uint64_t)g.N, (uint64_t)g.K, g.ldb, 32, BK, round_tf32));
+  const int items = tiles * splits;
+  const int grid = std::min(items, kNumSMs);
+  if (BN == 256) NLPS_TRY(launch<256>(st, ma, mb, ka, grid));
+  else NLPS_TRY(launch<128>(st, ma, mb, ka, grid));
+  if (splits > 1) {
+    const int64_t total = (int64_t)g.M * g.N;
+    const int rgrid = (int)std::min<int64_t>(ceil_div(total, 256), kNumSMs * 8);
+    splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(ka);
+    NLPS_LAUNCH_CHECK();
+    NLPS_CUDA(cudaFreeAsync(ka.ws, st));
+  }
+  return 0;
+}
+
+}  // namespace
+
+bool gemm_tf32_supported(const GemmArgs& g) {
+  return aligned16(g.A) && aligned16(g.B) && g.lda % 4 == 0 && g.ldb % 4 == 0 && g.M > 0 && g.N > 0 && g.K > 0;
+}
+
+int gemm_tf32(cudaStream_t st, const GemmArgs& g) { return gemm_tf32_impl(st, g, /*round_tf32=*/true); }
+
+// 3xTF32: A = Ah + Al, B = Bh + Bl with Ah,Bh exactly representable in TF32;
+// T = Al*Bh + Ah*Bl + Ah*Bh (small terms first), dropping only Al*Bl (~2^-22 relative);
+// the fused epilogue then runs once over T.
+int gemm_tf32x3(cudaStream_t st, const GemmArgs& g) {
+  if (g.M <= 0 || g.N <= 0) return 0;
+  const int a_rows = g.trans_a ? g.K : g.M, a_cols = g.trans_a ? g.M : g.K;
+  const int b_rows = g.trans_b ? g.N : g.K, b_cols = g.trans_b ? g.K : g.N;
+  const int64_t lda2 = round_up(a_cols, 4), ldb2 = round_up(b_cols, 4), ldt = round_up(g.N, 4);
+  const size_t na = (size_t)a_rows * lda2, nb = (size_t)b_rows * ldb2, nt = (size_t)g.M * ldt;
+  float* buf = nullptr;
+  NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&buf), (2 * na + 2 * nb + nt) * sizeof(float), st));
+  float *ah = buf, *al = buf + na, *bh = buf + 2 * na, *bl = buf + 2 * na + nb, *tmp = buf + 2 * na + 2 * nb;
+  split_hi_lo_kernel<<<(int)std::min<int64_t>(ceil_div((int64_t)na, 256), kNumSMs * 8), 256, 0, st>>>(
+      g.A, g.lda, a_rows, a_cols, lda2, ah, al);
+  NLPS_LAUNCH_CHECK();
+  split_hi_lo_kernel<<<(int)std::min<int64_t>(ceil_div((int64_t)nb, 256), kNumSMs * 8), 256, 0, st>>>(
+      g.B, g.ldb, b_rows, b_cols, ldb2, bh, bl);
+  NLPS_LAUNCH_CHECK();
+  GemmArgs p{};
+  p.M = g.M; p.N = g.N; p.K = g.K; p.trans_a = g.trans_a; p.trans_b = g.trans_b;
+  p.lda = lda2; p.ldb = ldb2; p.C = tmp; p.ldc = ldt;
+  p.A = al; p.B = bh;
+  NLPS_TRY(gemm_tf32_impl(st, p, false));
+  p.accumulate = true;
+  p.A = ah; p.B = bl;
+  NLPS_TRY(gemm_tf32_impl(st, p, false));
+  p.A = ah; p.B = bh;
+  NLPS_TRY(gemm_tf32_impl(st, p, false));
+  KernelArgs ka{};
+  ka.g = g;
+  ka.splits = 1;
+  ka.ws = tmp;
+  ka.ws_ld = ldt;
+  const int64_t total = (int64_t)g.M * g.N;
+  splitk_reduce_kernel<<<(int)std::min<int64_t>(ceil_div(total, 256), kNumSMs * 8), 256, 0, st>>>(ka);
+  NLPS_LAUNCH_CHECK();
+  NLPS_CUDA(cudaFreeAsync(buf, st));
+  return 0;
+}
+
+int gemm_dispatch(cudaStream_t st, int precision, const GemmArgs& g) {
+  if (precision == 0 || !gemm_tf32_supported(g)) return gemm_fp32(st, g);
+  if (precision == 2) return gemm_tf32x3(st, g);
+  return gemm_tf32(st, g);
+}
+
+}  // namespace nlps

@@ -1,0 +1,858 @@
+// Model handle, memory layout and the training-step orchestration behind the C ABI.
+//
+// HBM layout (all fp32, every tensor 256-B aligned inside ONE flat buffer per kind):
+//   params / grads / adam_m / adam_v :  [ We | layer 0 | ... | layer L-1 | W_vocab | b_vocab ]
+//   layer l = [ Wqkv (E,3E: Wq|Wk|Wv packed column-wise) | Wo (E,E) | ln1_gamma | ln1_beta |
+//               W1 (E,F) | b1 | W2 (F,E) | b2 | ln2_gamma | ln2_beta ]
+//   W_vocab is (E, ldV) with ldV = round_up(V,4) so that every row start is 16-B aligned for TMA;
+//   pad columns are zero in params and grads and therefore stay zero under Adam/SGD.
+// Gradient buckets (for data-parallel all-reduce) are contiguous ranges of the grad buffer in the
+// order the backward pass completes them: [vocab] [layer L-1] ... [layer 0] [We].
+//
+// Activations of one forward call live in one allocation per nlps_cache (pooled by size):
+//   per layer: qkv (N,3E), ctx (N,E), lse (B,h,S), r1 (N,E), mean1/rstd1 (N), y1 (N,E),
+//              hid (N,F), r2 (N,E), mean2/rstd2 (N), y2 (N,E);  plus h0 (N,E), x_flat, first_nonpad,
+//              logits (N,ldV).  The (B,h,S,S) attention tensors and dropout masks are never stored.
+#include "common.cuh"
+#include "../../include/nlps_b200.h"
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+using namespace nlps;
+
+namespace {
+constexpr int64_t kAlign = 64;   // floats (256 B)
+
+struct LayerOff {
+  int64_t wqkv, wo, ln1g, ln1b, w1, b1, w2, b2, ln2g, ln2b, begin, end;
+};
+}  // namespace
+
+struct nlps_cache {
+  int B = 0, S = 0;
+  int64_t N = 0;
+  size_t bytes = 0;
+  char* base = nullptr;
+  int32_t* x_flat = nullptr;
+  int32_t* fnp = nullptr;
+  float* h0 = nullptr;
+  struct L { float *qkv, *ctx, *lse, *r1, *mean1, *rstd1, *y1, *hid, *r2, *mean2, *rstd2, *y2; };
+  std::vector<L> layers;
+  float* logits = nullptr;
+  float drop_p = 0.f;       // dropout probability in effect during this forward
+  uint32_t drop_step = 0;
+  bool has_logits = false;
+  bool valid = false;
+};
+
+struct nlps_model {
+  nlps_config cfg{};
+  int device = 0;
+  int V = 0, E = 0, h = 0, d = 0, F = 0, L = 0, max_len = 0;
+  int64_t ldV = 0;
+  int precision = NLPS_PREC_TF32;
+  bool training = true;
+  float dropout_p = 0.f;
+  uint64_t seed = 0;
+  uint32_t fwd_counter = 0;
+  int64_t adam_t = 0;
+  cudaStream_t stream = nullptr;
+
+  int64_t flat = 0;                 // floats per flat buffer
+  float *P = nullptr, *G = nullptr, *M = nullptr, *Vv = nullptr, *pe = nullptr;
+  int64_t off_We = 0, off_Wvocab = 0, off_bvocab = 0;
+  std::vector<LayerOff> lo;
+  std::vector<std::pair<int64_t, int64_t>> buckets;   // (first, count) in completion order
+  std::vector<cudaEvent_t> bucket_ev;
+  cudaEvent_t aux_ev = nullptr;
+
+  // backward workspace (grows with N)
+  int64_t ws_N = 0;
+  float *g0 = nullptr, *g1 = nullptr, *gdrop = nullptr, *dctx = nullptr, *dqkv = nullptr, *dhid = nullptr;
+  float *delta = nullptr, *row_loss = nullptr, *small = nullptr, *rows_tmp = nullptr;
+  int32_t* iscratch = nullptr;
+  int64_t rows_tmp_cap = 0;
+  // fixed scratch
+  float *ln_partial = nullptr, *colsum_scratch = nullptr, *sumsq_scratch = nullptr;
+  float* scalars = nullptr;          // [0]=sumsq [1]=clip scale [2]=norm [3]=loss
+  int32_t* err_flag = nullptr;
+
+  std::vector<nlps_cache*> pool;
+};
+
+namespace {
+
+inline int64_t take(int64_t& cursor, int64_t n) {
+  const int64_t at = cursor;
+  cursor = round_up(cursor + n, kAlign);
+  return at;
+}
+
+int build_layout(nlps_model* m) {
+  const int64_t E = m->E, F = m->F, V = m->V;
+  m->ldV = round_up(V, 4);
+  int64_t c = 0;
+  m->off_We = take(c, V * E);
+  m->lo.resize(m->L);
+  for (int l = 0; l < m->L; ++l) {
+    LayerOff& o = m->lo[l];
+    o.begin = c;
+    o.wqkv = take(c, E * 3 * E);
+    o.wo = take(c, E * E);
+    o.ln1g = take(c, E);
+    o.ln1b = take(c, E);
+    o.w1 = take(c, E * F);
+    o.b1 = take(c, F);
+    o.w2 = take(c, F * E);
+    o.b2 = take(c, E);
+    o.ln2g = take(c, E);
+    o.ln2b = take(c, E);
+    o.end = c;
+  }
+  const int64_t vocab_begin = c;
+  m->off_Wvocab = take(c, E * m->ldV);
+  m->off_bvocab = take(c, m->ldV);
+  m->flat = c;
+  m->buckets.clear();
+  m->buckets.push_back({vocab_begin, c - vocab_begin});
+  for (int l = m->L - 1; l >= 0; --l) m->buckets.push_back({m->lo[l].begin, m->lo[l].end - m->lo[l].begin});
+  m->buckets.push_back({m->off_We, m->lo.empty() ? vocab_begin - m->off_We : m->lo[0].begin - m->off_We});
+  return 0;
+}
+
+int ensure_workspace(nlps_model* m, int B, int S) {
+  const int64_t N = (int64_t)B * S;
+  if (N <= m->ws_N) return 0;
+  NLPS_CUDA(cudaStreamSynchronize(m->stream));
+  float** bufs[] = {&m->g0, &m->g1, &m->gdrop, &m->dctx, &m->dqkv, &m->dhid, &m->delta, &m->row_loss};
+  for (float** b : bufs) { if (*b) cudaFree(*b); *b = nullptr; }
+  if (m->iscratch) { cudaFree(m->iscratch); m->iscratch = nullptr; }
+  const int64_t E = m->E, F = m->F;
+  NLPS_CUDA(cudaMalloc(&m->g0, sizeof(float) * N * E));
+  NLPS_CUDA(cudaMalloc(&m->g1, sizeof(float) * N * E));
+  NLPS_CUDA(cudaMalloc(&m->gdrop, sizeof(float) * N * E));
+  NLPS_CUDA(cudaMalloc(&m->dctx, sizeof(float) * N * E));
+  NLPS_CUDA(cudaMalloc(&m->dqkv, sizeof(float) * N * 3 * E));
+  NLPS_CUDA(cudaMalloc(&m->dhid, sizeof(float) * N * F));
+  NLPS_CUDA(cudaMalloc(&m->delta, sizeof(float) * N * m->h));
+  NLPS_CUDA(cudaMalloc(&m->row_loss, sizeof(float) * N));
+  NLPS_CUDA(cudaMalloc(&m->iscratch, sizeof(int32_t) * embed_backward_scratch_ints(N, m->V)));
+  m->ws_N = N;
+  return 0;
+}
+
+int ensure_rows_tmp(nlps_model* m, int64_t floats) {
+  if (floats <= m->rows_tmp_cap) return 0;
+  NLPS_CUDA(cudaStreamSynchronize(m->stream));
+  if (m->rows_tmp) cudaFree(m->rows_tmp);
+  m->rows_tmp = nullptr;
+  NLPS_CUDA(cudaMalloc(&m->rows_tmp, sizeof(float) * floats));
+  m->rows_tmp_cap = floats;
+  return 0;
+}
+
+GemmArgs gemm_nn(int M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc) {
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+  return g;
+}
+
+DropoutParams drop_for(const nlps_model* m, const nlps_cache* c, int layer, int which) {
+  return make_dropout(c->drop_p, m->seed, (uint32_t)(layer * 2 + which), c->drop_step);
+}
+
+int record_bucket(nlps_model* m, int bucket) {
+  NLPS_CUDA(cudaEventRecord(m->bucket_ev[bucket], m->stream));
+  return 0;
+}
+
+// layers L-1..0 and the embedding scatter, starting from dH in m->g0 (transformer.py:360-457)
+int backward_stack(nlps_model* m, nlps_cache* c) {
+  const int E = m->E, F = m->F;
+  const int N = (int)c->N;
+  cudaStream_t st = m->stream;
+  const int prec = m->precision;
+  const bool dropping = c->drop_p > 0.f;
+  for (int l = m->L - 1; l >= 0; --l) {
+    const LayerOff& o = m->lo[l];
+    const nlps_cache::L& a = c->layers[l];
+    const float* x_in = l == 0 ? c->h0 : c->layers[l - 1].y2;
+    // LN2 backward (+ dropout backward of the FFN branch)
+    DropoutParams dpf = drop_for(m, c, l, 1);
+    NLPS_TRY(layernorm_backward(st, N, E, m->g0, a.r2, a.mean2, a.rstd2, m->P + o.ln2g, m->g1,
+                                dropping ? m->gdrop : nullptr, dropping ? &dpf : nullptr, m->G + o.ln2g,
+                                m->G + o.ln2b, m->ln_partial));
+    const float* d_f = dropping ? m->gdrop : m->g1;
+    {  // dW2 = hid^T d_f ; db2
+      GemmArgs g = gemm_nn(F, E, N, a.hid, F, d_f, E, m->G + o.w2, E);
+      g.trans_a = true;
+      NLPS_TRY(gemm_dispatch(st, prec, g));
+      NLPS_TRY(colsum(st, N, E, d_f, E, m->G + o.b2, m->colsum_scratch));
+    }
+    {  // dz = (d_f W2^T) * (hid > 0)
+      GemmArgs g = gemm_nn(N, F, E, d_f, E, m->P + o.w2, E, m->dhid, F);
+      g.trans_b = true;
+      g.gate = a.hid; g.ldg = F;
+      NLPS_TRY(gemm_dispatch(st, prec, g));
+    }
+    {  // dW1 = y1^T dz ; db1
+      GemmArgs g = gemm_nn(E, F, N, a.y1, E, m->dhid, F, m->G + o.w1, F);
+      g.trans_a = true;
+      NLPS_TRY(gemm_dispatch(st, prec, g));
+      NLPS_TRY(colsum(st, N, F, m->dhid, F, m->G + o.b1, m->colsum_scratch));
+    }
+    {  // d(y1) = dz W1^T + d_r2
+      GemmArgs g = gemm_nn(N, E, F, m->dhid, F, m->P + o.w1, F, m->g0, E);
+      g.trans_b = true;
+      g.residual = m->g1; g.ldr = E;
+      NLPS_TRY(gemm_dispatch(st, prec, g));
+    }
+    // LN1 backward (+ dropout backward of the attention branch)
+    DropoutParams dpa = drop_for(m, c, l, 0);
+    NLPS_TRY(layernorm_backward(st, N, E, m->g0, a.r1, a.mean1, a.rstd1, m->P + o.ln1g, m->g1,
+                                dropping ? m->gdrop : nullptr, dropping ? &dpa : nullptr, m->G + o.ln1g,
+                                m->G + o.ln1b, m->ln_partial));
+    const float* d_a = dropping ? m->gdrop : m->g1;
+    {  // dWo = ctx^T d_a
+      GemmArgs g = gemm_nn(E, E, N, a.ctx, E, d_a, E, m->G + o.wo, E);
+      g.trans_a = true;
+      NLPS_TRY(gemm_dispatch(st, prec, g));
+    }
+    {  // dctx = d_a Wo^T
+      GemmArgs g = gemm_nn(N, E, E, d_a, E, m->P + o.wo, E, m->dctx, E);
+      g.trans_b = true;
+      NLPS_TRY(gemm_dispatch(st, prec, g));
+    }
+    NLPS_TRY(attention_backward(st, prec, c->B, c->S, m->h, m->d, a.qkv, c->x_flat, c->fnp, a.ctx, a.lse, m->dctx,
+                                m->delta, m->dqkv));
+    {  // dWqkv = x_in^T dqkv
+      GemmArgs g = gemm_nn(E, 3 * E, N, x_in, E, m->dqkv, 3 * E, m->G + o.wqkv, 3 * E);
+      g.trans_a = true;
+      NLPS_TRY(gemm_dispatch(st, prec, g));
+    }
+    {  // dx_in = dqkv Wqkv^T + d_r1
+      GemmArgs g = gemm_nn(N, E, 3 * E, m->dqkv, 3 * E, m->P + o.wqkv, 3 * E, m->g0, E);
+      g.trans_b = true;
+      g.residual = m->g1; g.ldr = E;
+      NLPS_TRY(gemm_dispatch(st, prec, g));
+    }
+    NLPS_TRY(record_bucket(m, 1 + (m->L - 1 - l)));
+  }
+  NLPS_TRY(embed_backward(st, N, E, m->V, c->x_flat, m->g0, m->G + m->off_We, m->iscratch));
+  NLPS_TRY(record_bucket(m, m->L + 1));
+  return 0;
+}
+
+int check_cache(const nlps_model* m, const nlps_cache* c) {
+  NLPS_REQUIRE(m && c, "null model or cache");
+  NLPS_REQUIRE(c->valid, "cache does not hold a forward pass");
+  return 0;
+}
+
+}  // namespace
+
+// =========================================================================================
+//                                         C ABI
+// =========================================================================================
+extern "C" {
+
+int nlps_abi_version(void) { return NLPS_ABI_VERSION; }
+const char* nlps_last_error(void) { return get_error(); }
+
+int nlps_device_count(int* count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { n = 0; cudaGetLastError(); }
+  if (count) *count = n;
+  return 0;
+}
+
+int nlps_device_info(int device, char* name_out, size_t name_cap, int* sm_count, int* cc_major, int* cc_minor,
+                     size_t* total_mem) {
+  cudaDeviceProp p;
+  NLPS_CUDA(cudaGetDeviceProperties(&p, device));
+  if (name_out && name_cap) { strncpy(name_out, p.name, name_cap - 1); name_out[name_cap - 1] = 0; }
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (total_mem) *total_mem = p.totalGlobalMem;
+  return 0;
+}
+
+int nlps_malloc(void** d_ptr, size_t bytes) {
+  NLPS_REQUIRE(d_ptr, "nlps_malloc: null out pointer");
+  NLPS_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 4));
+  return 0;
+}
+int nlps_free(void* d_ptr) {
+  if (d_ptr) NLPS_CUDA(cudaFree(d_ptr));
+  return 0;
+}
+int nlps_memcpy_h2d(void* d, const void* h, size_t bytes, void* stream) {
+  if (bytes) NLPS_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+int nlps_memcpy_d2h(void* h, const void* d, size_t bytes, void* stream) {
+  if (bytes) NLPS_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  NLPS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+int nlps_memcpy_d2d(void* dd, const void* ds, size_t bytes, void* stream) {
+  if (bytes) NLPS_CUDA(cudaMemcpyAsync(dd, ds, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+int nlps_memset(void* d, int value, size_t bytes, void* stream) {
+  if (bytes) NLPS_CUDA(cudaMemsetAsync(d, value, bytes, (cudaStream_t)stream));
+  return 0;
+}
+int nlps_stream_sync(void* stream) {
+  NLPS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+int nlps_host_alloc_pinned(void** h_ptr, size_t bytes) {
+  NLPS_CUDA(cudaMallocHost(h_ptr, bytes ? bytes : 4));
+  return 0;
+}
+int nlps_host_free_pinned(void* h_ptr) {
+  if (h_ptr) NLPS_CUDA(cudaFreeHost(h_ptr));
+  return 0;
+}
+
+// ---- model lifetime -----------------------------------------------------------------------
+int nlps_create(const nlps_config* cfg, int device, nlps_model** out) {
+  NLPS_REQUIRE(cfg && out, "nlps_create: null argument");
+  NLPS_REQUIRE(cfg->vocab_size > 0 && cfg->embed_dim > 0 && cfg->num_heads > 0 && cfg->ff_dim > 0 &&
+                   cfg->num_layers >= 0 && cfg->max_len > 0, "nlps_create: non-positive dimension");
+  NLPS_REQUIRE(cfg->embed_dim % cfg->num_heads == 0, "embed_dim must be divisible by num_heads");
+  NLPS_REQUIRE(cfg->embed_dim / cfg->num_heads <= 128, "head_dim > 128 is not supported");
+  int ndev = 0;
+  nlps_device_count(&ndev);
+  NLPS_REQUIRE(ndev > 0, "no CUDA device: libnlps_b200 has no CPU fallback");
+  NLPS_REQUIRE(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
+  NLPS_CUDA(cudaSetDevice(device));
+  nlps_model* m = new nlps_model();
+  m->cfg = *cfg;
+  m->device = device;
+  m->V = cfg->vocab_size; m->E = cfg->embed_dim; m->h = cfg->num_heads; m->d = m->E / m->h;
+  m->F = cfg->ff_dim; m->L = cfg->num_layers; m->max_len = cfg->max_len;
+  m->precision = cfg->precision;
+  m->dropout_p = cfg->dropout_p;
+  m->seed = cfg->seed;
+  build_layout(m);
+  const size_t fb = sizeof(float) * (size_t)m->flat;
+  float** bufs[] = {&m->P, &m->G, &m->M, &m->Vv};
+  for (float** b : bufs) {
+    NLPS_CUDA(cudaMalloc(b, fb));
+    NLPS_CUDA(cudaMemset(*b, 0, fb));
+  }
+  NLPS_CUDA(cudaMalloc(&m->pe, sizeof(float) * (size_t)m->max_len * m->E));
+  {  // positional table in f64 then f32 (transformer.py:609-615)
+    std::vector<float> pe((size_t)m->max_len * m->E, 0.f);
+    for (int pos = 0; pos < m->max_len; ++pos)
+      for (int i = 0; i < m->E; i += 2) {
+        const double div = std::exp((double)i * -(std::log(10000.0) / (double)m->E));
+        pe[(size_t)pos * m->E + i] = (float)std::sin((double)pos * div);
+        if (i + 1 < m->E) pe[(size_t)pos * m->E + i + 1] = (float)std::cos((double)pos * div);
+      }
+    NLPS_CUDA(cudaMemcpy(m->pe, pe.data(), sizeof(float) * pe.size(), cudaMemcpyHostToDevice));
+  }
+  NLPS_CUDA(cudaMalloc(&m->ln_partial, sizeof(float) * layernorm_backward_scratch_floats(m->E)));
+  NLPS_CUDA(cudaMalloc(&m->colsum_scratch, sizeof(float) * colsum_scratch_floats(std::max<int64_t>(std::max(m->E, m->F), m->ldV))));
+  NLPS_CUDA(cudaMalloc(&m->sumsq_scratch, sizeof(float) * sumsq_scratch_floats()));
+  NLPS_CUDA(cudaMalloc(&m->scalars, sizeof(float) * 16));
+  NLPS_CUDA(cudaMemset(m->scalars, 0, sizeof(float) * 16));
+  NLPS_CUDA(cudaMalloc(&m->err_flag, sizeof(int32_t)));
+  NLPS_CUDA(cudaMemset(m->err_flag, 0, sizeof(int32_t)));
+  m->bucket_ev.resize(m->buckets.size());
+  for (auto& e : m->bucket_ev) NLPS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  NLPS_CUDA(cudaEventCreateWithFlags(&m->aux_ev, cudaEventDisableTiming));
+  *out = m;
+  return 0;
+}
+
+int nlps_destroy(nlps_model* m) {
+  if (!m) return 0;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  for (nlps_cache* c : m->pool) { if (c->base) cudaFree(c->base); delete c; }
+  float* bufs[] = {m->P, m->G, m->M, m->Vv, m->pe, m->g0, m->g1, m->gdrop, m->dctx, m->dqkv, m->dhid, m->delta,
+                   m->row_loss, m->rows_tmp, m->ln_partial, m->colsum_scratch, m->sumsq_scratch, m->scalars};
+  for (float* b : bufs) if (b) cudaFree(b);
+  if (m->iscratch) cudaFree(m->iscratch);
+  if (m->err_flag) cudaFree(m->err_flag);
+  for (auto& e : m->bucket_ev) cudaEventDestroy(e);
+  if (m->aux_ev) cudaEventDestroy(m->aux_ev);
+  delete m;
+  return 0;
+}
+
+int nlps_set_stream(nlps_model* m, void* s) { NLPS_REQUIRE(m, "null model"); m->stream = (cudaStream_t)s; return 0; }
+int nlps_set_precision(nlps_model* m, int p) {
+  NLPS_REQUIRE(m, "null model");
+  NLPS_REQUIRE(p >= 0 && p <= 2, "unknown precision %d", p);
+  m->precision = p;
+  return 0;
+}
+int nlps_set_training(nlps_model* m, int t) { NLPS_REQUIRE(m, "null model"); m->training = t != 0; return 0; }
+int nlps_set_dropout(nlps_model* m, float p, uint64_t seed) {
+  NLPS_REQUIRE(m, "null model");
+  NLPS_REQUIRE(p < 1.f, "dropout_p must be < 1");
+  m->dropout_p = p; m->seed = seed;
+  return 0;
+}
+int nlps_sync(nlps_model* m) {
+  NLPS_REQUIRE(m, "null model");
+  NLPS_CUDA(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int nlps_flat_size(const nlps_model* m, int64_t* n) { NLPS_REQUIRE(m && n, "null argument"); *n = m->flat; return 0; }
+int nlps_flat_ptr(nlps_model* m, int which, void** p) {
+  NLPS_REQUIRE(m && p, "null argument");
+  float* b[] = {m->P, m->G, m->M, m->Vv};
+  NLPS_REQUIRE(which >= 0 && which < 4, "unknown buffer %d", which);
+  *p = b[which];
+  return 0;
+}
+
+int nlps_param_view(nlps_model* m, int which, int id, nlps_view* v) {
+  NLPS_REQUIRE(m && v, "null argument");
+  void* basev = nullptr;
+  NLPS_TRY(nlps_flat_ptr(m, which, &basev));
+  float* base = static_cast<float*>(basev);
+  const int64_t E = m->E, F = m->F, V = m->V, L = m->L;
+  const int64_t ls = m->L > 1 ? m->lo[1].begin - m->lo[0].begin : 0;
+  auto set = [&](int64_t off, int nd, int64_t s0, int64_t s1, int64_t s2, int64_t t0, int64_t t1, int64_t t2) {
+    v->d_ptr = base + off; v->ndim = nd;
+    v->shape[0] = s0; v->shape[1] = s1; v->shape[2] = s2;
+    v->stride[0] = t0; v->stride[1] = t1; v->stride[2] = t2;
+  };
+  const LayerOff zero{};
+  const LayerOff& o = m->L > 0 ? m->lo[0] : zero;
+  switch (id) {
+    case NLPS_P_We: set(m->off_We, 2, V, E, 1, E, 1, 0); break;
+    case NLPS_P_Wq: set(o.wqkv, 3, L, E, E, ls, 3 * E, 1); break;
+    case NLPS_P_Wk: set(o.wqkv + E, 3, L, E, E, ls, 3 * E, 1); break;
+    case NLPS_P_Wv: set(o.wqkv + 2 * E, 3, L, E, E, ls, 3 * E, 1); break;
+    case NLPS_P_Wo: set(o.wo, 3, L, E, E, ls, E, 1); break;
+    case NLPS_P_W1: set(o.w1, 3, L, E, F, ls, F, 1); break;
+    case NLPS_P_W2: set(o.w2, 3, L, F, E, ls, E, 1); break;
+    case NLPS_P_b1: set(o.b1, 2, L, F, 1, ls, 1, 0); break;
+    case NLPS_P_b2: set(o.b2, 2, L, E, 1, ls, 1, 0); break;
+    case NLPS_P_W_vocab: set(m->off_Wvocab, 2, E, V, 1, m->ldV, 1, 0); break;
+    case NLPS_P_b_vocab: set(m->off_bvocab, 1, V, 1, 1, 1, 0, 0); break;
+    case NLPS_P_ln1_gamma: set(o.ln1g, 2, L, E, 1, ls, 1, 0); break;
+    case NLPS_P_ln1_beta: set(o.ln1b, 2, L, E, 1, ls, 1, 0); break;
+    case NLPS_P_ln2_gamma: set(o.ln2g, 2, L, E, 1, ls, 1, 0); break;
+    case NLPS_P_ln2_beta: set(o.ln2b, 2, L, E, 1, ls, 1, 0); break;
+    default: NLPS_REQUIRE(false, "unknown parameter id %d", id);
+  }
+  return 0;
+}
+
+int nlps_pe_ptr(nlps_model* m, void** p) { NLPS_REQUIRE(m && p, "null argument"); *p = m->pe; return 0; }
+int nlps_num_buckets(const nlps_model* m, int* n) { NLPS_REQUIRE(m && n, "null argument"); *n = (int)m->buckets.size(); return 0; }
+int nlps_bucket_range(const nlps_model* m, int b, int64_t* first, int64_t* count) {
+  NLPS_REQUIRE(m && first && count, "null argument");
+  NLPS_REQUIRE(b >= 0 && b < (int)m->buckets.size(), "bucket %d out of range", b);
+  *first = m->buckets[b].first; *count = m->buckets[b].second;
+  return 0;
+}
+int nlps_stream_wait_bucket(nlps_model* m, int b, void* other) {
+  NLPS_REQUIRE(m, "null model");
+  NLPS_REQUIRE(b >= 0 && b < (int)m->buckets.size(), "bucket %d out of range", b);
+  NLPS_CUDA(cudaStreamWaitEvent((cudaStream_t)other, m->bucket_ev[b], 0));
+  return 0;
+}
+int nlps_wait_stream(nlps_model* m, void* other) {
+  NLPS_REQUIRE(m, "null model");
+  NLPS_CUDA(cudaEventRecord(m->aux_ev, (cudaStream_t)other));
+  NLPS_CUDA(cudaStreamWaitEvent(m->stream, m->aux_ev, 0));
+  return 0;
+}
+int nlps_logits_ld(const nlps_model* m, int64_t* ld) { NLPS_REQUIRE(m && ld, "null argument"); *ld = m->ldV; return 0; }
+
+// ---- caches ------------------------------------------------------------------------------
+int nlps_cache_create(nlps_model* m, int B, int S, nlps_cache** out) {
+  NLPS_REQUIRE(m && out, "null argument");
+  NLPS_REQUIRE(B > 0 && S > 0, "forward needs a non-empty batch (B=%d, S=%d)", B, S);
+  NLPS_REQUIRE(S <= m->max_len, "sequence length %d exceeds max_len %d", S, m->max_len);
+  for (size_t i = 0; i < m->pool.size(); ++i)
+    if (m->pool[i]->B == B && m->pool[i]->S == S) {
+      *out = m->pool[i];
+      m->pool.erase(m->pool.begin() + i);
+      (*out)->valid = false;
+      return 0;
+    }
+  NLPS_CUDA(cudaSetDevice(m->device));
+  nlps_cache* c = new nlps_cache();
+  c->B = B; c->S = S; c->N = (int64_t)B * S;
+  const int64_t N = c->N, E = m->E, F = m->F;
+  int64_t cur = 0;   // in floats
+  auto carve = [&](int64_t n) { const int64_t at = cur; cur = round_up(cur + n, kAlign); return at; };
+  const int64_t o_x = carve(N), o_fnp = carve(B), o_h0 = carve(N * E);
+  struct LO { int64_t qkv, ctx, lse, r1, mean1, rstd1, y1, hid, r2, mean2, rstd2, y2; };
+  std::vector<LO> lo(m->L);
+  for (auto& q : lo) {
+    q.qkv = carve(N * 3 * E); q.ctx = carve(N * E); q.lse = carve((int64_t)B * m->h * S);
+    q.r1 = carve(N * E); q.mean1 = carve(N); q.rstd1 = carve(N); q.y1 = carve(N * E);
+    q.hid = carve(N * F); q.r2 = carve(N * E); q.mean2 = carve(N); q.rstd2 = carve(N); q.y2 = carve(N * E);
+  }
+  const int64_t o_logits = carve(N * m->ldV);
+  c->bytes = (size_t)cur * sizeof(float);
+  cudaError_t e = cudaMalloc(&c->base, c->bytes);
+  if (e != cudaSuccess) {
+    // out of memory: drop pooled caches and retry once
+    cudaGetLastError();
+    for (nlps_cache* p : m->pool) { cudaFree(p->base); delete p; }
+    m->pool.clear();
+    e = cudaMalloc(&c->base, c->bytes);
+  }
+  if (e != cudaSuccess) {
+    set_error("cache allocation of %zu bytes failed: %s", c->bytes, cudaGetErrorString(e));
+    delete c;
+    return 1;
+  }
+  float* f = reinterpret_cast<float*>(c->base);
+  c->x_flat = reinterpret_cast<int32_t*>(f + o_x);
+  c->fnp = reinterpret_cast<int32_t*>(f + o_fnp);
+  c->h0 = f + o_h0;
+  c->layers.resize(m->L);
+  for (int l = 0; l < m->L; ++l) {
+    const LO& q = lo[l];
+    c->layers[l] = {f + q.qkv, f + q.ctx, f + q.lse, f + q.r1, f + q.mean1, f + q.rstd1, f + q.y1,
+                    f + q.hid, f + q.r2, f + q.mean2, f + q.rstd2, f + q.y2};
+  }
+  c->logits = f + o_logits;
+  *out = c;
+  return 0;
+}
+
+int nlps_cache_release(nlps_model* m, nlps_cache* c) {
+  if (!c) return 0;
+  NLPS_REQUIRE(m, "null model");
+  c->valid = false;
+  if (m->pool.size() >= 6) {       // bound the pool: free the oldest entry
+    nlps_cache* old = m->pool.front();
+    m->pool.erase(m->pool.begin());
+    cudaStreamSynchronize(m->stream);
+    cudaFree(old->base);
+    delete old;
+  }
+  m->pool.push_back(c);
+  return 0;
+}
+
+int nlps_cache_hidden_ptr(nlps_cache* c, void** p) {
+  NLPS_REQUIRE(c && p, "null argument");
+  *p = c->layers.empty() ? c->h0 : c->layers.back().y2;
+  return 0;
+}
+int nlps_cache_logits_ptr(nlps_cache* c, void** p, int64_t* ld) {
+  NLPS_REQUIRE(c && p, "null argument");
+  *p = c->logits;
+  (void)ld;
+  return 0;
+}
+
+// ---- forward -------------------------------------------------------------------------------
+int nlps_forward(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, int hidden_only, float* d_out,
+                 int64_t ld_out) {
+  NLPS_REQUIRE(m && c && d_x, "nlps_forward: null argument");
+  NLPS_CUDA(cudaSetDevice(m->device));
+  const int E = m->E, F = m->F, N = (int)c->N;
+  cudaStream_t st = m->stream;
+  const int prec = m->precision;
+  c->drop_p = (m->training && m->dropout_p > 0.f) ? m->dropout_p : 0.f;
+  c->drop_step = m->fwd_counter++;
+  c->has_logits = false;
+  NLPS_TRY(embed_forward(st, c->B, c->S, E, m->V, d_x, xs, m->P + m->off_We, m->pe, c->h0, c->x_flat, m->err_flag));
+  NLPS_TRY(first_nonpad(st, c->B, c->S, c->x_flat, c->fnp));
+  const float* x_in = c->h0;
+  for (int l = 0; l < m->L; ++l) {
+    const LayerOff& o = m->lo[l];
+    nlps_cache::L& a = c->layers[l];
+    {  // Q|K|V = x Wqkv                                              (transformer.py:127-129)
+      GemmArgs g = gemm_nn(N, 3 * E, E, x_in, E, m->P + o.wqkv, 3 * E, a.qkv, 3 * E);
+      NLPS_TRY(gemm_dispatch(st, prec, g));
+    }
+    NLPS_TRY(attention_forward(st, prec, c->B, c->S, m->h, m->d, a.qkv, c->x_flat, c->fnp, a.ctx, a.lse));
+    {  // r1 = x + dropout(ctx Wo)                                    (:142-148)
+      GemmArgs g = gemm_nn(N, E, E, a.ctx, E, m->P + o.wo, E, a.r1, E);
+      g.drop = drop_for(m, c, l, 0);
+      g.residual = x_in; g.ldr = E;
+      NLPS_TRY(gemm_dispatch(st, prec, g));
+    }
+    NLPS_TRY(layernorm_forward(st, N, E, a.r1, m->P + o.ln1g, m->P + o.ln1b, a.y1, a.mean1, a.rstd1));
+    {  // hid = relu(y1 W1 + b1)                                      (:153)
+      GemmArgs g = gemm_nn(N, F, E, a.y1, E, m->P + o.w1, F, a.hid, F);
+      g.bias = m->P + o.b1; g.relu = true;
+      NLPS_TRY(gemm_dispatch(st, prec, g));
+    }
+    {  // r2 = y1 + dropout(hid W2 + b2)                              (:154-159)
+      GemmArgs g = gemm_nn(N, E, F, a.hid, F, m->P + o.w2, E, a.r2, E);
+      g.bias = m->P + o.b2;
+      g.drop = drop_for(m, c, l, 1);
+      g.residual = a.y1; g.ldr = E;
+      NLPS_TRY(gemm_dispatch(st, prec, g));
+    }
+    NLPS_TRY(layernorm_forward(st, N, E, a.r2, m->P + o.ln2g, m->P + o.ln2b, a.y2, a.mean2, a.rstd2));
+    x_in = a.y2;
+  }
+  if (!hidden_only) {  // logits = H W_vocab + b_vocab                 (:191)
+    GemmArgs g = gemm_nn(N, m->V, E, x_in, E, m->P + m->off_Wvocab, m->ldV, c->logits, m->ldV);
+    g.bias = m->P + m->off_bvocab;
+    NLPS_TRY(gemm_dispatch(st, prec, g));
+    c->has_logits = true;
+  }
+  c->valid = true;
+  if (d_out) {
+    const int64_t cols = hidden_only ? E : m->V;
+    const int64_t sld = hidden_only ? E : m->ldV;
+    const int64_t shape[2] = {N, cols}, ss[2] = {sld, 1}, ds[2] = {ld_out, 1};
+    NLPS_TRY(strided_copy(st, 4, 2, shape, hidden_only ? x_in : c->logits, ss, d_out, ds));
+  }
+  return 0;
+}
+
+int nlps_loss_dlogits(nlps_model* m, const float* d_logits, int64_t ld, const int32_t* d_y, int64_t rows,
+                      float grad_scale, float* d_loss, float* d_dlogits, int64_t ldd) {
+  NLPS_REQUIRE(m && d_logits && d_y && d_dlogits, "nlps_loss_dlogits: null argument");
+  NLPS_CUDA(cudaSetDevice(m->device));
+  NLPS_TRY(ensure_rows_tmp(m, rows));
+  float* loss = d_loss ? d_loss : m->scalars + 3;
+  return softmax_xent(m->stream, d_logits, ld, d_y, rows, m->V, grad_scale, loss, d_dlogits, ldd, m->rows_tmp);
+}
+
+int nlps_backward(nlps_model* m, nlps_cache* c, const float* d_dlogits, int64_t ldd) {
+  NLPS_TRY(check_cache(m, c));
+  NLPS_REQUIRE(d_dlogits, "nlps_backward: null dlogits");
+  NLPS_CUDA(cudaSetDevice(m->device));
+  NLPS_TRY(ensure_workspace(m, c->B, c->S));
+  const int E = m->E, N = (int)c->N;
+  cudaStream_t st = m->stream;
+  const float* h_final = m->L > 0 ? c->layers.back().y2 : c->h0;
+  {  // dW_vocab = H^T dlogits ; db_vocab                               (transformer.py:352-353)
+    GemmArgs g = gemm_nn(E, m->V, N, h_final, E, d_dlogits, ldd, m->G + m->off_Wvocab, m->ldV);
+    g.trans_a = true;
+    NLPS_TRY(gemm_dispatch(st, m->precision, g));
+    NLPS_TRY(colsum(st, N, m->V, d_dlogits, ldd, m->G + m->off_bvocab, m->colsum_scratch));
+  }
+  {  // dH = dlogits W_vocab^T                                          (:355)
+    GemmArgs g = gemm_nn(N, E, m->V, d_dlogits, ldd, m->P + m->off_Wvocab, m->ldV, m->g0, E);
+    g.trans_b = true;
+    NLPS_TRY(gemm_dispatch(st, m->precision, g));
+  }
+  NLPS_TRY(record_bucket(m, 0));
+  return backward_stack(m, c);
+}
+
+int nlps_backward_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_t, const float* d_dl, int64_t ldd) {
+  NLPS_TRY(check_cache(m, c));
+  NLPS_REQUIRE(d_t && d_dl, "nlps_backward_last_token: null argument");
+  NLPS_CUDA(cudaSetDevice(m->device));
+  NLPS_TRY(ensure_workspace(m, c->B, c->S));
+  const int E = m->E, B = c->B;
+  cudaStream_t st = m->stream;
+  const float* h_final = m->L > 0 ? c->layers.back().y2 : c->h0;
+  // H_last = H[arange(B), t]  (B,E)  and the (B,E) gradient rows
+  NLPS_TRY(ensure_rows_tmp(m, (int64_t)2 * B * E));
+  float* h_last = m->rows_tmp;
+  float* dh_rows = m->rows_tmp + (int64_t)B * E;
+  NLPS_TRY(gather_last(st, B, c->S, E, h_final, d_t, h_last));
+  {  // dW_vocab = H_last^T dlogits_last ; db_vocab                     (transformer.py:235-236)
+    GemmArgs g = gemm_nn(E, m->V, B, h_last, E, d_dl, ldd, m->G + m->off_Wvocab, m->ldV);
+    g.trans_a = true;
+    NLPS_TRY(gemm_dispatch(st, m->precision, g));
+    NLPS_TRY(colsum(st, B, m->V, d_dl, ldd, m->G + m->off_bvocab, m->colsum_scratch));
+  }
+  {  // dH[arange(B), t] = dlogits_last W_vocab^T, zero elsewhere       (:239-240)
+    GemmArgs g = gemm_nn(B, E, m->V, d_dl, ldd, m->P + m->off_Wvocab, m->ldV, dh_rows, E);
+    g.trans_b = true;
+    NLPS_TRY(gemm_dispatch(st, m->precision, g));
+    NLPS_TRY(scatter_rows(st, B, c->S, E, d_t, dh_rows, m->g0));
+  }
+  NLPS_TRY(record_bucket(m, 0));
+  return backward_stack(m, c);
+}
+
+int nlps_clip_compute(nlps_model* m, float max_norm) {
+  NLPS_REQUIRE(m, "null model");
+  NLPS_CUDA(cudaSetDevice(m->device));
+  NLPS_TRY(sumsq(m->stream, m->flat, m->G, m->scalars + 0, m->sumsq_scratch));
+  return clip_scale_from_sumsq(m->stream, m->scalars + 0, max_norm, m->scalars + 1, m->scalars + 2);
+}
+
+int nlps_clip(nlps_model* m, float max_norm, float* h_norm_out) {
+  NLPS_TRY(nlps_clip_compute(m, max_norm));
+  NLPS_TRY(scale_inplace(m->stream, m->flat, m->G, m->scalars + 1));
+  if (h_norm_out) NLPS_TRY(nlps_memcpy_d2h(h_norm_out, m->scalars + 2, sizeof(float), m->stream));
+  return 0;
+}
+
+int nlps_step(nlps_model* m, float lr, int use_clip_scale) {
+  NLPS_REQUIRE(m, "null model");
+  NLPS_CUDA(cudaSetDevice(m->device));
+  const float* cs = use_clip_scale ? m->scalars + 1 : nullptr;
+  if (!m->cfg.use_adam) return sgd_update(m->stream, m->flat, m->P, m->G, lr, cs);
+  m->adam_t += 1;
+  const double b1 = 0.9, b2 = 0.999;                       // transformer.py:29-31
+  const float bc1 = (float)(1.0 - std::pow(b1, (double)m->adam_t));
+  const float bc2 = (float)(1.0 - std::pow(b2, (double)m->adam_t));
+  return adam_update(m->stream, m->flat, m->P, m->G, m->M, m->Vv, lr, (float)b1, (float)b2, (float)(1.0 - b1),
+                     (float)(1.0 - b2), 1e-8f, bc1, bc2, cs);
+}
+
+int nlps_adam_t(nlps_model* m, int64_t* t, int set, int64_t value) {
+  NLPS_REQUIRE(m, "null model");
+  if (set) m->adam_t = value;
+  if (t) *t = m->adam_t;
+  return 0;
+}
+
+int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_y, float lr,
+                    float max_norm, float grad_scale, int defer_update, float* d_loss) {
+  NLPS_REQUIRE(m && c && d_x && d_y, "nlps_train_step: null argument");
+  NLPS_TRY(nlps_forward(m, c, d_x, xs, 0, nullptr, 0));
+  // dlogits overwrite the logits in place: 8V bytes of HBM traffic per token for the loss
+  NLPS_TRY(nlps_loss_dlogits(m, c->logits, m->ldV, d_y, c->N, grad_scale, d_loss, c->logits, m->ldV));
+  c->has_logits = false;
+  NLPS_TRY(nlps_backward(m, c, c->logits, m->ldV));
+  if (defer_update) return 0;
+  if (max_norm > 0.f) NLPS_TRY(nlps_clip_compute(m, max_norm));
+  return nlps_step(m, lr, max_norm > 0.f ? 1 : 0);
+}
+
+int nlps_launch_count(nlps_model*, int64_t* launches, int reset) {
+  const long long n = launch_count(reset != 0);
+  if (launches) *launches = n;
+  return 0;
+}
+
+// ---- stand-alone operators ------------------------------------------------------------------
+int nlps_gemm(void* stream, int precision, int M, int N, int K, const float* A, int64_t lda, int ta, const float* B,
+              int64_t ldb, int tb, float* C, int64_t ldc, const float* bias, int relu, const float* gate, int64_t ldg,
+              const float* residual, int64_t ldr, int accumulate) {
+  NLPS_REQUIRE(A && B && C, "nlps_gemm: null operand");
+  GemmArgs g = gemm_nn(M, N, K, A, lda, B, ldb, C, ldc);
+  g.trans_a = ta != 0; g.trans_b = tb != 0;
+  g.bias = bias; g.relu = relu != 0; g.gate = gate; g.ldg = ldg; g.residual = residual; g.ldr = ldr;
+  g.accumulate = accumulate != 0;
+  if (precision != NLPS_PREC_FP32)
+    NLPS_REQUIRE(gemm_tf32_supported(g), "nlps_gemm: tensor-core path needs 16-B aligned operands with ld %% 4 == 0");
+  return gemm_dispatch((cudaStream_t)stream, precision, g);
+}
+
+int nlps_attention_forward(void* stream, int precision, int B, int S, int h, int d, const float* qkv, const int32_t* x,
+                           float* ctx, float* lse) {
+  int32_t* fnp = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&fnp), sizeof(int32_t) * B, st));
+  NLPS_TRY(first_nonpad(st, B, S, x, fnp));
+  const int rc = attention_forward(st, precision, B, S, h, d, qkv, x, fnp, ctx, lse);
+  NLPS_CUDA(cudaFreeAsync(fnp, st));
+  return rc;
+}
+
+int nlps_attention_backward(void* stream, int precision, int B, int S, int h, int d, const float* qkv,
+                            const int32_t* x, const float* ctx, const float* lse, const float* dctx, float* dqkv) {
+  cudaStream_t st = (cudaStream_t)stream;
+  char* buf = nullptr;
+  const size_t nd = sizeof(float) * (size_t)B * h * S;
+  NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&buf), nd + sizeof(int32_t) * B, st));
+  float* delta = reinterpret_cast<float*>(buf);
+  int32_t* fnp = reinterpret_cast<int32_t*>(buf + nd);
+  NLPS_TRY(first_nonpad(st, B, S, x, fnp));
+  const int rc = attention_backward(st, precision, B, S, h, d, qkv, x, fnp, ctx, lse, dctx, delta, dqkv);
+  NLPS_CUDA(cudaFreeAsync(buf, st));
+  return rc;
+}
+
+int nlps_layernorm_forward(void* stream, int64_t rows, int E, const float* x, const float* gamma, const float* beta,
+                           float* y, float* mean, float* rstd) {
+  return layernorm_forward((cudaStream_t)stream, rows, E, x, gamma, beta, y, mean, rstd);
+}
+
+int nlps_layernorm_backward(void* stream, int64_t rows, int E, const float* dy, const float* x, const float* mean,
+                            const float* rstd, const float* gamma, float* dx, float* dgamma, float* dbeta) {
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = nullptr;
+  NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partial), sizeof(float) * layernorm_backward_scratch_floats(E), st));
+  const int rc = layernorm_backward(st, rows, E, dy, x, mean, rstd, gamma, dx, nullptr, nullptr, dgamma, dbeta, partial);
+  NLPS_CUDA(cudaFreeAsync(partial, st));
+  return rc;
+}
+
+int nlps_embed_forward(void* stream, int B, int S, int E, int V, const int32_t* x, int64_t xs, const float* We,
+                       const float* pe, float* out, int32_t* x_flat, int32_t* err) {
+  return embed_forward((cudaStream_t)stream, B, S, E, V, x, xs, We, pe, out, x_flat, err);
+}
+
+int nlps_embed_backward(void* stream, int64_t N, int E, int V, const int32_t* x_flat, const float* dh, float* dWe) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* scratch = nullptr;
+  NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), sizeof(int32_t) * embed_backward_scratch_ints(N, V), st));
+  const int rc = embed_backward(st, N, E, V, x_flat, dh, dWe, scratch);
+  NLPS_CUDA(cudaFreeAsync(scratch, st));
+  return rc;
+}
+
+int nlps_colsum(void* stream, int64_t rows, int cols, const float* x, int64_t ld, float* out) {
+  cudaStream_t st = (cudaStream_t)stream;
+  float* scratch = nullptr;
+  NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), sizeof(float) * colsum_scratch_floats(cols), st));
+  const int rc = colsum(st, rows, cols, x, ld, out, scratch);
+  NLPS_CUDA(cudaFreeAsync(scratch, st));
+  return rc;
+}
+
+int nlps_sumsq(void* stream, int64_t n, const float* x, float* out) {
+  cudaStream_t st = (cudaStream_t)stream;
+  float* scratch = nullptr;
+  NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), sizeof(float) * sumsq_scratch_floats(), st));
+  const int rc = sumsq(st, n, x, out, scratch);
+  NLPS_CUDA(cudaFreeAsync(scratch, st));
+  return rc;
+}
+
+int nlps_strided_copy(void* stream, int es, int nd, const int64_t* shape, const void* src, const int64_t* ss, void* dst,
+                      const int64_t* ds) {
+  return strided_copy((cudaStream_t)stream, es, nd, shape, src, ss, dst, ds);
+}
+int nlps_gather_rows(void* stream, int es, int64_t n_out, int64_t row_elems, const void* src, int64_t stride,
+                     const int32_t* index, int64_t n_src, void* dst) {
+  return gather_rows((cudaStream_t)stream, es, n_out, row_elems, src, stride, index, n_src, dst);
+}
+int nlps_gather_last(void* stream, int B, int S, int E, const float* h, const int32_t* t, float* out) {
+  return gather_last((cudaStream_t)stream, B, S, E, h, t, out);
+}
+int nlps_count_nonzero_rows(void* stream, int64_t rows, int64_t cols, const int32_t* x, int64_t stride, int32_t* out) {
+  return count_nonzero_rows((cudaStream_t)stream, rows, cols, x, stride, out);
+}
+int nlps_binary_f32(void* stream, int op, int64_t n, int64_t cols, const float* a, const float* b, float bs, int mode,
+                    float* out) {
+  return binary_f32((cudaStream_t)stream, op, n, cols, a, b, bs, mode, out);
+}
+int nlps_binary_i32(void* stream, int op, int64_t n, const int32_t* a, const int32_t* b, int32_t bs, int mode,
+                    int32_t* out) {
+  return binary_i32((cudaStream_t)stream, op, n, a, b, bs, mode, out);
+}
+int nlps_unary_f32(void* stream, int op, int64_t n, const float* a, float* out) {
+  return unary_f32((cudaStream_t)stream, op, n, a, out);
+}
+int nlps_reduce_f32(void* stream, int op, int64_t n, const float* a, float* out) {
+  return reduce_f32((cudaStream_t)stream, op, n, a, out);
+}
+int nlps_reduce_i32(void* stream, int op, int64_t n, const int32_t* a, int32_t* out) {
+  return reduce_i32((cudaStream_t)stream, op, n, a, out);
+}
+int nlps_compare_ne_i32(void* stream, int64_t n, const int32_t* a, int32_t value, int32_t* out) {
+  return compare_ne_i32((cudaStream_t)stream, n, a, value, out);
+}
+int nlps_cast_i32_f32(void* stream, int64_t n, const int32_t* a, float* out) {
+  return cast_i32_f32((cudaStream_t)stream, n, a, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,445 @@
+// Bandwidth-bound row kernels: affine LayerNorm forward/backward (function.py:90-124), softmax
+// cross-entropy with its gradient (transformer.py:515-549), column sums (bias gradients) and the
+// sum of squares behind the global-norm clip (function.py:27-38).
+//
+// All of them are one pass over HBM per tensor where the algorithm allows it: a warp owns a row,
+// keeps it in registers (float4 loads, 16 B per lane per request) and reduces with shuffles.
+// Cross-row reductions (dgamma/dbeta, bias grads, loss, norms) are two-stage with a fixed
+// partition and a fixed summation order: deterministic, no floating-point atomics.
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+
+namespace nlps {
+namespace {
+
+constexpr int kLnWarps = 8;                 // rows in flight per CTA
+constexpr int kLnPartials = kNumSMs * 2;    // CTAs of the LayerNorm backward (fixed => deterministic)
+
+// ---------------- LayerNorm forward: warp per row, row cached in registers ----------------
+// VEC = float4 per lane (E == VEC*128).  VEC == 0: generic E, three passes over L1-resident row.
+template <int VEC>
+__global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_kernel(int64_t rows, int E, const float* __restrict__ x,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float* __restrict__ y,
+                                                               float* __restrict__ mean_out,
+                                                               float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * E;
+  float* yr = y + row * E;
+  const float invE = 1.f / (float)E;
+  if constexpr (VEC > 0) {
+    float4 v[VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mu = warp_sum(s) * invE;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float var = warp_sum(q) * invE;
+    const float rstd = 1.f / sqrtf(var + kLnEps);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+      const float4 bt = *reinterpret_cast<const float4*>(beta + c);
+      float4 o;
+      o.x = (v[i].x - mu) * rstd * g.x + bt.x;
+      o.y = (v[i].y - mu) * rstd * g.y + bt.y;
+      o.z = (v[i].z - mu) * rstd * g.z + bt.z;
+      o.w = (v[i].w - mu) * rstd * g.w + bt.w;
+      *reinterpret_cast<float4*>(yr + c) = o;
+    }
+    if (lane == 0) { mean_out[row] = mu; rstd_out[row] = rstd; }
+  } else {
+    float s = 0.f;
+    for (int c = lane; c < E; c += 32) s += xr[c];
+    const float mu = warp_sum(s) * invE;
+    float q = 0.f;
+    for (int c = lane; c < E; c += 32) { const float a = xr[c] - mu; q += a * a; }
+    const float rstd = 1.f / sqrtf(warp_sum(q) * invE + kLnEps);
+    for (int c = lane; c < E; c += 32) yr[c] = (xr[c] - mu) * rstd * gamma[c] + beta[c];
+    if (lane == 0) { mean_out[row] = mu; rstd_out[row] = rstd; }
+  }
+}
+
+// ---------------- LayerNorm backward ----------------
+// dx = (dxh - mean(dxh) - xh*mean(dxh*xh)) * rstd with dxh = dy*gamma, xh = (x-mean)*rstd.
+// Each CTA walks a fixed slab of rows, accumulating dgamma/dbeta per column in registers;
+// the per-CTA partials are summed in CTA order by ln_bwd_finish_kernel.
+// If drop != nullptr a second output dx_dropped = dx * mask / keep is written (dropout backward of
+// the sub-layer branch, transformer.py:377-379 / :416-418) with the forward's Philox mask.
+template <int VEC>
+__global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(int64_t rows, int E, const float* __restrict__ dy,
+                                                               const float* __restrict__ x,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd,
+                                                               const float* __restrict__ gamma,
+                                                               float* __restrict__ dx, float* __restrict__ dx_dropped,
+                                                               const DropoutParams drop, int use_drop,
+                                                               float* __restrict__ partial) {
+  extern __shared__ float red[];     // [kLnWarps][2][E]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float invE = 1.f / (float)E;
+  const int64_t rows_per_cta = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(rows, r0 + rows_per_cta);
+  if constexpr (VEC > 0) {
+    float4 g[VEC], ag[VEC], ab[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      g[i] = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
+      ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int64_t row = r0 + warp; row < r1; row += kLnWarps) {
+      const float mu = mean[row], rs = rstd[row];
+      float4 xh[VEC], dh[VEC];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 xv = *reinterpret_cast<const float4*>(x + row * E + c);
+        const float4 dv = *reinterpret_cast<const float4*>(dy + row * E + c);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        dh[i] = make_float4(dv.x * g[i].x, dv.y * g[i].y, dv.z * g[i].z, dv.w * g[i].w);
+        s1 += (dh[i].x + dh[i].y) + (dh[i].z + dh[i].w);
+        s2 += (dh[i].x * xh[i].x + dh[i].y * xh[i].y) + (dh[i].z * xh[i].z + dh[i].w * xh[i].w);
+        ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
+        ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+      }
+      s1 = warp_sum(s1) * invE;
+      s2 = warp_sum(s2) * invE;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        float4 o;
+        o.x = (dh[i].x - s1 - xh[i].x * s2) * rs;
+        o.y = (dh[i].y - s1 - xh[i].y * s2) * rs;
+        o.z = (dh[i].z - s1 - xh[i].z * s2) * rs;
+        o.w = (dh[i].w - s1 - xh[i].w * s2) * rs;
+        *reinterpret_cast<float4*>(dx + row * E + c) = o;
+        if (use_drop) {
+          const uint64_t idx = (uint64_t)row * (uint64_t)E + (uint64_t)c;
+          const uint4 rnd = dropout_rand4(drop, idx >> 2);
+          o.x = rnd.x < drop.threshold ? o.x * drop.inv_keep : 0.f;
+          o.y = rnd.y < drop.threshold ? o.y * drop.inv_keep : 0.f;
+          o.z = rnd.z < drop.threshold ? o.z * drop.inv_keep : 0.f;
+          o.w = rnd.w < drop.threshold ? o.w * drop.inv_keep : 0.f;
+          *reinterpret_cast<float4*>(dx_dropped + row * E + c) = o;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      *reinterpret_cast<float4*>(red + (warp * 2 + 0) * E + c) = ag[i];
+      *reinterpret_cast<float4*>(red + (warp * 2 + 1) * E + c) = ab[i];
+    }
+  } else {
+    for (int c = lane; c < E; c += 32) { red[(warp * 2 + 0) * E + c] = 0.f; red[(warp * 2 + 1) * E + c] = 0.f; }
+    for (int64_t row = r0 + warp; row < r1; row += kLnWarps) {
+      const float mu = mean[row], rs = rstd[row];
+      float s1 = 0.f, s2 = 0.f;
+      for (int c = lane; c < E; c += 32) {
+        const float xh = (x[row * E + c] - mu) * rs, dv = dy[row * E + c], dh = dv * gamma[c];
+        s1 += dh; s2 += dh * xh;
+        red[(warp * 2 + 0) * E + c] += dv * xh;
+        red[(warp * 2 + 1) * E + c] += dv;
+      }
+      s1 = warp_sum(s1) * invE;
+      s2 = warp_sum(s2) * invE;
+      for (int c = lane; c < E; c += 32) {
+        const float xh = (x[row * E + c] - mu) * rs, dh = dy[row * E + c] * gamma[c];
+        const float o = (dh - s1 - xh * s2) * rs;
+        dx[row * E + c] = o;
+        if (use_drop) dx_dropped[row * E + c] = dropout_one(drop, (uint64_t)row * (uint64_t)E + (uint64_t)c, o);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * E; c += blockDim.x) {
+    const int which = c / E, col = c - which * E;
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLnWarps; ++w) acc += red[(w * 2 + which) * E + col];
+    partial[((int64_t)blockIdx.x * 2 + which) * E + col] = acc;
+  }
+}
+
+__global__ void ln_bwd_finish_kernel(int nparts, int E, const float* __restrict__ partial, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * E) return;
+  const int which = c / E, col = c - which * E;
+  float acc = 0.f;
+  for (int p = 0; p < nparts; ++p) acc += partial[((int64_t)p * 2 + which) * E + col];
+  (which == 0 ? dgamma : dbeta)[col] = acc;
+}
+
+// ---------------- softmax cross-entropy: CTA per row, online (max,sum), 2 reads + 1 write ------
+__device__ __forceinline__ void online_merge(float& m, float& s, float m2, float s2) {
+  const float mn = fmaxf(m, m2);
+  s = s * expf(m - mn) + s2 * expf(m2 - mn);
+  m = mn;
+}
+
+__global__ void __launch_bounds__(256) xent_kernel(const float* logits, int64_t ld,
+                                                   const int32_t* __restrict__ y, int V, float inv_rows_scaled,
+                                                   float* dlogits, int64_t ldd,
+                                                   float* __restrict__ row_loss, int vec_ok) {
+  __shared__ float sm_m[8], sm_s[8];
+  __shared__ float bc[2];
+  const int64_t row = blockIdx.x;
+  const float* z = logits + row * ld;
+  float* dz = dlogits + row * ldd;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float m = -INFINITY, s = 0.f;
+  if (vec_ok) {
+    for (int c = tid * 4; c < V; c += 1024) {
+      const float4 v = *reinterpret_cast<const float4*>(z + c);
+      const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+      if (mx > m) { s *= expf(m - mx); m = mx; }
+      s += (expf(v.x - m) + expf(v.y - m)) + (expf(v.z - m) + expf(v.w - m));
+    }
+  } else {
+    for (int c = tid; c < V; c += 256) {
+      const float v = z[c];
+      if (v > m) { s *= expf(m - v); m = v; }
+      s += expf(v - m);
+    }
+  }
+  // threads that saw no element keep (m=-inf, s=0): merge must not produce NaN
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    if (m2 > -INFINITY) { if (m > -INFINITY) online_merge(m, s, m2, s2); else { m = m2; s = s2; } }
+  }
+  if (lane == 0) { sm_m[warp] = m; sm_s[warp] = s; }
+  __syncthreads();
+  if (tid == 0) {
+    float M = sm_m[0], S = sm_s[0];
+    for (int w = 1; w < 8; ++w)
+      if (sm_m[w] > -INFINITY) { if (M > -INFINITY) online_merge(M, S, sm_m[w], sm_s[w]); else { M = sm_m[w]; S = sm_s[w]; } }
+    bc[0] = M; bc[1] = S;
+    const int t = y[row];
+    // loss_row = -(z_t - max - log(sum))
+    row_loss[row] = -(z[t] - M - logf(S));
+  }
+  __syncthreads();
+  const float M = bc[0], invS = 1.f / bc[1];
+  const int target = y[row];
+  if (vec_ok) {
+    for (int c = tid * 4; c < V; c += 1024) {
+      const float4 v = *reinterpret_cast<const float4*>(z + c);
+      float4 o;
+      o.x = (expf(v.x - M) * invS - (c + 0 == target ? 1.f : 0.f)) * inv_rows_scaled;
+      o.y = (expf(v.y - M) * invS - (c + 1 == target ? 1.f : 0.f)) * inv_rows_scaled;
+      o.z = (expf(v.z - M) * invS - (c + 2 == target ? 1.f : 0.f)) * inv_rows_scaled;
+      o.w = (expf(v.w - M) * invS - (c + 3 == target ? 1.f : 0.f)) * inv_rows_scaled;
+      *reinterpret_cast<float4*>(dz + c) = o;
+    }
+  } else {
+    for (int c = tid; c < V; c += 256)
+      dz[c] = (expf(z[c] - M) * invS - (c == target ? 1.f : 0.f)) * inv_rows_scaled;
+  }
+}
+
+// out[0] = scale * sum(x[0..n)) with a fixed tree: one CTA, deterministic
+__global__ void __launch_bounds__(1024) sum_to_scalar_kernel(const float* __restrict__ x, int64_t n, float scale,
+                                                             float* __restrict__ out) {
+  __shared__ float sm[32];
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) acc += x[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = sm[threadIdx.x];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = v * scale;
+  }
+}
+
+// ---------------- column sums (bias gradients): two-stage ----------------
+constexpr int kColSlabs = 64;
+__global__ void __launch_bounds__(256) colsum_partial_kernel(int64_t rows, int cols, const float* __restrict__ x,
+                                                             int64_t ld, float* __restrict__ partial) {
+  // block = 32 lanes (columns) x 8 warps (rows); grid = (ceil(cols/32), kColSlabs)
+  __shared__ float sm[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const int64_t rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+  float acc = 0.f;
+  if (col < cols)
+    for (int64_t r = r0 + warp; r < r1; r += 8) acc += x[r * ld + col];
+  sm[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && col < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][lane];
+    partial[(int64_t)blockIdx.y * cols + col] = t;
+  }
+}
+__global__ void colsum_finish_kernel(int nparts, int cols, const float* __restrict__ partial, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float acc = 0.f;
+  for (int p = 0; p < nparts; ++p) acc += partial[(int64_t)p * cols + c];
+  out[c] = acc;
+}
+
+// ---------------- sum of squares: two-stage ----------------
+constexpr int kSumsqBlocks = kNumSMs * 4;
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(int64_t n, const float* __restrict__ x,
+                                                            float* __restrict__ partial) {
+  __shared__ float sm[8];
+  float acc = 0.f;
+  const int64_t n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 v = x4[i];
+    acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += 256) acc += x[i] * x[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void sumsq_scalar_partial_kernel(int64_t n, const float* __restrict__ x, float* __restrict__ partial) {
+  // unaligned base: scalar loads
+  __shared__ float sm[8];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) acc += x[i] * x[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+int layernorm_forward(cudaStream_t st, int64_t rows, int E, const float* x, const float* gamma, const float* beta,
+                      float* y, float* mean, float* rstd) {
+  if (rows <= 0) return 0;
+  const unsigned grid = (unsigned)ceil_div(rows, kLnWarps);
+  const bool vec = (E % 128 == 0) && E <= 1024 && aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta);
+#define NLPS_LN_FWD(V) ln_fwd_kernel<V><<<grid, kLnWarps * 32, 0, st>>>(rows, E, x, gamma, beta, y, mean, rstd)
+  if (!vec) NLPS_LN_FWD(0);
+  else switch (E / 128) {
+    case 1: NLPS_LN_FWD(1); break;
+    case 2: NLPS_LN_FWD(2); break;
+    case 3: NLPS_LN_FWD(3); break;
+    case 4: NLPS_LN_FWD(4); break;
+    case 5: NLPS_LN_FWD(5); break;
+    case 6: NLPS_LN_FWD(6); break;
+    case 7: NLPS_LN_FWD(7); break;
+    default: NLPS_LN_FWD(8); break;
+  }
+#undef NLPS_LN_FWD
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t layernorm_backward_scratch_floats(int E) { return (size_t)kLnPartials * 2 * E; }
+
+int layernorm_backward(cudaStream_t st, int64_t rows, int E, const float* dy, const float* x, const float* mean,
+                       const float* rstd, const float* gamma, float* dx, float* dx_dropped,
+                       const DropoutParams* drop, float* dgamma, float* dbeta, float* partial) {
+  if (rows <= 0) return 0;
+  const int grid = (int)std::min<int64_t>(kLnPartials, ceil_div(rows, kLnWarps));
+  const int use_drop = (drop != nullptr && drop->p > 0.f && dx_dropped != nullptr) ? 1 : 0;
+  DropoutParams dp = drop ? *drop : make_dropout(0.f, 0, 0, 0);
+  const bool vec = (E % 128 == 0) && E <= 1024 && aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(gamma) &&
+                   (!use_drop || aligned16(dx_dropped));
+  const size_t smem = (size_t)kLnWarps * 2 * E * sizeof(float);
+#define NLPS_LN_BWD(V)                                                                                         \
+  {                                                                                                            \
+    static size_t smem_set = 0;                                                                                \
+    if (smem > 48 * 1024 && smem > smem_set) {                                                                 \
+      NLPS_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      smem_set = smem;                                                                                         \
+    }                                                                                                          \
+    ln_bwd_kernel<V><<<grid, kLnWarps * 32, smem, st>>>(rows, E, dy, x, mean, rstd, gamma, dx, dx_dropped, dp, \
+                                                        use_drop, partial);                                    \
+  }
+  NLPS_REQUIRE(smem <= 200 * 1024, "layernorm_backward: embed_dim %d too large", E);
+  if (!vec) NLPS_LN_BWD(0)
+  else switch (E / 128) {
+    case 1: NLPS_LN_BWD(1) break;
+    case 2: NLPS_LN_BWD(2) break;
+    case 3: NLPS_LN_BWD(3) break;
+    case 4: NLPS_LN_BWD(4) break;
+    case 5: NLPS_LN_BWD(5) break;
+    case 6: NLPS_LN_BWD(6) break;
+    case 7: NLPS_LN_BWD(7) break;
+    default: NLPS_LN_BWD(8) break;
+  }
+#undef NLPS_LN_BWD
+  NLPS_LAUNCH_CHECK();
+  ln_bwd_finish_kernel<<<(unsigned)ceil_div(2 * E, 256), 256, 0, st>>>(grid, E, partial, dgamma, dbeta);
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+
+int softmax_xent(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
+                 float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss) {
+  NLPS_REQUIRE(rows > 0 && V > 0, "softmax_xent: empty input");
+  const int vec_ok = (V % 4 == 0 && ld % 4 == 0 && ldd % 4 == 0 && aligned16(logits) && aligned16(dlogits)) ? 1 : 0;
+  const float inv = (float)((double)grad_scale / (double)rows);
+  xent_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, ld, y, V, inv, dlogits, ldd, row_loss, vec_ok);
+  NLPS_LAUNCH_CHECK();
+  sum_to_scalar_kernel<<<1, 1024, 0, st>>>(row_loss, rows, (float)(1.0 / (double)rows), loss);
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t colsum_scratch_floats(int cols) { return (size_t)kColSlabs * cols; }
+
+int colsum(cudaStream_t st, int64_t rows, int cols, const float* x, int64_t ld, float* out, float* scratch) {
+  if (cols <= 0) return 0;
+  const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(kColSlabs, ceil_div(rows, 8)));
+  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)slabs);
+  colsum_partial_kernel<<<grid, 256, 0, st>>>(rows, cols, x, ld, scratch);
+  NLPS_LAUNCH_CHECK();
+  colsum_finish_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, st>>>(slabs, cols, scratch, out);
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t sumsq_scratch_floats() { return kSumsqBlocks; }
+
+int sumsq(cudaStream_t st, int64_t n, const float* x, float* out, float* scratch) {
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(kSumsqBlocks, ceil_div(n, 1024)));
+  if (aligned16(x)) sumsq_partial_kernel<<<blocks, 256, 0, st>>>(n, x, scratch);
+  else sumsq_scalar_partial_kernel<<<blocks, 256, 0, st>>>(n, x, scratch);
+  NLPS_LAUNCH_CHECK();
+  sum_to_scalar_kernel<<<1, 1024, 0, st>>>(scratch, blocks, 1.f, out);
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace nlps

@@ -1,0 +1,17 @@
+#include "common.cuh"
+#include <atomic>
+namespace nlps {
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count(bool reset) {
+  return reset ? g_launches.exchange(0, std::memory_order_relaxed) : g_launches.load(std::memory_order_relaxed);
+}
+}  // namespace nlps

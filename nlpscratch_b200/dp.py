@@ -1,0 +1,142 @@
+"""Data-parallel training over one NVLink/NVSwitch box: one process per GPU, batch sharded by rows.
+
+The reference has no distributed code; what must hold is the identity checked on the
+oracle: a step on R equal shards with gradients averaged over ranks equals the
+reference's single step on the concatenated batch, because loss and dlogits are means over rows
+(transformer.py:542,547).  Each rank therefore scales its dlogits by n_local/n_global (1/R for
+equal shards), the flat gradient buffer is summed with NCCL, and clip + Adam then run identically
+on every rank.
+
+Overlap: the C library records one CUDA event per gradient bucket ([vocab] [layer L-1] ... [layer 0]
+[We], contiguous ranges of the flat buffer) as backward completes it; the whole step is enqueued
+asynchronously, so the all-reduces are enqueued on a side stream right behind it and run on
+NVLink while earlier layers are still in backward.  torch is used for exactly two things here:
+``torch.distributed`` (NCCL / gloo) and a CUDA side stream.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def shard_rows(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """[begin, end) of this rank's rows; the first ``n_rows % world`` ranks take one extra row."""
+    base, extra = divmod(int(n_rows), int(world))
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def shard_weight(n_rows: int, rank: int, world: int, seq_len: int = 1) -> float:
+    """Factor for this rank's dlogits so that SUM over ranks of local mean-gradients equals the
+    gradient of the mean over the global batch (ragged last batch: utils/train.py:104-110)."""
+    b, e = shard_rows(n_rows, rank, world)
+    return float((e - b) * seq_len) / float(n_rows * seq_len) if n_rows else 0.0
+
+
+def bucket_plan(sizes: Sequence[int], min_bucket: int) -> List[Tuple[int, int]]:
+    """Coalesce consecutive (first, count) gradient ranges given as sizes in completion order into
+    launches of at least ``min_bucket`` floats -- NVSwitch collectives are latency-, not link-bound,
+    so tiny buckets (biases, LayerNorm) ride with their layer."""
+    plan, start, acc = [], 0, 0
+    for i, n in enumerate(sizes):
+        acc += int(n)
+        if acc >= min_bucket or i == len(sizes) - 1:
+            plan.append((start, i + 1))
+            start, acc = i + 1, 0
+    return plan
+
+
+class _CudaBuffer:
+    """Expose a raw device range to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr: int, n_floats: int, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def allreduce_sum_host(arrays: Sequence[np.ndarray], group=None):
+    """CPU (gloo) twin of the bucketed all-reduce, used by the world_size-2 tests: sums each
+    float32 array over ranks in place."""
+    import torch
+    import torch.distributed as dist
+    works = []
+    tensors = [torch.from_numpy(a) for a in arrays]
+    for t in tensors:
+        works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    for w in works:
+        w.wait()
+
+
+class DataParallel:
+    """Wraps a ``nlpscratch_b200.Transformer`` for one rank of a data-parallel job."""
+
+    def __init__(self, model, group=None, min_bucket_floats: int = 1 << 20, overlap: bool = True):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (NCCL) before DataParallel")
+        self.model, self.group, self.overlap = model, group, overlap
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self._torch, self._dist, self._lib, self._C = torch, dist, _lib, C
+        n = C.c_int()
+        _lib.call("nlps_num_buckets", model._h, C.byref(n))
+        self.ranges = []
+        for b in range(n.value):
+            first, cnt = C.c_int64(), C.c_int64()
+            _lib.call("nlps_bucket_range", model._h, C.c_int(b), C.byref(first), C.byref(cnt))
+            self.ranges.append((first.value, cnt.value))
+        self.plan = bucket_plan([c for _, c in self.ranges], min_bucket_floats)
+        flat = model.flat("grad")
+        self._grad_t = torch.as_tensor(_CudaBuffer(flat.ptr, flat.size, model), device="cuda")
+        pflat = model.flat("param")
+        self._param_t = torch.as_tensor(_CudaBuffer(pflat.ptr, pflat.size, model), device="cuda")
+        self.comm_stream = torch.cuda.Stream()
+        self.launches = 0
+
+    def broadcast_parameters(self, src: int = 0):
+        """Identical replicas: rank ``src``'s weights everywhere (the reference has one process)."""
+        self.model.synchronize()
+        self._dist.broadcast(self._param_t, src=src, group=self.group)
+        self._torch.cuda.current_stream().synchronize()
+
+    def allreduce_gradients(self):
+        """Sum the flat gradient buffer over ranks, bucket by bucket as backward finishes them."""
+        torch, dist, C = self._torch, self._dist, self._C
+        m = self.model
+        cs = self.comm_stream
+        with torch.cuda.stream(cs):
+            for lo, hi in self.plan:
+                # the last bucket of the group is the last one to complete
+                self._lib.call("nlps_stream_wait_bucket", m._h, C.c_int(hi - 1), C.c_void_p(cs.cuda_stream))
+                # ranges of one group are adjacent only within a layer block; reduce each contiguous run
+                for first, cnt in _merge_adjacent(self.ranges[lo:hi]):
+                    dist.all_reduce(self._grad_t[first:first + cnt], op=dist.ReduceOp.SUM, group=self.group)
+                    self.launches += 1
+        # the model's stream continues (clip + Adam) only after the reductions
+        self._lib.call("nlps_wait_stream", m._h, C.c_void_p(cs.cuda_stream))
+
+    def train_step(self, x_local, y_local, learning_rate=1e-4, clip_grad_norm: Optional[float] = 1.0,
+                   weight: Optional[float] = None):
+        """One data-parallel step; returns this rank's local mean loss (device scalar)."""
+        w = (1.0 / self.world) if weight is None else float(weight)
+        loss = self.model.train_step(x_local, y_local, learning_rate, clip_grad_norm, grad_scale=w,
+                                     defer_update=True)
+        if self.world > 1:
+            self.allreduce_gradients()
+        self.model.apply_update(learning_rate, clip_grad_norm)
+        return loss
+
+
+def _merge_adjacent(ranges):
+    out = []
+    for first, cnt in sorted(ranges):
+        if out and out[-1][0] + out[-1][1] == first:
+            out[-1] = (out[-1][0], out[-1][1] + cnt)
+        else:
+            out.append((first, cnt))
+    return out
