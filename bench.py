@@ -247,6 +247,14 @@ def run_ours(args, wl):
         ms = float(t.item())
     tokens = B * S * world * args.steps
     value = tokens / (ms * 1e-3)
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
+                              "quick": True, "loss_last": last_loss}), flush=True)
+        if distributed:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- end to end: pinned host -> device copies of x,y and a loss read-back inside every step ----
     pin = []
@@ -357,6 +365,7 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "tf32x3"])
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only (for ncu launch lists)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

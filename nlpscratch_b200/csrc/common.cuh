@@ -14,6 +14,7 @@ void set_error(const char* fmt, ...);
 const char* get_error();
 void count_launch(int n = 1);         // every kernel launch of ours goes through this counter
 long long launch_count(bool reset);
+void ensure_mempool_config();
 
 #define NLPS_CUDA(expr)                                                                   \
   do {                                                                                    \

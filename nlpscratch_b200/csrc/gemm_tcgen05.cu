@@ -1,6 +1,6 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = op(A)[M,K] * op(B)[K,N]  with fused epilogue.
 //
-//   * operands are FP32 in HBM, fed by TMA (SWIZZLE_128B boxes, 128 B = 32 floats wide) into a
+//   * operands are FP32 in HBM, fed by TMA (128-byte-swizzled boxes, 128 B = 32 floats wide) into a
 //     4..6 stage shared-memory ring; `tcgen05.mma.cta_group::1.kind::tf32` (M=128, N=128|256, K=8)
 //     accumulates FP32 in TMEM; two accumulator buffers let the epilogue of tile i overlap the
 //     MMAs of tile i+1.
@@ -105,11 +105,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
-//   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor (sm_100 "version 1").
+//   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout type
+// K-major operands use SWIZZLE_128B (type 2: 16-B chunks XOR row%8).  MN-major 32-bit operands have
+// exactly one legal swizzled layout, SWIZZLE_128B_BASE32B (type 1: 32-B chunks XOR row%4, written by
+// TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); with type 2 the MMA silently yields zeros (measured,
+// tools/umma_probe.cu).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t type) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (type << 61);
 }
 
 struct KernelArgs {
@@ -274,10 +278,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t b_src = a_src + Cfg::kABytes;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // K-major: rows of 128 B, 8-row groups 1024 B apart, +32 B per K=8 step.
-            // MN-major: 32-float column slabs of (BK x 128 B) = 4096 B (LBO), +1024 B per K=8 step.
-            const uint64_t ad = A_MN ? make_desc(a_src + k * 1024, 4096, 1024) : make_desc(a_src + k * 32, 16, 1024);
-            const uint64_t bd = B_MN ? make_desc(b_src + k * 1024, 4096, 1024) : make_desc(b_src + k * 32, 16, 1024);
+            // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO), +32 B per K=8 step.
+            // MN-major: 32-float column slabs of (BK x 128 B) = 4096 B (LBO), 4-row K groups 512 B
+            //           apart (SBO), +1024 B per K=8 step.
+            const uint64_t ad = A_MN ? make_desc(a_src + k * 1024, 4096, 512, 1) : make_desc(a_src + k * 32, 16, 1024, 2);
+            const uint64_t bd = B_MN ? make_desc(b_src + k * 1024, 4096, 512, 1) : make_desc(b_src + k * 32, 16, 1024, 2);
             umma_tf32(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));        // smem slot free once these MMAs retire
@@ -389,7 +394,7 @@ EncodeTiledFn encode_fn() {
 
 // 2-D fp32 tensor map: dim0 = contiguous (inner) extent, dim1 = rows with stride ld floats.
 int make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, int64_t ld, uint32_t box_inner,
-             uint32_t box_outer, bool round_tf32) {
+             uint32_t box_outer, bool round_tf32, bool mn_major) {
   EncodeTiledFn fn = encode_fn();
   NLPS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
   cuuint64_t dims[2] = {inner, outer};
@@ -398,7 +403,8 @@ int make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer,
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NLPS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%lld)",
                (int)r, (unsigned long long)inner, (unsigned long long)outer, (long long)ld);
   return 0;
@@ -456,13 +462,14 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
   ka.ws = nullptr;
   ka.ws_ld = round_up(g.N, 4);
   if (splits > 1) {
+    ensure_mempool_config();
     NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ka.ws), (size_t)splits * g.M * ka.ws_ld * sizeof(float), st));
   }
   CUtensorMap ma, mb;
-  if (g.trans_a) NLPS_TRY(make_map(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K, g.lda, 32, BK, round_tf32));
-  else NLPS_TRY(make_map(&ma, g.A, (uint64_t)g.K, (uint64_t)g.M, g.lda, BK, BM, round_tf32));
-  if (g.trans_b) NLPS_TRY(make_map(&mb, g.B, (uint64_t)g.K, (uint64_t)g.N, g.ldb, BK, (uint32_t)BN, round_tf32));
-  else NLPS_TRY(make_map(&mb, g.B, (uint64_t)g.N, (uint64_t)g.K, g.ldb, 32, BK, round_tf32));
+  if (g.trans_a) NLPS_TRY(make_map(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K, g.lda, 32, BK, round_tf32, true));
+  else NLPS_TRY(make_map(&ma, g.A, (uint64_t)g.K, (uint64_t)g.M, g.lda, BK, BM, round_tf32, false));
+  if (g.trans_b) NLPS_TRY(make_map(&mb, g.B, (uint64_t)g.K, (uint64_t)g.N, g.ldb, BK, (uint32_t)BN, round_tf32, false));
+  else NLPS_TRY(make_map(&mb, g.B, (uint64_t)g.N, (uint64_t)g.K, g.ldb, 32, BK, round_tf32, true));
   const int items = tiles * splits;
   const int grid = std::min(items, kNumSMs);
   if (BN == 256) NLPS_TRY(launch<256>(st, ma, mb, ka, grid));
@@ -495,6 +502,7 @@ int gemm_tf32x3(cudaStream_t st, const GemmArgs& g) {
   const int64_t lda2 = round_up(a_cols, 4), ldb2 = round_up(b_cols, 4), ldt = round_up(g.N, 4);
   const size_t na = (size_t)a_rows * lda2, nb = (size_t)b_rows * ldb2, nt = (size_t)g.M * ldt;
   float* buf = nullptr;
+  ensure_mempool_config();
   NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&buf), (2 * na + 2 * nb + nt) * sizeof(float), st));
   float *ah = buf, *al = buf + na, *bh = buf + 2 * na, *bl = buf + 2 * na + nb, *tmp = buf + 2 * na + 2 * nb;
   split_hi_lo_kernel<<<(int)std::min<int64_t>(ceil_div((int64_t)na, 256), kNumSMs * 8), 256, 0, st>>>(

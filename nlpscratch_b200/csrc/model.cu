@@ -332,6 +332,7 @@ int nlps_create(const nlps_config* cfg, int device, nlps_model** out) {
   NLPS_REQUIRE(ndev > 0, "no CUDA device: libnlps_b200 has no CPU fallback");
   NLPS_REQUIRE(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
   NLPS_CUDA(cudaSetDevice(device));
+  ensure_mempool_config();
   nlps_model* m = new nlps_model();
   m->cfg = *cfg;
   m->device = device;

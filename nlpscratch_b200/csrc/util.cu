@@ -14,4 +14,18 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count(bool reset) {
   return reset ? g_launches.exchange(0, std::memory_order_relaxed) : g_launches.load(std::memory_order_relaxed);
 }
+
+// cudaMallocAsync scratch (split-K workspaces, 3xTF32 splits) must not go back to the driver at every
+// synchronisation: keep the default pool's memory cached.
+void ensure_mempool_config() {
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done[dev] = true;
+}
 }  // namespace nlps

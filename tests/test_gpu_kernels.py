@@ -129,24 +129,24 @@ def test_embedding_gather_is_bit_exact_and_scatter_matches_add_at():
     x = rng.integers(0, V, (B, S + 3)).astype(np.int32)
     x[:, 5] = 0
     xs = x[:, :S]                                           # the driver's non-contiguous slice
-    Xd = dev(x)
+    Xd, Wd, Pd = dev(x), dev(We), dev(pe)              # keep the device buffers alive across the call
     out, xf, err = DeviceArray.empty((B, S, E)), DeviceArray.empty((B * S,), np.int32), b200np.zeros((1,), np.int32)
     _lib.call("nlps_embed_forward", S0, C.c_int(B), C.c_int(S), C.c_int(E), C.c_int(V), _lib.vp(Xd.ptr),
-              C.c_int64(S + 3), _lib.vp(dev(We).ptr), _lib.vp(dev(pe).ptr), _lib.vp(out.ptr), _lib.vp(xf.ptr),
+              C.c_int64(S + 3), _lib.vp(Wd.ptr), _lib.vp(Pd.ptr), _lib.vp(out.ptr), _lib.vp(xf.ptr),
               _lib.vp(err.ptr))
     assert np.array_equal(out.get(), We[xs] + pe[:S])       # bit-exact (transformer.py:114)
     assert np.array_equal(xf.get(), xs.reshape(-1))
     assert int(err.get()[0]) == 0
     dh = rng.standard_normal((B * S, E)).astype(np.float32)
-    dWe = DeviceArray.empty((V, E))
+    dWe, DH = DeviceArray.empty((V, E)), dev(dh)
     _lib.call("nlps_embed_backward", S0, C.c_int64(B * S), C.c_int(E), C.c_int(V), _lib.vp(xf.ptr),
-              _lib.vp(dev(dh).ptr), _lib.vp(dWe.ptr))
+              _lib.vp(DH.ptr), _lib.vp(dWe.ptr))
     want = np.zeros((V, E), np.float32)
     np.add.at(want, xs.reshape(-1), dh)                     # transformer.py:453-457, same ascending order
     assert np.array_equal(dWe.get(), want)                  # deterministic AND bit-identical to NumPy
     again = DeviceArray.empty((V, E))
     _lib.call("nlps_embed_backward", S0, C.c_int64(B * S), C.c_int(E), C.c_int(V), _lib.vp(xf.ptr),
-              _lib.vp(dev(dh).ptr), _lib.vp(again.ptr))
+              _lib.vp(DH.ptr), _lib.vp(again.ptr))
     assert np.array_equal(again.get(), dWe.get())
 
 
@@ -155,9 +155,9 @@ def test_embedding_scatter_heavy_collisions():
     V, E, N = 11, 128, 5000
     x = rng.choice(V, size=N, p=np.array([0.6] + [0.04] * 10)).astype(np.int32)    # Zipf-like, PAD heavy
     dh = rng.standard_normal((N, E)).astype(np.float32)
-    dWe = DeviceArray.empty((V, E))
-    _lib.call("nlps_embed_backward", S0, C.c_int64(N), C.c_int(E), C.c_int(V), _lib.vp(dev(x).ptr),
-              _lib.vp(dev(dh).ptr), _lib.vp(dWe.ptr))
+    dWe, Xd, DH = DeviceArray.empty((V, E)), dev(x), dev(dh)
+    _lib.call("nlps_embed_backward", S0, C.c_int64(N), C.c_int(E), C.c_int(V), _lib.vp(Xd.ptr),
+              _lib.vp(DH.ptr), _lib.vp(dWe.ptr))
     want = np.zeros((V, E), np.float32)
     np.add.at(want, x, dh)
     assert np.array_equal(dWe.get(), want)
@@ -167,9 +167,9 @@ def test_out_of_range_id_is_flagged():
     V, E = 10, 8
     x = np.array([[1, 12, 3]], np.int32)
     err = b200np.zeros((1,), np.int32)
-    out = DeviceArray.empty((1, 3, E))
-    _lib.call("nlps_embed_forward", S0, C.c_int(1), C.c_int(3), C.c_int(E), C.c_int(V), _lib.vp(dev(x).ptr),
-              C.c_int64(3), _lib.vp(b200np.zeros((V, E)).ptr), _lib.vp(b200np.zeros((4, E)).ptr), _lib.vp(out.ptr),
+    out, Xd, Wd, Pd = DeviceArray.empty((1, 3, E)), dev(x), b200np.zeros((V, E)), b200np.zeros((4, E))
+    _lib.call("nlps_embed_forward", S0, C.c_int(1), C.c_int(3), C.c_int(E), C.c_int(V), _lib.vp(Xd.ptr),
+              C.c_int64(3), _lib.vp(Wd.ptr), _lib.vp(Pd.ptr), _lib.vp(out.ptr),
               None, _lib.vp(err.ptr))
     assert int(err.get()[0]) == 1
 
