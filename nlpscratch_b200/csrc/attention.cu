@@ -503,9 +503,10 @@ int first_nonpad(cudaStream_t st, int B, int S, const int32_t* x, int32_t* out) 
   return 0;
 }
 
-int attention_forward(cudaStream_t st, int /*precision*/, int B, int S, int h, int d, const float* qkv,
+int attention_forward(cudaStream_t st, int precision, int B, int S, int h, int d, const float* qkv,
                       const int32_t* x, const int32_t* fnp, float* ctx, float* lse) {
   NLPS_TRY(check_dims(B, S, h, d));
+  if (precision == 1 && d <= 64 && d % 4 == 0) return attention_forward_mma(st, B, S, h, d, qkv, x, fnp, ctx, lse);
   AttnDims p{B, S, h, d, h * d, (float)(1.0 / sqrt((double)d))};
   if (d <= 8) return fwd_launch<8>(st, p, qkv, x, fnp, ctx, lse);
   if (d <= 16) return fwd_launch<16>(st, p, qkv, x, fnp, ctx, lse);
@@ -514,7 +515,7 @@ int attention_forward(cudaStream_t st, int /*precision*/, int B, int S, int h, i
   return fwd_launch<128>(st, p, qkv, x, fnp, ctx, lse);
 }
 
-int attention_backward(cudaStream_t st, int /*precision*/, int B, int S, int h, int d, const float* qkv,
+int attention_backward(cudaStream_t st, int precision, int B, int S, int h, int d, const float* qkv,
                        const int32_t* x, const int32_t* fnp, const float* ctx, const float* lse,
                        const float* dctx, float* delta, float* dqkv) {
   NLPS_TRY(check_dims(B, S, h, d));
@@ -522,6 +523,7 @@ int attention_backward(cudaStream_t st, int /*precision*/, int B, int S, int h, 
   const int threads = std::min(1024, 32 * h);
   attn_delta_kernel<<<(unsigned)((int64_t)B * S), threads, 0, st>>>(p, ctx, dctx, delta);
   NLPS_LAUNCH_CHECK();
+  if (precision == 1 && d <= 64 && d % 4 == 0) return attention_backward_mma(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv);
   if (d <= 8) return bwd_launch<8>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
   if (d <= 16) return bwd_launch<16>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
   if (d <= 32) return bwd_launch<32>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);

@@ -158,6 +158,12 @@ int attention_backward(cudaStream_t st, int precision, int B, int S, int h, int 
                        const int32_t* x, const int32_t* first_nonpad, const float* ctx, const float* lse,
                        const float* dctx, float* delta_scratch, float* dqkv);
 int first_nonpad(cudaStream_t st, int B, int S, const int32_t* x, int32_t* out);
+// attention_mma.cu (TF32 tensor-core versions, head_dim <= 64)
+int attention_forward_mma(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
+                          const int32_t* first_nonpad, float* ctx, float* lse);
+int attention_backward_mma(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
+                           const int32_t* first_nonpad, const float* dctx, const float* lse, const float* delta,
+                           float* dqkv);
 
 // rowwise.cu
 int layernorm_forward(cudaStream_t st, int64_t rows, int E, const float* x, const float* gamma,

@@ -72,22 +72,27 @@ def _attention_case(B, S, h, d, pad_mode, seed):
 @pytest.mark.parametrize("B,S,h,d,pad", [(2, 5, 8, 8, "none"), (3, 10, 4, 8, "tail"), (3, 8, 4, 8, "lead"),
                                          (2, 77, 2, 32, "tail"), (1, 130, 2, 64, "none"), (2, 65, 1, 16, "lead"),
                                          (1, 64, 1, 128, "none"), (2, 33, 3, 20, "tail")])
-def test_attention_forward_backward(B, S, h, d, pad):
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_attention_forward_backward(B, S, h, d, pad, prec):
+    # fp32: CUDA-core kernels (attention.cu); tf32: mma.sync tensor-core kernels (attention_mma.cu,
+    # operands rounded to TF32: 10 mantissa bits => ~1e-3 relative, asserted < 4e-3 / 8e-3)
+    PREC = C.c_int(_lib.PREC[prec])
+    tol_f, tol_b = (5e-6, 1e-5) if prec == "fp32" else (4e-3, 8e-3)
     qkv, x = _attention_case(B, S, h, d, pad, seed=S * 7 + d)
     E = h * d
     QKV, X = dev(qkv), dev(x)
     ctx = DeviceArray.empty((B, S, E))
     lse = DeviceArray.empty((B, h, S))
-    _lib.call("nlps_attention_forward", S0, C.c_int(0), C.c_int(B), C.c_int(S), C.c_int(h), C.c_int(d),
+    _lib.call("nlps_attention_forward", S0, PREC, C.c_int(B), C.c_int(S), C.c_int(h), C.c_int(d),
               _lib.vp(QKV.ptr), _lib.vp(X.ptr), _lib.vp(ctx.ptr), _lib.vp(lse.ptr))
     q, k, v, p, ctx_ref = _attention_ref(qkv, x, h)
-    assert rel_err(ctx.get(), ctx_ref) < 5e-6
+    assert rel_err(ctx.get(), ctx_ref) < tol_f
     # backward against the analytic formulas of transformer.py:430-437
     rng = np.random.default_rng(1)
     dctx = rng.standard_normal((B, S, E)).astype(np.float32)
     DC = dev(dctx)
     dqkv = DeviceArray.empty((B, S, 3 * E))
-    _lib.call("nlps_attention_backward", S0, C.c_int(0), C.c_int(B), C.c_int(S), C.c_int(h), C.c_int(d),
+    _lib.call("nlps_attention_backward", S0, PREC, C.c_int(B), C.c_int(S), C.c_int(h), C.c_int(d),
               _lib.vp(QKV.ptr), _lib.vp(X.ptr), _lib.vp(ctx.ptr), _lib.vp(lse.ptr), _lib.vp(DC.ptr), _lib.vp(dqkv.ptr))
     do = dctx.astype(np.float64).reshape(B, S, h, d).transpose(0, 2, 1, 3)
     dp = np.einsum("bhid,bhjd->bhij", do, v)
@@ -96,7 +101,7 @@ def test_attention_forward_backward(B, S, h, d, pad):
     dq = np.einsum("bhij,bhjd->bhid", ds, k) / np.sqrt(d)
     dk = np.einsum("bhij,bhid->bhjd", ds, q) / np.sqrt(d)
     want = np.concatenate([t.transpose(0, 2, 1, 3).reshape(B, S, E) for t in (dq, dk, dv)], axis=-1)
-    assert rel_err(dqkv.get(), want) < 1e-5
+    assert rel_err(dqkv.get(), want) < tol_b
 
 
 @pytest.mark.parametrize("rows,E", [(1, 8), (7, 32), (33, 64), (19, 128), (50, 256), (9, 512), (5, 100)])
