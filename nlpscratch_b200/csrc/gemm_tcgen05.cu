@@ -8,14 +8,17 @@
 //     [K,rows] operand is MN-major (instruction-descriptor transpose bits), so forward (X@W),
 //     dgrad (dY@W^T) and wgrad (X^T@dY) all read the tensors where they lie -- no transposes.
 //   * warp roles: warp0 = TMA producer, warp1 = TMEM owner + single-thread MMA issuer,
-//     warps2-5 = epilogue (tcgen05.ld 32x32b -> smem transpose -> coalesced float4 stores with
-//     bias / ReLU / ReLU-gate / Philox dropout / residual fused).
-//   * persistent: grid = min(#work items, #SMs); work item = (split-K slice, n tile, m tile),
-//     m fastest so concurrent CTAs share the B tile in L2.  Small-MN/large-K products (weight
-//     gradients) are split along K into a workspace and reduced in a fixed order (deterministic).
+//     warps2-5 = epilogue (tcgen05.ld 32x32b -> swizzled smem transpose -> coalesced float4 stores
+//     with bias / ReLU / ReLU-gate / Philox dropout / residual fused).
+//   * persistent: grid = min(#work items, #SMs); work item = (split-K slice, m tile, n tile), n
+//     fastest: the ~148 tiles in flight then cover a few m-tiles times ALL n-tiles, so each
+//     activation tile is fetched from HBM once and the (small) weight matrix stays in L2.
+//     Small-MN/large-K products (weight gradients) are split along K into a workspace and reduced
+//     in a fixed order (deterministic); the split count is chosen to fill whole waves of 148 CTAs.
 #include "common.cuh"
 #include <cuda.h>
 #include <algorithm>
+#include <cstdlib>
 
 namespace nlps {
 namespace {
@@ -23,8 +26,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 32;                 // floats per k-block = one 128-byte swizzle span
 constexpr int UMMA_K = 8;              // kind::tf32: 32 bytes of K per instruction
-constexpr int kThreads = 192;
-constexpr int kEpiStageFloats = 32 * 36;   // per epilogue warp: 32 rows x (32+4) floats
+constexpr int kEpiWarps = 4;             // one warp per TMEM lane quarter (8 = two per quarter, splitting columns)
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kEpiStageFloats = 32 * 32;   // per epilogue warp: 32x32 block, 16-B chunks XOR-swizzled by row
 constexpr uint32_t kSpinLimit = 1u << 27;  // a lost barrier traps instead of hanging the GPU
 
 template <int BN>
@@ -34,7 +38,7 @@ struct TileCfg {
   static constexpr int kBBytes = BN * BK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kEpiBytes = 4 * kEpiStageFloats * 4;
+  static constexpr int kEpiBytes = kEpiWarps * kEpiStageFloats * 4;
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
 };
@@ -122,60 +126,106 @@ struct KernelArgs {
   float* ws;            // split-K workspace [splits][M][ws_ld] or null
   int64_t ws_ld;
   int vec_ok;           // float4 epilogue allowed (alignment of C / residual / gate / N)
+  int debug;            // NLPS_GEMM_DEBUG bits: 1 = skip global stores, 2 = skip the whole epilogue body
 };
 
 // ---- epilogue store of one 32x32 fp32 block, coalesced ---------------------------------
-__device__ __forceinline__ void store_block(const KernelArgs& ka, float* stg, int lane, int row0, int col0,
+// The warp re-reads the block it just transposed through smem so that one store instruction covers
+// 4 rows x 128 contiguous bytes.  The epilogue warps run alone on their SM sub-partitions, so the
+// code is organised for instruction-level parallelism: all 8 smem reads, then all global reads of a
+// fused operand, then all 8 stores, with the feature tests hoisted out of the loops.
+__device__ __forceinline__ void f4_add(float4& v, const float4& t) { v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+
+__device__ __forceinline__ void store_block(const KernelArgs& ka, const float* stg, int lane, int row0, int col0,
                                             int split) {
   const GemmArgs& g = ka.g;
+  const int r_in = lane >> 3, c4 = (lane & 7) * 4;
+  const int col = col0 + c4;
+  float4 v[8];
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + (lane >> 3);
-    const int c4 = (lane & 7) * 4;
-    const int row = row0 + r, col = col0 + c4;
-    if (row >= g.M || col >= g.N) continue;
-    float4 v = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
-    if (ka.ws != nullptr) {      // split-K partial: raw accumulators, epilogue runs in the reducer
-      float* dst = ka.ws + ((int64_t)split * g.M + row) * ka.ws_ld + col;
-      *reinterpret_cast<float4*>(dst) = v;   // ws_ld is a multiple of 4 and padded
-      continue;
-    }
-    if (ka.vec_ok && col + 3 < g.N) {
-      if (g.bias) {
-        const float4 b = *reinterpret_cast<const float4*>(g.bias + col);
-        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-      }
-      if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-      if (g.gate) {
-        const float4 t = *reinterpret_cast<const float4*>(g.gate + (int64_t)row * g.ldg + col);
-        v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f;
-        v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
-      }
-      if (g.drop.p > 0.f) {
-        const uint64_t idx = (uint64_t)row * (uint64_t)g.N + (uint64_t)col;   // multiple of 4 here
-        const uint4 rnd = dropout_rand4(g.drop, idx >> 2);
-        v.x = rnd.x < g.drop.threshold ? v.x * g.drop.inv_keep : 0.f;
-        v.y = rnd.y < g.drop.threshold ? v.y * g.drop.inv_keep : 0.f;
-        v.z = rnd.z < g.drop.threshold ? v.z * g.drop.inv_keep : 0.f;
-        v.w = rnd.w < g.drop.threshold ? v.w * g.drop.inv_keep : 0.f;
-      }
-      if (g.residual) {
-        const float4 t = *reinterpret_cast<const float4*>(g.residual + (int64_t)row * g.ldr + col);
-        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-      }
-      float4* dst = reinterpret_cast<float4*>(g.C + (int64_t)row * g.ldc + col);
-      if (g.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-      *dst = v;
-    } else {
-      const float vv[4] = {v.x, v.y, v.z, v.w};
+    const int r = it * 4 + r_in;
+    v[it] = *reinterpret_cast<const float4*>(stg + r * 32 + (((lane & 7) ^ (r & 7)) << 2));
+  }
+  if (ka.ws != nullptr) {        // split-K partial: raw accumulators, the epilogue runs in the reducer
+    if (col < g.N) {
+      float* dst = ka.ws + ((int64_t)split * g.M + row0 + r_in) * ka.ws_ld + col;   // ws_ld % 4 == 0, padded
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (col + j >= g.N) break;
-        float o = gemm_epilogue_one(g, vv[j], row, col + j);
-        float* dst = g.C + (int64_t)row * g.ldc + col + j;
-        if (g.accumulate) o += *dst;
-        *dst = o;
+      for (int it = 0; it < 8; ++it)
+        if (row0 + it * 4 + r_in < g.M) *reinterpret_cast<float4*>(dst + (int64_t)it * 4 * ka.ws_ld) = v[it];
+    }
+    return;
+  }
+  const bool interior = (row0 + 32 <= g.M) && (col0 + 32 <= g.N);
+  if (ka.vec_ok && interior) {
+    const int64_t row = row0 + r_in;
+    if (g.bias) {
+      const float4 bv = *reinterpret_cast<const float4*>(g.bias + col);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) f4_add(v[it], bv);
+    }
+    if (g.relu) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        v[it].x = fmaxf(v[it].x, 0.f); v[it].y = fmaxf(v[it].y, 0.f);
+        v[it].z = fmaxf(v[it].z, 0.f); v[it].w = fmaxf(v[it].w, 0.f);
       }
+    }
+    if (g.gate) {
+      const float* src = g.gate + row * g.ldg + col;
+      float4 t[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) t[it] = *reinterpret_cast<const float4*>(src + (int64_t)it * 4 * g.ldg);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        v[it].x = t[it].x > 0.f ? v[it].x : 0.f; v[it].y = t[it].y > 0.f ? v[it].y : 0.f;
+        v[it].z = t[it].z > 0.f ? v[it].z : 0.f; v[it].w = t[it].w > 0.f ? v[it].w : 0.f;
+      }
+    }
+    if (g.drop.p > 0.f) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const uint64_t idx = (uint64_t)(row + it * 4) * (uint64_t)g.N + (uint64_t)col;   // multiple of 4 here
+        const uint4 rnd = dropout_rand4(g.drop, idx >> 2);
+        v[it].x = rnd.x < g.drop.threshold ? v[it].x * g.drop.inv_keep : 0.f;
+        v[it].y = rnd.y < g.drop.threshold ? v[it].y * g.drop.inv_keep : 0.f;
+        v[it].z = rnd.z < g.drop.threshold ? v[it].z * g.drop.inv_keep : 0.f;
+        v[it].w = rnd.w < g.drop.threshold ? v[it].w * g.drop.inv_keep : 0.f;
+      }
+    }
+    if (g.residual) {
+      const float* src = g.residual + row * g.ldr + col;
+      float4 t[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) t[it] = *reinterpret_cast<const float4*>(src + (int64_t)it * 4 * g.ldr);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) f4_add(v[it], t[it]);
+    }
+    float* dst = g.C + row * g.ldc + col;
+    if (g.accumulate) {
+      float4 t[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) t[it] = *reinterpret_cast<const float4*>(dst + (int64_t)it * 4 * g.ldc);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) f4_add(v[it], t[it]);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(dst + (int64_t)it * 4 * g.ldc) = v[it];
+    return;
+  }
+  // edge blocks / unaligned outputs: element-wise with bounds checks
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {
+    const int row = row0 + it * 4 + r_in;
+    if (row >= g.M) continue;
+    const float vv[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (col + j >= g.N) break;
+      float o = gemm_epilogue_one(g, vv[j], row, col + j);
+      float* dst = g.C + (int64_t)row * g.ldc + col + j;
+      if (g.accumulate) o += *dst;
+      *dst = o;
     }
   }
 }
@@ -183,7 +233,7 @@ __device__ __forceinline__ void store_block(const KernelArgs& ka, float* stg, in
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const KernelArgs ka) {
+                 const __grid_constant__ KernelArgs ka) {
   using Cfg = TileCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -211,7 +261,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -228,8 +278,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int split = item / tiles;
         const int t = item - split * tiles;
-        const int m0 = (t % ka.num_m_tiles) * BM;
-        const int n0 = (t / ka.num_m_tiles) * BN;
+        const int m0 = (t / ka.num_n_tiles) * BM;
+        const int n0 = (t % ka.num_n_tiles) * BN;
         const int kb0 = split * ka.kblocks_per_split;
         const int kb1 = min(ka.kblocks_total, kb0 + ka.kblocks_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -295,41 +345,42 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;            // which share of the tile's columns (0 when kEpiWarps == 4)
+    constexpr int kChunksPerWarp = BN / 32 / (kEpiWarps / 4);
     float* stg = epi_ptr + (warp - 2) * kEpiStageFloats;
     int local = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++local) {
       const int split = item / tiles;
       const int t = item - split * tiles;
-      const int m0 = (t % ka.num_m_tiles) * BM;
-      const int n0 = (t / ka.num_m_tiles) * BN;
+      const int m0 = (t / ka.num_n_tiles) * BM;
+      const int n0 = (t % ka.num_n_tiles) * BN;
       const int buf = local & 1;
       const uint32_t aphase = (uint32_t)(local >> 1) & 1u;
       mbar_wait(tfull_bar(buf), aphase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
       const bool rows_live = (m0 + q * 32) < g.M;
+      const int c_begin = half * kChunksPerWarp;
+      int c_end = min(c_begin + kChunksPerWarp, (g.N - n0 + 31) / 32);    // live chunks only
+      if (!rows_live || (ka.debug & 2)) c_end = c_begin;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const bool live = rows_live && (n0 + c * 32) < g.N;     // warp-uniform
-        if (live) {
-          uint32_t v[32];
-          tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(stg + lane * 36 + i * 4) =
-                make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                            __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-          __syncwarp();
-          if (c == BN / 32 - 1 || (n0 + (c + 1) * 32) >= g.N) {
-            // last TMEM read of this buffer done: hand it back before the global stores
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(tempty_bar(buf));
-          }
-          store_block(ka, stg, lane, m0 + q * 32, n0 + c * 32, split);
-          __syncwarp();
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                          __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        __syncwarp();
+        if (c == c_end - 1) {      // last TMEM read of this warp's share: hand the buffer back before storing
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));
         }
+        if (!(ka.debug & 1)) store_block(ka, stg, lane, m0 + q * 32, n0 + c * 32, split);
+        __syncwarp();
       }
-      if (!rows_live) {
+      if (c_end <= c_begin) {
         tc_fence_before();
         if (lane == 0) mbar_arrive(tempty_bar(buf));
       }
@@ -439,9 +490,8 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
   if (g.M <= 0 || g.N <= 0) return 0;
   NLPS_REQUIRE(g.K > 0, "gemm_tf32: K must be positive");
   NLPS_REQUIRE(gemm_tf32_supported(g), "gemm_tf32: operands not TMA-addressable (need 16-B aligned bases, ld %% 4 == 0)");
-  // tile shape: wide tiles when there is enough work to fill the machine
-  const int64_t tiles256 = ceil_div(g.M, BM) * ceil_div(g.N, 256);
-  const int BN = (g.N > 128 && tiles256 >= 96) ? 256 : 128;
+  // tile shape: 128x256 whenever N allows it (operand bytes per flop are what limits a TF32 GEMM)
+  const int BN = g.N > 128 ? 256 : 128;
   KernelArgs ka{};
   ka.g = g;
   ka.num_m_tiles = (int)ceil_div(g.M, BM);
@@ -449,9 +499,15 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
   ka.kblocks_total = (int)ceil_div(g.K, BK);
   const int tiles = ka.num_m_tiles * ka.num_n_tiles;
   int splits = 1;
-  if (tiles < 64 && ka.kblocks_total >= 64) {            // weight-gradient shaped: few tiles, long K
-    splits = (int)std::min<int64_t>(std::min<int64_t>(ceil_div(kNumSMs, tiles), ka.kblocks_total / 16), 32);
-    if (splits < 1) splits = 1;
+  if (tiles < 2 * kNumSMs && ka.kblocks_total >= 64) {
+    // weight-gradient shaped (few tiles, long K): pick the split that minimises
+    //   waves(s) * (k-blocks per split + fixed per-tile cost)   with whole waves of 148 CTAs
+    double best = 1e30;
+    for (int s = 1; s <= 32 && ka.kblocks_total / s >= 8; ++s) {
+      const int64_t waves = ceil_div((int64_t)tiles * s, kNumSMs);
+      const double t = (double)waves * ((double)ceil_div(ka.kblocks_total, s) + 24.0);
+      if (t < best - 1e-9) { best = t; splits = s; }
+    }
   }
   ka.kblocks_per_split = (int)ceil_div(ka.kblocks_total, splits);
   splits = (int)ceil_div(ka.kblocks_total, ka.kblocks_per_split);
@@ -461,6 +517,11 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
                (!g.gate || (aligned16(g.gate) && g.ldg % 4 == 0)) && (g.drop.p <= 0.f || g.N % 4 == 0)) ? 1 : 0;
   ka.ws = nullptr;
   ka.ws_ld = round_up(g.N, 4);
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("NLPS_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    ka.debug = dbg;
+  }
   if (splits > 1) {
     ensure_mempool_config();
     NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ka.ws), (size_t)splits * g.M * ka.ws_ld * sizeof(float), st));
