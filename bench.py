@@ -114,7 +114,7 @@ def run_reference(args, wl):
         return
     from oracle.transformer_oracle import OracleTransformer, full_sequence_step
     L, E, h, F, S, B, V = wl
-    sample_B = 1 if L * E * S > 1_000_000 else min(B, 4)
+    sample_B = min(B, 4)
     try:
         from threadpoolctl import threadpool_info
         threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
@@ -161,7 +161,7 @@ def workload_config(name, wl, n_gpus, note):
 def cpu_baseline_sample(wl, seconds=20.0):
     from oracle.transformer_oracle import OracleTransformer, full_sequence_step
     L, E, h, F, S, B, V = wl
-    sample_B = 1 if L * E * S > 1_000_000 else min(B, 4)
+    sample_B = min(B, 4)
     try:
         from threadpoolctl import threadpool_info
         threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])

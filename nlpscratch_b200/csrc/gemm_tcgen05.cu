@@ -19,6 +19,8 @@
 #include <cuda.h>
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 
 namespace nlps {
 namespace {
@@ -463,6 +465,28 @@ int make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer,
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Split-K workspace: one persistent buffer per (device, stream), grown on demand.  GEMMs on one
+// stream are ordered, so consecutive calls can share it; no allocator call on the hot path.
+struct SplitWs { float* ptr = nullptr; size_t bytes = 0; };
+int splitk_workspace(cudaStream_t st, size_t bytes, float** out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, SplitWs> table;
+  int dev = 0;
+  NLPS_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  SplitWs& w = table[{dev, st}];
+  if (w.bytes < bytes) {
+    NLPS_CUDA(cudaStreamSynchronize(st));
+    if (w.ptr) NLPS_CUDA(cudaFree(w.ptr));
+    w.ptr = nullptr; w.bytes = 0;
+    const size_t want = std::max(bytes, (size_t)64 << 20);
+    NLPS_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.ptr), want));
+    w.bytes = want;
+  }
+  *out = w.ptr;
+  return 0;
+}
+
 template <int BN>
 int launch(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const KernelArgs& ka, int grid) {
   using Cfg = TileCfg<BN>;
@@ -522,10 +546,7 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
     if (dbg < 0) { const char* e = getenv("NLPS_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
     ka.debug = dbg;
   }
-  if (splits > 1) {
-    ensure_mempool_config();
-    NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ka.ws), (size_t)splits * g.M * ka.ws_ld * sizeof(float), st));
-  }
+  if (splits > 1) NLPS_TRY(splitk_workspace(st, (size_t)splits * g.M * ka.ws_ld * sizeof(float), &ka.ws));
   CUtensorMap ma, mb;
   if (g.trans_a) NLPS_TRY(make_map(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K, g.lda, 32, BK, round_tf32, true));
   else NLPS_TRY(make_map(&ma, g.A, (uint64_t)g.K, (uint64_t)g.M, g.lda, BK, BM, round_tf32, false));
@@ -540,7 +561,6 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
     const int rgrid = (int)std::min<int64_t>(ceil_div(total, 256), kNumSMs * 8);
     splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(ka);
     NLPS_LAUNCH_CHECK();
-    NLPS_CUDA(cudaFreeAsync(ka.ws, st));
   }
   return 0;
 }

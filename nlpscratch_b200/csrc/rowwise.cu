@@ -176,14 +176,23 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(int64_t rows, int
   }
 }
 
-__global__ void ln_bwd_finish_kernel(int nparts, int E, const float* __restrict__ partial, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * E) return;
-  const int which = c / E, col = c - which * E;
+// block = 32 columns x 8 partial-slices; fixed summation order (slice-major) => deterministic
+__global__ void __launch_bounds__(256) ln_bwd_finish_kernel(int nparts, int E, const float* __restrict__ partial,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float sm[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;               // column in the concatenated [dgamma | dbeta] row
   float acc = 0.f;
-  for (int p = 0; p < nparts; ++p) acc += partial[((int64_t)p * 2 + which) * E + col];
-  (which == 0 ? dgamma : dbeta)[col] = acc;
+  if (c < 2 * E)
+    for (int p = warp; p < nparts; p += 8) acc += partial[(int64_t)p * 2 * E + c];
+  sm[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < 2 * E) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][lane];
+    (c < E ? dgamma : dbeta)[c < E ? c : c - E] = t;
+  }
 }
 
 // ---------------- softmax cross-entropy: CTA per row, online (max,sum), 2 reads + 1 write ------
@@ -400,7 +409,7 @@ int layernorm_backward(cudaStream_t st, int64_t rows, int E, const float* dy, co
   }
 #undef NLPS_LN_BWD
   NLPS_LAUNCH_CHECK();
-  ln_bwd_finish_kernel<<<(unsigned)ceil_div(2 * E, 256), 256, 0, st>>>(grid, E, partial, dgamma, dbeta);
+  ln_bwd_finish_kernel<<<(unsigned)ceil_div(2 * E, 32), 256, 0, st>>>(grid, E, partial, dgamma, dbeta);
   NLPS_LAUNCH_CHECK();
   return 0;
 }
