@@ -1,0 +1,62 @@
+"""Data-parallel step over NCCL (2 ranks) == single-GPU step on the concatenated batch.
+Needs two GPUs; skipped otherwise (the single-GPU identity test in test_gpu_model.py and the gloo
+test in test_cpu_abi_and_host.py cover the arithmetic and the host logic)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["REPO"])
+from nlpscratch_b200 import Transformer
+from nlpscratch_b200.dp import DataParallel, shard_rows
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+cfg = (211, 64, 2, 128, 2, 48)
+rng = np.random.default_rng(0)
+x = rng.integers(1, 211, (8, 48)).astype(np.int32); x[3, 30:] = 0
+y = rng.integers(0, 211, (8, 48)).astype(np.int32)
+np.random.seed(11 + rank)                      # ranks start from DIFFERENT weights: broadcast must fix it
+model = Transformer(*cfg, dropout_p=0.0, precision="fp32", device=local)
+dp = DataParallel(model, min_bucket_floats=1)  # one all-reduce per bucket: exercises the bucket events
+dp.broadcast_parameters(0)
+b, e = shard_rows(8, rank, world)
+for step in range(3):
+    loss = dp.train_step(x[b:e], y[b:e], 1e-3, 0.5)
+got = model.get_params()
+losses = torch.tensor([float(loss)], device="cuda"); dist.all_reduce(losses)
+if rank == 0:
+    np.random.seed(11)
+    ref = Transformer(*cfg, dropout_p=0.0, precision="fp32", device=local)
+    for step in range(3):
+        l = ref.train_step(x, y, 1e-3, 0.5)
+    want = ref.get_params()
+    worst = max(float(np.linalg.norm(got[k].astype(np.float64) - want[k]) / max(np.linalg.norm(want[k]), 1e-30)) for k in want)
+    assert worst < 1e-5, worst
+    assert abs(float(losses.item()) / world - float(l)) < 1e-4, (losses.item() / world, float(l))
+    print("dp ok", worst, dp.launches)
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_two_rank_nccl_step_matches_single_gpu(tmp_path):
+    from nlpscratch_b200 import _lib
+    if _lib.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = os.path.join(tmp_path, "worker.py")
+    with open(script, "w") as fh:
+        fh.write(WORKER)
+    env = dict(os.environ, REPO=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29541", script]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=280)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "dp ok" in res.stdout
