@@ -16,6 +16,7 @@
 // Q|K|V arrive packed as rows of 3E floats; head j owns columns [j*d,(j+1)*d) of each block.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace nlps {
 namespace {
@@ -497,6 +498,13 @@ int check_dims(int B, int S, int h, int d) {
 
 }  // namespace
 
+// NLPS_ATTN=mma forces the mma.sync kernels where the tcgen05 ones would run (A/B measurements)
+static int attn_impl() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NLPS_ATTN"); v = (e && e[0] == 'm') ? 1 : 0; }
+  return v;
+}
+
 int first_nonpad(cudaStream_t st, int B, int S, const int32_t* x, int32_t* out) {
   first_nonpad_kernel<<<B, 128, 0, st>>>(B, S, x, out);
   NLPS_LAUNCH_CHECK();
@@ -506,6 +514,8 @@ int first_nonpad(cudaStream_t st, int B, int S, const int32_t* x, int32_t* out) 
 int attention_forward(cudaStream_t st, int precision, int B, int S, int h, int d, const float* qkv,
                       const int32_t* x, const int32_t* fnp, float* ctx, float* lse) {
   NLPS_TRY(check_dims(B, S, h, d));
+  if (precision == 1 && attention_tc_supported(d, h * d, qkv) && attn_impl() == 0)
+    return attention_forward_tc(st, B, S, h, d, qkv, x, fnp, ctx, lse);
   if (precision == 1 && d <= 64 && d % 4 == 0) return attention_forward_mma(st, B, S, h, d, qkv, x, fnp, ctx, lse);
   AttnDims p{B, S, h, d, h * d, (float)(1.0 / sqrt((double)d))};
   if (d <= 8) return fwd_launch<8>(st, p, qkv, x, fnp, ctx, lse);
@@ -523,6 +533,9 @@ int attention_backward(cudaStream_t st, int precision, int B, int S, int h, int 
   const int threads = std::min(1024, 32 * h);
   attn_delta_kernel<<<(unsigned)((int64_t)B * S), threads, 0, st>>>(p, ctx, dctx, delta);
   NLPS_LAUNCH_CHECK();
+  if (precision == 1 && attention_tc_supported(d, h * d, qkv) && attn_impl() == 0 &&
+      (reinterpret_cast<uintptr_t>(dctx) & 15u) == 0)
+    return attention_backward_tc(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv);
   if (precision == 1 && d <= 64 && d % 4 == 0) return attention_backward_mma(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv);
   if (d <= 8) return bwd_launch<8>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
   if (d <= 16) return bwd_launch<16>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);

@@ -158,6 +158,13 @@ int attention_backward(cudaStream_t st, int precision, int B, int S, int h, int 
                        const int32_t* x, const int32_t* first_nonpad, const float* ctx, const float* lse,
                        const float* dctx, float* delta_scratch, float* dqkv);
 int first_nonpad(cudaStream_t st, int B, int S, const int32_t* x, int32_t* out);
+// attention_tc.cu (tcgen05 / TMEM versions, head_dim 32 or 64)
+bool attention_tc_supported(int d, int E, const float* qkv);
+int attention_forward_tc(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
+                         const int32_t* first_nonpad, float* ctx, float* lse);
+int attention_backward_tc(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
+                          const int32_t* first_nonpad, const float* dctx, const float* lse, const float* delta,
+                          float* dqkv);
 // attention_mma.cu (TF32 tensor-core versions, head_dim <= 64)
 int attention_forward_mma(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
                           const int32_t* first_nonpad, float* ctx, float* lse);
