@@ -69,9 +69,11 @@ __global__ void __launch_bounds__(kThreads, 2) attn_fwd_tc(const __grid_constant
   const uint32_t q_s = base, k_s = q_s + Cfg::kQBytes, v_s = k_s + Cfg::kKBytes, p_s = v_s + Cfg::kVBytes;
   uint8_t* p_ptr = base_ptr + Cfg::kQBytes + Cfg::kKBytes + Cfg::kVBytes;
   const uint32_t bar = p_s + Cfg::kPBytes;
-  const uint32_t q_full = bar, kv_full = bar + 8, kv_empty = bar + 16, s_full = bar + 24, p_full = bar + 32,
-                 o_full = bar + 40, o_read = bar + 48, tmem_slot = bar + 56;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(p_ptr + Cfg::kPBytes + 56);
+  // K and V have separate full/empty barriers: K(j+1) streams in as soon as S(j) has been issued (during
+  // softmax j and P V j), V(j+1) as soon as P V j retires -- TMA latency hidden without a second buffer.
+  const uint32_t q_full = bar, k_full = bar + 8, k_empty = bar + 16, s_full = bar + 24, p_full = bar + 32,
+                 o_full = bar + 40, o_read = bar + 48, v_full = bar + 56, v_empty = bar + 64, tmem_slot = bar + 72;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(p_ptr + Cfg::kPBytes + 72);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * BQ;
@@ -85,8 +87,8 @@ __global__ void __launch_bounds__(kThreads, 2) attn_fwd_tc(const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
-    mbar_init(q_full, 1); mbar_init(kv_full, 1); mbar_init(kv_empty, 1); mbar_init(s_full, 1);
-    mbar_init(p_full, 128); mbar_init(o_full, 1); mbar_init(o_read, 128);
+    mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(s_full, 1);
+    mbar_init(p_full, 128); mbar_init(o_full, 1); mbar_init(o_read, 128); mbar_init(v_full, 1); mbar_init(v_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
@@ -104,14 +106,17 @@ __global__ void __launch_bounds__(kThreads, 2) attn_fwd_tc(const __grid_constant
       for (int a = 0; a < Cfg::kAtoms; ++a)
         tma_load_2d(q_s + a * (BQ * 128), &map_q, q_full, head * D + a * 32, row_base + q0);
       for (int kb = 0; kb < n_kv; ++kb) {
-        mbar_wait(kv_empty, (uint32_t)(kb & 1) ^ 1u);
-        mbar_expect_tx(kv_full, Cfg::kKBytes + Cfg::kVBytes);
         const int krow = row_base + kb * BKV;
+        mbar_wait(k_empty, (uint32_t)(kb & 1) ^ 1u);
+        mbar_expect_tx(k_full, Cfg::kKBytes);
 #pragma unroll
-        for (int a = 0; a < Cfg::kAtoms; ++a) {
-          tma_load_2d(k_s + a * (BKV * 128), &map_k, kv_full, p.E + head * D + a * 32, krow);
-          tma_load_2d(v_s + a * (BKV * 128), &map_v, kv_full, 2 * p.E + head * D + a * 32, krow);
-        }
+        for (int a = 0; a < Cfg::kAtoms; ++a)
+          tma_load_2d(k_s + a * (BKV * 128), &map_k, k_full, p.E + head * D + a * 32, krow);
+        mbar_wait(v_empty, (uint32_t)(kb & 1) ^ 1u);
+        mbar_expect_tx(v_full, Cfg::kVBytes);
+#pragma unroll
+        for (int a = 0; a < Cfg::kAtoms; ++a)
+          tma_load_2d(v_s + a * (BKV * 128), &map_v, v_full, 2 * p.E + head * D + a * 32, krow);
       }
     }
     __syncwarp();
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_fwd_tc(const __grid_constant
       mbar_wait(q_full, 0);
       for (int kb = 0; kb < n_kv; ++kb) {
         const uint32_t ph = (uint32_t)(kb & 1);
-        mbar_wait(kv_full, ph);
+        mbar_wait(k_full, ph);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < D / 8; ++kk) {
@@ -132,6 +137,8 @@ __global__ void __launch_bounds__(kThreads, 2) attn_fwd_tc(const __grid_constant
           umma_tf32(tmem_s, ad, bd, idesc_s, kk > 0 ? 1u : 0u);
         }
         umma_commit(s_full);
+        umma_commit(k_empty);                          // K tile free once S retires
+        mbar_wait(v_full, ph);
         mbar_wait(p_full, ph);                         // P written (and S consumed) by all 128 rows
         if (kb > 0) mbar_wait(o_read, (uint32_t)((kb - 1) & 1));   // previous O block folded into registers
         tc_fence_after();
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_fwd_tc(const __grid_constant
           umma_tf32(tmem_o, ad, bd, idesc_o, kk > 0 ? 1u : 0u);
         }
         umma_commit(o_full);
-        umma_commit(kv_empty);
+        umma_commit(v_empty);
       }
     }
     __syncwarp();
@@ -334,9 +341,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_tc(const __grid_con
   uint8_t* dst_ptr = pt_ptr + Cfg::kPBytes;
   const uint32_t bar = dst_s + Cfg::kPBytes;
   uint8_t* bar_ptr = dst_ptr + Cfg::kPBytes;
+  // two operand groups with their own barriers: the K-major copies (first pair of products) are refilled
+  // while the threads work on P^T/dS^T, the MN-major copies (second pair) while the next S^T is formed
   const uint32_t res_full = bar, blk_full = bar + 8, blk_empty = bar + 16, sdp_full = bar + 24, pds_full = bar + 32,
-                 acc_full = bar + 40, tmem_slot = bar + 48;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(bar_ptr + 48);
+                 acc_full = bar + 40, mn_full = bar + 48, mn_empty = bar + 56, tmem_slot = bar + 64;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(bar_ptr + 64);
   float* lse_s = reinterpret_cast<float*>(bar_ptr + 128);
   float* delta_s = lse_s + 64;
 
@@ -352,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_tc(const __grid_con
 
   if (warp == 0 && lane == 0) {
     mbar_init(res_full, 1); mbar_init(blk_full, 1); mbar_init(blk_empty, 1); mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 128); mbar_init(acc_full, 1);
+    mbar_init(pds_full, 128); mbar_init(acc_full, 1); mbar_init(mn_full, 1); mbar_init(mn_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
@@ -372,15 +381,20 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_tc(const __grid_con
         tma_load_2d(v_s + a * (128 * 128), &map_res, res_full, 2 * p.E + head * D + a * 32, row_base + k0);
       }
       for (int it = 0; it < n_it; ++it) {
-        mbar_wait(blk_empty, (uint32_t)(it & 1) ^ 1u);
-        mbar_expect_tx(blk_full, 4 * Cfg::kBlkBytes);
         const int qrow = row_base + block_of(it) * 64;
+        mbar_wait(blk_empty, (uint32_t)(it & 1) ^ 1u);
+        mbar_expect_tx(blk_full, 2 * Cfg::kBlkBytes);
 #pragma unroll
         for (int a = 0; a < Cfg::kAtoms; ++a) {
           tma_load_2d(qk_s + a * (64 * 128), &map_qk, blk_full, head * D + a * 32, qrow);
-          tma_load_2d(qmn_s + a * (64 * 128), &map_qmn, blk_full, head * D + a * 32, qrow);
           tma_load_2d(dok_s + a * (64 * 128), &map_dok, blk_full, head * D + a * 32, qrow);
-          tma_load_2d(domn_s + a * (64 * 128), &map_domn, blk_full, head * D + a * 32, qrow);
+        }
+        mbar_wait(mn_empty, (uint32_t)(it & 1) ^ 1u);
+        mbar_expect_tx(mn_full, 2 * Cfg::kBlkBytes);
+#pragma unroll
+        for (int a = 0; a < Cfg::kAtoms; ++a) {
+          tma_load_2d(qmn_s + a * (64 * 128), &map_qmn, mn_full, head * D + a * 32, qrow);
+          tma_load_2d(domn_s + a * (64 * 128), &map_domn, mn_full, head * D + a * 32, qrow);
         }
       }
     }
@@ -401,6 +415,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_tc(const __grid_con
           umma_tf32(t_dpt, make_desc(v_s + ao, 16, 1024, 2), make_desc(dok_s + bo, 16, 1024, 2), idesc_t, kk > 0 ? 1u : 0u);
         }
         umma_commit(sdp_full);
+        umma_commit(blk_empty);                    // K-major copies free once S^T / dP^T retire
+        mbar_wait(mn_full, ph);
         mbar_wait(pds_full, ph);
         tc_fence_after();
 #pragma unroll
@@ -410,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_tc(const __grid_con
           umma_tf32(t_dv, make_desc(pt_s + ao, 16, 1024, 2), make_desc(domn_s + kk * 1024, 64 * 128, 512, 1), idesc_a, acc);
           umma_tf32(t_dk, make_desc(dst_s + ao, 16, 1024, 2), make_desc(qmn_s + kk * 1024, 64 * 128, 512, 1), idesc_a, acc);
         }
-        umma_commit(blk_empty);
+        umma_commit(mn_empty);
       }
       umma_commit(acc_full);
     }
@@ -513,8 +529,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_tc(const __grid_const
   const uint32_t bar = ds_s + Cfg::kPBytes;
   uint8_t* bar_ptr = ds_ptr + Cfg::kPBytes;
   const uint32_t res_full = bar, blk_full = bar + 8, blk_empty = bar + 16, sdp_full = bar + 24, ds_full = bar + 32,
-                 acc_full = bar + 40, tmem_slot = bar + 48;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(bar_ptr + 48);
+                 acc_full = bar + 40, mn_full = bar + 48, mn_empty = bar + 56, tmem_slot = bar + 64;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(bar_ptr + 64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * BQ;
@@ -526,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_tc(const __grid_const
 
   if (warp == 0 && lane == 0) {
     mbar_init(res_full, 1); mbar_init(blk_full, 1); mbar_init(blk_empty, 1); mbar_init(sdp_full, 1);
-    mbar_init(ds_full, 128); mbar_init(acc_full, 1);
+    mbar_init(ds_full, 128); mbar_init(acc_full, 1); mbar_init(mn_full, 1); mbar_init(mn_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
@@ -546,15 +562,19 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_tc(const __grid_const
         tma_load_2d(do_s + a * (128 * 128), &map_dores, res_full, head * D + a * 32, row_base + q0);
       }
       for (int kb = 0; kb < n_kv; ++kb) {
-        mbar_wait(blk_empty, (uint32_t)(kb & 1) ^ 1u);
-        mbar_expect_tx(blk_full, 3 * Cfg::kBlkBytes);
         const int krow = row_base + kb * BKV;
+        mbar_wait(blk_empty, (uint32_t)(kb & 1) ^ 1u);
+        mbar_expect_tx(blk_full, 2 * Cfg::kBlkBytes);
 #pragma unroll
         for (int a = 0; a < Cfg::kAtoms; ++a) {
           tma_load_2d(kk_s + a * (64 * 128), &map_kk, blk_full, p.E + head * D + a * 32, krow);
           tma_load_2d(vk_s + a * (64 * 128), &map_kk, blk_full, 2 * p.E + head * D + a * 32, krow);
-          tma_load_2d(kmn_s + a * (64 * 128), &map_kmn, blk_full, p.E + head * D + a * 32, krow);
         }
+        mbar_wait(mn_empty, (uint32_t)(kb & 1) ^ 1u);
+        mbar_expect_tx(mn_full, Cfg::kBlkBytes);
+#pragma unroll
+        for (int a = 0; a < Cfg::kAtoms; ++a)
+          tma_load_2d(kmn_s + a * (64 * 128), &map_kmn, mn_full, p.E + head * D + a * 32, krow);
       }
     }
     __syncwarp();
@@ -574,6 +594,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_tc(const __grid_const
           umma_tf32(t_dp, make_desc(do_s + ao, 16, 1024, 2), make_desc(vk_s + bo, 16, 1024, 2), idesc_t, kk > 0 ? 1u : 0u);
         }
         umma_commit(sdp_full);
+        umma_commit(blk_empty);                    // K-major K/V copies free once S / dP retire
+        mbar_wait(mn_full, ph);
         mbar_wait(ds_full, ph);
         tc_fence_after();
 #pragma unroll
@@ -582,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_tc(const __grid_const
           umma_tf32(t_dq, make_desc(ds_s + ao, 16, 1024, 2), make_desc(kmn_s + kk * 1024, 64 * 128, 512, 1), idesc_a,
                     (kb > 0 || kk > 0) ? 1u : 0u);
         }
-        umma_commit(blk_empty);
+        umma_commit(mn_empty);
       }
       umma_commit(acc_full);
     }

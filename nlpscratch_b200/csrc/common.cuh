@@ -85,21 +85,33 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c
 struct DropoutParams {
   float p;             // drop probability; <=0 disables
   float inv_keep;      // 1/(1-p)
-  uint32_t threshold;  // keep iff rand32 < threshold  (threshold = keep * 2^32, saturated)
+  uint32_t threshold;  // keep iff rand16 < threshold  (threshold = round(keep * 2^16))
   uint32_t seed_lo, seed_hi;
   uint32_t stream;     // (layer*2 + which)
   uint32_t step;       // forward-call counter so that every step draws fresh masks
 };
 
-// keep-mask of 4 consecutive elements idx4*4 .. idx4*4+3  (inverted dropout, transformer.py:102-108)
-__device__ __forceinline__ uint4 dropout_rand4(const DropoutParams& d, uint64_t idx4) {
-  return philox4x32((uint32_t)idx4, (uint32_t)(idx4 >> 32), d.stream, d.step, d.seed_lo, d.seed_hi);
+// One Philox4x32-10 call yields the keep decisions of 8 consecutive elements (16 random bits each):
+// element idx uses call idx>>3, 16-bit field idx&7.  Inverted dropout, transformer.py:102-108.
+__device__ __forceinline__ uint4 dropout_rand8(const DropoutParams& d, uint64_t idx8) {
+  return philox4x32((uint32_t)idx8, (uint32_t)(idx8 >> 32), d.stream, d.step, d.seed_lo, d.seed_hi);
+}
+__device__ __forceinline__ bool dropout_keep(const DropoutParams& d, const uint4& r, int field) {
+  const uint32_t w = (field >> 1) == 0 ? r.x : (field >> 1) == 1 ? r.y : (field >> 1) == 2 ? r.z : r.w;
+  return ((w >> ((field & 1) * 16)) & 0xFFFFu) < d.threshold;
 }
 __device__ __forceinline__ float dropout_one(const DropoutParams& d, uint64_t idx, float v) {
-  const uint4 r = dropout_rand4(d, idx >> 2);
-  const uint32_t lane = (uint32_t)(idx & 3);
-  const uint32_t rv = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
-  return rv < d.threshold ? v * d.inv_keep : 0.f;
+  const uint4 r = dropout_rand8(d, idx >> 3);
+  return dropout_keep(d, r, (int)(idx & 7)) ? v * d.inv_keep : 0.f;
+}
+// 4 consecutive elements starting at idx (idx % 4 == 0)
+__device__ __forceinline__ void dropout_four(const DropoutParams& d, uint64_t idx, float4& v) {
+  const uint4 r = dropout_rand8(d, idx >> 3);
+  const uint32_t w0 = (idx & 4) ? r.z : r.x, w1 = (idx & 4) ? r.w : r.y;
+  v.x = (w0 & 0xFFFFu) < d.threshold ? v.x * d.inv_keep : 0.f;
+  v.y = (w0 >> 16) < d.threshold ? v.y * d.inv_keep : 0.f;
+  v.z = (w1 & 0xFFFFu) < d.threshold ? v.z * d.inv_keep : 0.f;
+  v.w = (w1 >> 16) < d.threshold ? v.w * d.inv_keep : 0.f;
 }
 
 inline DropoutParams make_dropout(float p, uint64_t seed, uint32_t stream, uint32_t step) {
@@ -108,11 +120,11 @@ inline DropoutParams make_dropout(float p, uint64_t seed, uint32_t stream, uint3
   if (p > 0.f) {
     const double keep = 1.0 - (double)p;
     d.inv_keep = (float)(1.0 / keep);
-    double t = keep * 4294967296.0;
-    d.threshold = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    const double t = keep * 65536.0 + 0.5;
+    d.threshold = t >= 65536.0 ? 65536u : (uint32_t)t;
   } else {
     d.inv_keep = 1.f;
-    d.threshold = 0xFFFFFFFFu;
+    d.threshold = 65536u;
   }
   d.seed_lo = (uint32_t)seed;
   d.seed_hi = (uint32_t)(seed >> 32);
@@ -130,7 +142,10 @@ struct GemmArgs {
   const float* bias = nullptr;      // [N], added first
   bool relu = false;                // then max(0,.)
   const float* gate = nullptr; int64_t ldg = 0;       // then *= (gate > 0)       (ReLU backward)
-  DropoutParams drop = {0.f, 1.f, 0xFFFFFFFFu, 0, 0, 0, 0};   // then inverted dropout
+  // bit-packed ReLU mask, one uint32 per (row, 32 columns): written by the ReLU GEMM, read by its
+  // backward instead of the float gate (tensor-core path only; needs N % 32 == 0)
+  uint32_t* relu_bits_out = nullptr; const uint32_t* gate_bits = nullptr; int64_t ld_bits = 0;
+  DropoutParams drop = {0.f, 1.f, 65536u, 0, 0, 0, 0};        // then inverted dropout
   const float* residual = nullptr; int64_t ldr = 0;   // then += residual
   bool accumulate = false;          // finally C += result instead of C = result
 };

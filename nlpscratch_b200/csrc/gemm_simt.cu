@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs g) {
 
 int gemm_fp32(cudaStream_t st, const GemmArgs& g) {
   if (g.M <= 0 || g.N <= 0) return 0;
+  NLPS_REQUIRE(!g.relu_bits_out && !g.gate_bits, "gemm_fp32: bit-packed ReLU masks are a tensor-core-path feature");
   dim3 grid((unsigned)ceil_div(g.M, TM), (unsigned)ceil_div(g.N, TN));
   NLPS_REQUIRE(grid.y <= 65535u, "gemm_fp32: N=%d too large for this grid", g.N);
   if (g.trans_a && g.trans_b) gemm_simt_kernel<true, true><<<grid, 256, 0, st>>>(g);

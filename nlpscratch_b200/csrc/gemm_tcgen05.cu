@@ -83,18 +83,6 @@ __device__ __forceinline__ void store_block(const KernelArgs& ka, const float* s
   const bool interior = (row0 + 32 <= g.M) && (col0 + 32 <= g.N);
   if (ka.vec_ok && interior) {
     const int64_t row = row0 + r_in;
-    if (g.bias) {
-      const float4 bv = *reinterpret_cast<const float4*>(g.bias + col);
-#pragma unroll
-      for (int it = 0; it < 8; ++it) f4_add(v[it], bv);
-    }
-    if (g.relu) {
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        v[it].x = fmaxf(v[it].x, 0.f); v[it].y = fmaxf(v[it].y, 0.f);
-        v[it].z = fmaxf(v[it].z, 0.f); v[it].w = fmaxf(v[it].w, 0.f);
-      }
-    }
     if (g.gate) {
       const float* src = g.gate + row * g.ldg + col;
       float4 t[8];
@@ -104,17 +92,6 @@ __device__ __forceinline__ void store_block(const KernelArgs& ka, const float* s
       for (int it = 0; it < 8; ++it) {
         v[it].x = t[it].x > 0.f ? v[it].x : 0.f; v[it].y = t[it].y > 0.f ? v[it].y : 0.f;
         v[it].z = t[it].z > 0.f ? v[it].z : 0.f; v[it].w = t[it].w > 0.f ? v[it].w : 0.f;
-      }
-    }
-    if (g.drop.p > 0.f) {
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const uint64_t idx = (uint64_t)(row + it * 4) * (uint64_t)g.N + (uint64_t)col;   // multiple of 4 here
-        const uint4 rnd = dropout_rand4(g.drop, idx >> 2);
-        v[it].x = rnd.x < g.drop.threshold ? v[it].x * g.drop.inv_keep : 0.f;
-        v[it].y = rnd.y < g.drop.threshold ? v[it].y * g.drop.inv_keep : 0.f;
-        v[it].z = rnd.z < g.drop.threshold ? v[it].z * g.drop.inv_keep : 0.f;
-        v[it].w = rnd.w < g.drop.threshold ? v[it].w * g.drop.inv_keep : 0.f;
       }
     }
     if (g.residual) {
@@ -146,10 +123,69 @@ __device__ __forceinline__ void store_block(const KernelArgs& ka, const float* s
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (col + j >= g.N) break;
-      float o = gemm_epilogue_one(g, vv[j], row, col + j);
+      float o = vv[j];
+      if (g.gate) o = g.gate[(int64_t)row * g.ldg + col + j] > 0.f ? o : 0.f;
+      if (g.residual) o += g.residual[(int64_t)row * g.ldr + col + j];
       float* dst = g.C + (int64_t)row * g.ldc + col + j;
       if (g.accumulate) o += *dst;
       *dst = o;
+    }
+  }
+}
+
+// Phase 1 of the epilogue, on the accumulator row a thread just read from TMEM (32 consecutive
+// columns in registers): bias, ReLU (+ bit-packed mask out), bit-packed ReLU gate, inverted dropout.
+// Everything here needs no extra global traffic beyond a broadcast bias load and one mask word.
+__device__ __forceinline__ void epilogue_row(const GemmArgs& g, uint32_t (&v)[32], int row, int col0) {
+  const bool full = col0 + 32 <= g.N;
+  if (g.bias) {
+    if (full && ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = *reinterpret_cast<const float4*>(g.bias + col0 + 4 * i);
+        v[4 * i] = __float_as_uint(__uint_as_float(v[4 * i]) + b.x);
+        v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + b.y);
+        v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + b.z);
+        v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + b.w);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (col0 + c < g.N) v[c] = __float_as_uint(__uint_as_float(v[c]) + g.bias[col0 + c]);
+    }
+  }
+  if (g.relu) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const float f = fmaxf(__uint_as_float(v[c]), 0.f);
+      v[c] = __float_as_uint(f);
+      bits |= (f > 0.f ? 1u : 0u) << c;
+    }
+    if (g.relu_bits_out && row < g.M) g.relu_bits_out[(int64_t)row * g.ld_bits + (col0 >> 5)] = bits;
+  }
+  if (g.gate_bits) {
+    const uint32_t bits = row < g.M ? g.gate_bits[(int64_t)row * g.ld_bits + (col0 >> 5)] : 0u;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = ((bits >> c) & 1u) ? v[c] : 0u;
+  }
+  if (g.drop.p > 0.f) {
+    if (g.N % 8 == 0) {                       // col0 % 32 == 0, so row*N + col0 is a multiple of 8
+      const uint64_t idx8 = ((uint64_t)row * (uint64_t)g.N + (uint64_t)col0) >> 3;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint4 r = dropout_rand8(g.drop, idx8 + k);
+#pragma unroll
+        for (int f = 0; f < 8; ++f) {
+          const int c = 8 * k + f;
+          v[c] = dropout_keep(g.drop, r, f) ? __float_as_uint(__uint_as_float(v[c]) * g.drop.inv_keep) : 0u;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (col0 + c < g.N)
+          v[c] = __float_as_uint(dropout_one(g.drop, (uint64_t)row * (uint64_t)g.N + (uint64_t)(col0 + c), __uint_as_float(v[c])));
     }
   }
 }
@@ -291,6 +327,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int c = c_begin; c < c_end; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+        if (ka.ws == nullptr) epilogue_row(g, v, m0 + q * 32 + lane, n0 + c * 32);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           *reinterpret_cast<float4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) =
@@ -422,9 +459,11 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
   ka.kblocks_per_split = (int)ceil_div(ka.kblocks_total, splits);
   splits = (int)ceil_div(ka.kblocks_total, ka.kblocks_per_split);
   ka.splits = splits;
-  ka.vec_ok = (aligned16(g.C) && g.ldc % 4 == 0 && (!g.bias || aligned16(g.bias)) &&
+  ka.vec_ok = (aligned16(g.C) && g.ldc % 4 == 0 &&
                (!g.residual || (aligned16(g.residual) && g.ldr % 4 == 0)) &&
-               (!g.gate || (aligned16(g.gate) && g.ldg % 4 == 0)) && (g.drop.p <= 0.f || g.N % 4 == 0)) ? 1 : 0;
+               (!g.gate || (aligned16(g.gate) && g.ldg % 4 == 0))) ? 1 : 0;
+  NLPS_REQUIRE(!(g.relu_bits_out || g.gate_bits) || (g.N % 32 == 0 && splits == 1),
+               "gemm_tf32: bit-packed ReLU masks need N %% 32 == 0 and no split-K");
   ka.ws = nullptr;
   ka.ws_ld = round_up(g.N, 4);
   {

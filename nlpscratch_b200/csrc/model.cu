@@ -38,13 +38,14 @@ struct nlps_cache {
   int32_t* x_flat = nullptr;
   int32_t* fnp = nullptr;
   float* h0 = nullptr;
-  struct L { float *qkv, *ctx, *lse, *r1, *mean1, *rstd1, *y1, *hid, *r2, *mean2, *rstd2, *y2; };
+  struct L { float *qkv, *ctx, *lse, *r1, *mean1, *rstd1, *y1, *hid, *r2, *mean2, *rstd2, *y2; uint32_t* relu_bits; };
   std::vector<L> layers;
   float* logits = nullptr;
   float drop_p = 0.f;       // dropout probability in effect during this forward
   uint32_t drop_step = 0;
   bool has_logits = false;
   bool valid = false;
+  bool relu_bits_valid = false;   // the forward ran the tensor-core FFN and left bit-packed ReLU masks
 };
 
 struct nlps_model {
@@ -194,7 +195,8 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
     {  // dz = (d_f W2^T) * (hid > 0)
       GemmArgs g = gemm_nn(N, F, E, d_f, E, m->P + o.w2, E, m->dhid, F);
       g.trans_b = true;
-      g.gate = a.hid; g.ldg = F;
+      if (c->relu_bits_valid && prec == NLPS_PREC_TF32) { g.gate_bits = a.relu_bits; g.ld_bits = F / 32; }
+      else { g.gate = a.hid; g.ldg = F; }
       NLPS_TRY(gemm_dispatch(st, prec, g));
     }
     {  // dW1 = y1^T dz ; db1
@@ -494,12 +496,13 @@ int nlps_cache_create(nlps_model* m, int B, int S, nlps_cache** out) {
   int64_t cur = 0;   // in floats
   auto carve = [&](int64_t n) { const int64_t at = cur; cur = round_up(cur + n, kAlign); return at; };
   const int64_t o_x = carve(N), o_fnp = carve(B), o_h0 = carve(N * E);
-  struct LO { int64_t qkv, ctx, lse, r1, mean1, rstd1, y1, hid, r2, mean2, rstd2, y2; };
+  struct LO { int64_t qkv, ctx, lse, r1, mean1, rstd1, y1, hid, r2, mean2, rstd2, y2, bits; };
   std::vector<LO> lo(m->L);
   for (auto& q : lo) {
     q.qkv = carve(N * 3 * E); q.ctx = carve(N * E); q.lse = carve((int64_t)B * m->h * S);
     q.r1 = carve(N * E); q.mean1 = carve(N); q.rstd1 = carve(N); q.y1 = carve(N * E);
     q.hid = carve(N * F); q.r2 = carve(N * E); q.mean2 = carve(N); q.rstd2 = carve(N); q.y2 = carve(N * E);
+    q.bits = carve(N * ((F + 31) / 32));
   }
   const int64_t o_logits = carve(N * m->ldV);
   c->bytes = (size_t)cur * sizeof(float);
@@ -524,7 +527,8 @@ int nlps_cache_create(nlps_model* m, int B, int S, nlps_cache** out) {
   for (int l = 0; l < m->L; ++l) {
     const LO& q = lo[l];
     c->layers[l] = {f + q.qkv, f + q.ctx, f + q.lse, f + q.r1, f + q.mean1, f + q.rstd1, f + q.y1,
-                    f + q.hid, f + q.r2, f + q.mean2, f + q.rstd2, f + q.y2};
+                    f + q.hid, f + q.r2, f + q.mean2, f + q.rstd2, f + q.y2,
+                    reinterpret_cast<uint32_t*>(f + q.bits)};
   }
   c->logits = f + o_logits;
   *out = c;
@@ -572,6 +576,9 @@ int nlps_forward(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, i
   NLPS_TRY(embed_forward(st, c->B, c->S, E, m->V, d_x, xs, m->P + m->off_We, m->pe, c->h0, c->x_flat, m->err_flag));
   NLPS_TRY(first_nonpad(st, c->B, c->S, c->x_flat, c->fnp));
   const float* x_in = c->h0;
+  // 1-bit ReLU masks replace the 4-byte gate read in backward (tensor-core path, F % 32 == 0)
+  const bool use_bits = prec == NLPS_PREC_TF32 && F % 32 == 0 && E % 4 == 0;
+  c->relu_bits_valid = use_bits;
   for (int l = 0; l < m->L; ++l) {
     const LayerOff& o = m->lo[l];
     nlps_cache::L& a = c->layers[l];
@@ -590,6 +597,7 @@ int nlps_forward(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, i
     {  // hid = relu(y1 W1 + b1)                                      (:153)
       GemmArgs g = gemm_nn(N, F, E, a.y1, E, m->P + o.w1, F, a.hid, F);
       g.bias = m->P + o.b1; g.relu = true;
+      if (use_bits) { g.relu_bits_out = a.relu_bits; g.ld_bits = F / 32; }
       NLPS_TRY(gemm_dispatch(st, prec, g));
     }
     {  // r2 = y1 + dropout(hid W2 + b2)                              (:154-159)

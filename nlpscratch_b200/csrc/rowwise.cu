@@ -129,12 +129,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(int64_t rows, int
         o.w = (dh[i].w - s1 - xh[i].w * s2) * rs;
         *reinterpret_cast<float4*>(dx + row * E + c) = o;
         if (use_drop) {
-          const uint64_t idx = (uint64_t)row * (uint64_t)E + (uint64_t)c;
-          const uint4 rnd = dropout_rand4(drop, idx >> 2);
-          o.x = rnd.x < drop.threshold ? o.x * drop.inv_keep : 0.f;
-          o.y = rnd.y < drop.threshold ? o.y * drop.inv_keep : 0.f;
-          o.z = rnd.z < drop.threshold ? o.z * drop.inv_keep : 0.f;
-          o.w = rnd.w < drop.threshold ? o.w * drop.inv_keep : 0.f;
+          dropout_four(drop, (uint64_t)row * (uint64_t)E + (uint64_t)c, o);
           *reinterpret_cast<float4*>(dx_dropped + row * E + c) = o;
         }
       }
