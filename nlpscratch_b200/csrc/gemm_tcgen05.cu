@@ -28,7 +28,7 @@ using namespace tc;
 constexpr int BM = 128;
 constexpr int BK = 32;                 // floats per k-block = one 128-byte swizzle span
 constexpr int UMMA_K = 8;              // kind::tf32: 32 bytes of K per instruction
-constexpr int kEpiWarps = 4;             // one warp per TMEM lane quarter (8 = two per quarter, splitting columns)
+constexpr int kEpiWarps = 8;             // one warp per TMEM lane quarter (8 = two per quarter, splitting columns)
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kEpiStageFloats = 32 * 32;   // per epilogue warp: 32x32 block, 16-B chunks XOR-swizzled by row
 
@@ -355,6 +355,180 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+// =========================================================================================
+// CTA-pair variant (cta_group::2): two CTAs on one TPC compute a 256x256 tile.  CTA r loads A rows
+// [m0+128r, +128) and B rows/columns [n0+128r, +128); the leader CTA issues one M=256,N=256 MMA per K=8
+// that reads A and B from BOTH shared memories, so each SM moves 32 KB per k-block through smem
+// instead of 48 KB -- shared-memory bandwidth, not the tensor pipe, is what bounds the FP32-operand
+// (TF32) GEMM.  Each CTA keeps its own 128 accumulator rows in its TMEM and runs its own epilogue.
+constexpr int kPairStages = 6;
+constexpr int kPairStageBytes = 2 * BM * BK * 4;                 // A half + B half, 16 KB each
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kEpiWarps * kEpiStageFloats * 4 + 256 + 1024;
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ KernelArgs ka) {
+  constexpr int BN = 256, BMP = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t epi_base = base + kPairStages * kPairStageBytes;
+  float* epi_ptr = reinterpret_cast<float*>(base_ptr + kPairStages * kPairStageBytes);
+  constexpr int kEpiBytes = kEpiWarps * kEpiStageFloats * 4;
+  const uint32_t bar_base = epi_base + kEpiBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kPairStages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kPairStages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kPairStages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kPairStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      base_ptr + kPairStages * kPairStageBytes + kEpiBytes + 8 * (2 * kPairStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const GemmArgs& g = ka.g;
+  const int tiles = ka.num_m_tiles * ka.num_n_tiles;
+  const int items = tiles * ka.splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < kPairStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 2 * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();                      // both CTAs' barriers and TMEM exist before anyone signals
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one per CTA) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = pair; item < items; item += num_pairs) {
+        const int split = item / tiles;
+        const int t = item - split * tiles;
+        const int m0 = (t / ka.num_n_tiles) * BMP + (int)rank * BM;
+        const int n0 = (t % ka.num_n_tiles) * BN + (int)rank * 128;
+        const int kb0 = split * ka.kblocks_per_split;
+        const int kb1 = min(ka.kblocks_total, kb0 + ka.kblocks_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = base + stage * kPairStageBytes;
+          const uint32_t b_dst = a_dst + BM * BK * 4;
+          const uint32_t lead_full = mapa_rank(full_bar(stage), 0);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * kPairStageBytes);   // both CTAs' bytes land here
+          const int k0 = kb * BK;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_2d_pair(a_dst + j * 4096, &map_a, lead_full, m0 + 32 * j, k0);
+          } else {
+            tma_load_2d_pair(a_dst, &map_a, lead_full, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_2d_pair(b_dst + j * 4096, &map_b, lead_full, n0 + 32 * j, k0);
+          } else {
+            tma_load_2d_pair(b_dst, &map_b, lead_full, k0, n0);
+          }
+          if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer: one thread of the leader CTA =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                 ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BMP >> 4) << 24);
+      int stage = 0; uint32_t phase = 0; int local = 0;
+      for (int item = pair; item < items; item += num_pairs, ++local) {
+        const int split = item / tiles;
+        const int kb0 = split * ka.kblocks_per_split;
+        const int kb1 = min(ka.kblocks_total, kb0 + ka.kblocks_per_split);
+        const int buf = local & 1;
+        const uint32_t aphase = (uint32_t)(local >> 1) & 1u;
+        mbar_wait(tempty_bar(buf), aphase ^ 1u);       // both CTAs' epilogues drained this buffer
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_src = base + stage * kPairStageBytes;
+          const uint32_t b_src = a_src + BM * BK * 4;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ad = A_MN ? make_desc(a_src + k * 1024, 4096, 512, 1) : make_desc(a_src + k * 32, 16, 1024, 2);
+            const uint64_t bd = B_MN ? make_desc(b_src + k * 1024, 4096, 512, 1) : make_desc(b_src + k * 32, 16, 1024, 2);
+            umma_tf32_pair(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(empty_bar(stage));           // frees the slot in both CTAs
+          if (kb == kb1 - 1) umma_commit_pair(tfull_bar(buf));
+          if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (each CTA stores its own 128 rows) =====================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int kChunksPerWarp = BN / 32 / (kEpiWarps / 4);
+    float* stg = epi_ptr + (warp - 2) * kEpiStageFloats;
+    int local = 0;
+    for (int item = pair; item < items; item += num_pairs, ++local) {
+      const int split = item / tiles;
+      const int t = item - split * tiles;
+      const int m0 = (t / ka.num_n_tiles) * BMP + (int)rank * BM;
+      const int n0 = (t % ka.num_n_tiles) * BN;
+      const int buf = local & 1;
+      const uint32_t aphase = (uint32_t)(local >> 1) & 1u;
+      mbar_wait(tfull_bar(buf), aphase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+      const uint32_t lead_tempty = mapa_rank(tempty_bar(buf), 0);
+      const bool rows_live = (m0 + q * 32) < g.M;
+      const int c_begin = half * kChunksPerWarp;
+      int c_end = min(c_begin + kChunksPerWarp, (g.N - n0 + 31) / 32);
+      if (!rows_live || (ka.debug & 2)) c_end = c_begin;
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+        if (ka.ws == nullptr) epilogue_row(g, v, m0 + q * 32 + lane, n0 + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                          __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        __syncwarp();
+        if (c == c_end - 1) {
+          tc_fence_before();
+          if (lane == 0) mbar_arrive_cluster(lead_tempty);
+        }
+        if (!(ka.debug & 1)) store_block(ka, stg, lane, m0 + q * 32, n0 + c * 32, split);
+        __syncwarp();
+      }
+      if (c_end <= c_begin) {
+        tc_fence_before();
+        if (lane == 0) mbar_arrive_cluster(lead_tempty);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                      // nobody leaves while the peer may still touch its smem / TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
 // ---- split-K reducer (fixed summation order => deterministic) --------------------------
 __global__ void splitk_reduce_kernel(const KernelArgs ka) {
   const GemmArgs& g = ka.g;
@@ -433,25 +607,55 @@ int launch(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const 
   return 0;
 }
 
+template <bool AM, bool BMN>
+int launch_pair_one(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const KernelArgs& ka, int grid) {
+  auto kern = gemm_tf32_pair_kernel<AM, BMN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NLPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    attr_set = true;
+  }
+  kern<<<grid, kThreads, kPairSmemBytes, st>>>(ma, mb, ka);
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_pair(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const KernelArgs& ka, int grid) {
+  const bool amn = ka.g.trans_a, bmn = !ka.g.trans_b;
+  if (amn && bmn) return launch_pair_one<true, true>(st, ma, mb, ka, grid);
+  if (amn) return launch_pair_one<true, false>(st, ma, mb, ka, grid);
+  if (bmn) return launch_pair_one<false, true>(st, ma, mb, ka, grid);
+  return launch_pair_one<false, false>(st, ma, mb, ka, grid);
+}
+
+int pair_mode() {                 // NLPS_GEMM_PAIR=0 disables the CTA-pair kernel (A/B measurements)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NLPS_GEMM_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
+
 int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
   if (g.M <= 0 || g.N <= 0) return 0;
   NLPS_REQUIRE(g.K > 0, "gemm_tf32: K must be positive");
   NLPS_REQUIRE(gemm_tf32_supported(g), "gemm_tf32: operands not TMA-addressable (need 16-B aligned bases, ld %% 4 == 0)");
-  // tile shape: 128x256 whenever N allows it (operand bytes per flop are what limits a TF32 GEMM)
+  // tile shape: CTA pairs on 256x256 tiles when both extents allow it, else 128x256 / 128x128 single CTAs
+  const bool pair = pair_mode() && g.M > 128 && g.N > 128;
   const int BN = g.N > 128 ? 256 : 128;
+  const int BMT = pair ? 256 : BM;
+  const int units = pair ? kNumSMs / 2 : kNumSMs;          // schedulable units per wave
   KernelArgs ka{};
   ka.g = g;
-  ka.num_m_tiles = (int)ceil_div(g.M, BM);
+  ka.num_m_tiles = (int)ceil_div(g.M, BMT);
   ka.num_n_tiles = (int)ceil_div(g.N, BN);
   ka.kblocks_total = (int)ceil_div(g.K, BK);
   const int tiles = ka.num_m_tiles * ka.num_n_tiles;
   int splits = 1;
-  if (tiles < 2 * kNumSMs && ka.kblocks_total >= 64) {
+  if (tiles < 2 * units && ka.kblocks_total >= 64) {
     // weight-gradient shaped (few tiles, long K): pick the split that minimises
-    //   waves(s) * (k-blocks per split + fixed per-tile cost)   with whole waves of 148 CTAs
+    //   waves(s) * (k-blocks per split + fixed per-tile cost)   with whole waves of CTAs / CTA pairs
     double best = 1e30;
     for (int s = 1; s <= 32 && ka.kblocks_total / s >= 8; ++s) {
-      const int64_t waves = ceil_div((int64_t)tiles * s, kNumSMs);
+      const int64_t waves = ceil_div((int64_t)tiles * s, units);
       const double t = (double)waves * ((double)ceil_div(ka.kblocks_total, s) + 24.0);
       if (t < best - 1e-9) { best = t; splits = s; }
     }
@@ -473,14 +677,19 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
   }
   if (splits > 1) NLPS_TRY(splitk_workspace(st, (size_t)splits * g.M * ka.ws_ld * sizeof(float), &ka.ws));
   CUtensorMap ma, mb;
+  const uint32_t b_rows = pair ? 128u : (uint32_t)BN;      // a CTA of a pair loads half of the B tile
   if (g.trans_a) NLPS_TRY(make_map(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K, g.lda, 32, BK, round_tf32, true));
   else NLPS_TRY(make_map(&ma, g.A, (uint64_t)g.K, (uint64_t)g.M, g.lda, BK, BM, round_tf32, false));
-  if (g.trans_b) NLPS_TRY(make_map(&mb, g.B, (uint64_t)g.K, (uint64_t)g.N, g.ldb, BK, (uint32_t)BN, round_tf32, false));
+  if (g.trans_b) NLPS_TRY(make_map(&mb, g.B, (uint64_t)g.K, (uint64_t)g.N, g.ldb, BK, b_rows, round_tf32, false));
   else NLPS_TRY(make_map(&mb, g.B, (uint64_t)g.N, (uint64_t)g.K, g.ldb, 32, BK, round_tf32, true));
   const int items = tiles * splits;
-  const int grid = std::min(items, kNumSMs);
-  if (BN == 256) NLPS_TRY(launch<256>(st, ma, mb, ka, grid));
-  else NLPS_TRY(launch<128>(st, ma, mb, ka, grid));
+  if (pair) {
+    NLPS_TRY(launch_pair(st, ma, mb, ka, 2 * std::min(items, units)));
+  } else {
+    const int grid = std::min(items, kNumSMs);
+    if (BN == 256) NLPS_TRY(launch<256>(st, ma, mb, ka, grid));
+    else NLPS_TRY(launch<128>(st, ma, mb, ka, grid));
+  }
   if (splits > 1) {
     const int64_t total = (int64_t)g.M * g.N;
     const int rgrid = (int)std::min<int64_t>(ceil_div(total, 256), kNumSMs * 8);
