@@ -50,6 +50,7 @@ struct KernelArgs {
   float* ws;            // split-K workspace [splits][M][ws_ld] or null
   int64_t ws_ld;
   int vec_ok;           // float4 epilogue allowed (alignment of C / residual / gate / N)
+  int direct_ok;        // 32-B aligned output/fused operands: epilogue stores rows straight from registers
   int debug;            // NLPS_GEMM_DEBUG bits: 1 = skip global stores, 2 = skip the whole epilogue body
 };
 
@@ -190,6 +191,62 @@ __device__ __forceinline__ void epilogue_row(const GemmArgs& g, uint32_t (&v)[32
   }
 }
 
+// Phase 2 without the shared-memory transpose: the thread owns 32 consecutive output floats of one row
+// (128 B) and moves them with four 256-bit accesses (LDG/STG.E.ENL2.256).  Every access is a full 32-B
+// sector, and the 2 x 128 KB per tile of staging traffic -- which competes with TMA fills and UMMA
+// operand reads for the 128 B/clk of shared-memory bandwidth -- disappears.
+__device__ __forceinline__ void ld_v8(const float* p, float (&r)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st_v8(float* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void store_row_direct(const KernelArgs& ka, uint32_t (&v)[32], int row, int col0, int split) {
+  const GemmArgs& g = ka.g;
+  if (ka.ws != nullptr) {
+    float* dst = ka.ws + ((int64_t)split * g.M + row) * ka.ws_ld + col0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) st_v8(dst + 8 * i, v + 8 * i);
+    return;
+  }
+  if (g.gate) {
+    const float* src = g.gate + (int64_t)row * g.ldg + col0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t[8];
+      ld_v8(src + 8 * i, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * i + j] = t[j] > 0.f ? v[8 * i + j] : 0u;
+    }
+  }
+  if (g.residual) {
+    const float* src = g.residual + (int64_t)row * g.ldr + col0;
+    float t[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ld_v8(src + 8 * i, t[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * i + j] = __float_as_uint(__uint_as_float(v[8 * i + j]) + t[i][j]);
+  }
+  float* dst = g.C + (int64_t)row * g.ldc + col0;
+  if (g.accumulate) {
+    float t[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ld_v8(dst + 8 * i, t[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * i + j] = __float_as_uint(__uint_as_float(v[8 * i + j]) + t[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) st_v8(dst + 8 * i, v + 8 * i);
+}
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -328,18 +385,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint32_t v[32];
         tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
         if (ka.ws == nullptr) epilogue_row(g, v, m0 + q * 32 + lane, n0 + c * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) =
-              make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                          __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-        __syncwarp();
         if (c == c_end - 1) {      // last TMEM read of this warp's share: hand the buffer back before storing
           tc_fence_before();
           if (lane == 0) mbar_arrive(tempty_bar(buf));
         }
-        if (!(ka.debug & 1)) store_block(ka, stg, lane, m0 + q * 32, n0 + c * 32, split);
-        __syncwarp();
+        if (ka.direct_ok && (m0 + q * 32 + 32 <= g.M) && (n0 + c * 32 + 32 <= g.N)) {      // warp-uniform
+          if (!(ka.debug & 1)) store_row_direct(ka, v, m0 + q * 32 + lane, n0 + c * 32, split);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) =
+                make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                            __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          __syncwarp();
+          if (!(ka.debug & 1)) store_block(ka, stg, lane, m0 + q * 32, n0 + c * 32, split);
+          __syncwarp();
+        }
       }
       if (c_end <= c_begin) {
         tc_fence_before();
@@ -502,18 +563,22 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         uint32_t v[32];
         tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
         if (ka.ws == nullptr) epilogue_row(g, v, m0 + q * 32 + lane, n0 + c * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) =
-              make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                          __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-        __syncwarp();
         if (c == c_end - 1) {
           tc_fence_before();
           if (lane == 0) mbar_arrive_cluster(lead_tempty);
         }
-        if (!(ka.debug & 1)) store_block(ka, stg, lane, m0 + q * 32, n0 + c * 32, split);
-        __syncwarp();
+        if (ka.direct_ok && (m0 + q * 32 + 32 <= g.M) && (n0 + c * 32 + 32 <= g.N)) {      // warp-uniform
+          if (!(ka.debug & 1)) store_row_direct(ka, v, m0 + q * 32 + lane, n0 + c * 32, split);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) =
+                make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                            __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          __syncwarp();
+          if (!(ka.debug & 1)) store_block(ka, stg, lane, m0 + q * 32, n0 + c * 32, split);
+          __syncwarp();
+        }
       }
       if (c_end <= c_begin) {
         tc_fence_before();
@@ -669,7 +734,14 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
   NLPS_REQUIRE(!(g.relu_bits_out || g.gate_bits) || (g.N % 32 == 0 && splits == 1),
                "gemm_tf32: bit-packed ReLU masks need N %% 32 == 0 and no split-K");
   ka.ws = nullptr;
-  ka.ws_ld = round_up(g.N, 4);
+  ka.ws_ld = round_up(g.N, 8);
+  {
+    auto a32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
+    static int nodirect = -1;
+    if (nodirect < 0) { const char* e = getenv("NLPS_GEMM_STAGED"); nodirect = (e && e[0] == '1') ? 1 : 0; }
+    ka.direct_ok = (!nodirect && a32(g.C) && g.ldc % 8 == 0 && (!g.residual || (a32(g.residual) && g.ldr % 8 == 0)) &&
+                    (!g.gate || (a32(g.gate) && g.ldg % 8 == 0))) ? 1 : 0;
+  }
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("NLPS_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
