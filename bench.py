@@ -350,8 +350,18 @@ def gemm_roofline(torch, _lib, N, E, F, precision):
     peaks = measured_peaks()
     peak = peaks["bf16_burst"] / 2.0
     ach = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32) %dx%dx%d" % (N, F, E),
-            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+    traffic = None
+    try:        # DRAM bytes of the same launch from the committed `ncu --set full` capture (profiles/)
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_ffn1_ncu.json")) as fh:
+            m = json.load(fh)
+        if (N, E, F) == (32768, 512, 2048):
+            traffic = (float(m["dram__bytes_read.sum"]["value"]) + float(m["dram__bytes_write.sum"]["value"])) * 1e6
+    except Exception:
+        traffic = None
+    return {"bound": "tensor", "kernel": "gemm_tf32_pair_kernel (tcgen05 cta_group::2 kind::tf32) %dx%dx%d" % (N, F, E),
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+            "traffic_note": "dram__bytes_read+write of this launch (profiles/r01_gemm_ffn1_ncu.json); algorithmic bytes %.1f MB" % (
+                (N * E + E * F + N * F) * 4 / 1e6),
             "ms_per_launch": ms, "peak_note": "TF32 dense = 1/2 of the %s burst BF16 peak" % peaks["source"]}
 
 

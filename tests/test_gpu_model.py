@@ -245,3 +245,31 @@ def test_errors_are_python_exceptions():
     with pytest.raises(RuntimeError):
         m.forward(np.ones((1, 9), np.int32))                      # longer than max_len
     m.close()
+
+
+def test_baseline_model_size_tf32_agrees_with_fp32():
+    """BASELINE.json's quoted model (6 layers, d_model 512, 8 heads, ff 2048, seq 512, vocab 8192) at a
+    reduced batch: the tensor-core path (tcgen05 GEMMs + tcgen05 attention) against the FP32-faithful
+    CUDA-core path on identical weights and inputs -- loss, every gradient tensor, and the linearity
+    property of the step (gradients scale with grad_scale)."""
+    L, E, h, F, S, V, B = 6, 512, 8, 2048, 512, 8192, 4
+    rng = np.random.default_rng(42)
+    x = rng.integers(1, V, (B, S)).astype(np.int32)
+    x[1, 400:] = 0                                          # one padded sequence
+    y = rng.integers(1, V, (B, S)).astype(np.int32)
+    np.random.seed(9)
+    ref = Transformer(V, E, h, F, L, S, dropout_p=0.0, precision="fp32")
+    params = ref.get_params()
+    l_ref = float(ref.train_step(x, y, defer_update=True))
+    g_ref = {k: ref._view(1, k).get() for k in NAMES}
+    ref.close()
+    m = Transformer(V, E, h, F, L, S, dropout_p=0.0, precision="tf32")
+    m.load_params(params)
+    l_tf = float(m.train_step(x, y, defer_update=True))
+    assert abs(l_tf - l_ref) < 2e-3 * abs(l_ref)
+    for k in NAMES:
+        assert rel_err(m._view(1, k).get(), g_ref[k]) < 5e-2, (k, rel_err(m._view(1, k).get(), g_ref[k]))
+    g1 = m.flat("grad").get()
+    m.train_step(x, y, grad_scale=0.25, defer_update=True)
+    assert rel_err(m.flat("grad").get(), 0.25 * g1) < 1e-6      # linear in the loss scale, bit-stable reductions
+    m.close()
