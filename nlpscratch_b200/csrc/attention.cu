@@ -221,6 +221,32 @@ __global__ void attn_delta_kernel(AttnDims p, const float* __restrict__ ctx, con
   }
 }
 
+// vectorised variant: one warp per token, float4 per lane; a head is G = d/4 adjacent lanes
+// (G a power of two <= 32), reduced with G-wide shuffles.  8 tokens per CTA.
+template <int G>
+__global__ void __launch_bounds__(256) attn_delta_vec_kernel(AttnDims p, int64_t ntok, const float* __restrict__ ctx,
+                                                             const float* __restrict__ dctx,
+                                                             float* __restrict__ delta) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tok >= ntok) return;
+  const int b = (int)(tok / p.S), i = (int)(tok - (int64_t)b * p.S);
+  const float4* c4 = reinterpret_cast<const float4*>(ctx + tok * p.E);
+  const float4* d4 = reinterpret_cast<const float4*>(dctx + tok * p.E);
+  const int n4 = p.E / 4;
+  for (int base = 0; base < n4; base += 32) {
+    const int idx = base + lane;
+    float acc = 0.f;
+    if (idx < n4) {
+      const float4 a = c4[idx], g = d4[idx];
+      acc = (a.x * g.x + a.y * g.y) + (a.z * g.z + a.w * g.w);
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (idx < n4 && (lane & (G - 1)) == 0) delta[((int64_t)b * p.h + idx / G) * p.S + i] = acc;
+  }
+}
+
 // recompute P and dS for one (query tile, key tile) pair; results left in registers
 template <int D>
 __device__ __forceinline__ void recompute_p_ds(const AttnDims& p, const float* Qs, const float* Ks, const float* dOs,
@@ -530,8 +556,15 @@ int attention_backward(cudaStream_t st, int precision, int B, int S, int h, int 
                        const float* dctx, float* delta, float* dqkv) {
   NLPS_TRY(check_dims(B, S, h, d));
   AttnDims p{B, S, h, d, h * d, (float)(1.0 / sqrt((double)d))};
-  const int threads = std::min(1024, 32 * h);
-  attn_delta_kernel<<<(unsigned)((int64_t)B * S), threads, 0, st>>>(p, ctx, dctx, delta);
+  const int64_t ntok = (int64_t)B * S;
+  const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(ctx) | reinterpret_cast<uintptr_t>(dctx)) & 15u) == 0;
+  const unsigned vgrid = (unsigned)ceil_div(ntok, 8);
+  if (vec && d == 64) attn_delta_vec_kernel<16><<<vgrid, 256, 0, st>>>(p, ntok, ctx, dctx, delta);
+  else if (vec && d == 32) attn_delta_vec_kernel<8><<<vgrid, 256, 0, st>>>(p, ntok, ctx, dctx, delta);
+  else if (vec && d == 128) attn_delta_vec_kernel<32><<<vgrid, 256, 0, st>>>(p, ntok, ctx, dctx, delta);
+  else if (vec && d == 16) attn_delta_vec_kernel<4><<<vgrid, 256, 0, st>>>(p, ntok, ctx, dctx, delta);
+  else if (vec && d == 8) attn_delta_vec_kernel<2><<<vgrid, 256, 0, st>>>(p, ntok, ctx, dctx, delta);
+  else attn_delta_kernel<<<(unsigned)ntok, std::min(1024, 32 * h), 0, st>>>(p, ctx, dctx, delta);
   NLPS_LAUNCH_CHECK();
   if (precision == 1 && attention_tc_supported(d, h * d, qkv) && attn_impl() == 0 &&
       (reinterpret_cast<uintptr_t>(dctx) & 15u) == 0)

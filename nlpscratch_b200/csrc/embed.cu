@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(int V, const int32_t* __rest
 }
 
 // rank[n] = #{n' < n : x[n'] == x[n]};  order[start[x[n]] + rank[n]] = n
+// (brute-force version, O(N^2) compares: kept for huge vocabulary x chunk products)
 __global__ void __launch_bounds__(256) rank_kernel(int64_t N, const int32_t* __restrict__ x,
                                                    const int32_t* __restrict__ start, int32_t* __restrict__ order) {
   __shared__ int32_t tile[1024];
@@ -99,10 +100,50 @@ __global__ void __launch_bounds__(256) rank_kernel(int64_t N, const int32_t* __r
     for (int i = threadIdx.x; i < 1024; i += 256) tile[i] = (base + i < N) ? x[base + i] : -2;
     __syncthreads();
     const int64_t rem = n - base;
-    const int64_t lim = rem < 1024 ? rem : 1024;                   // positions base..n-1
+    const int64_t lim = rem < 1024 ? rem : 1024;
     for (int i = 0; i < lim; ++i) rank += (tile[i] == mine);
   }
   if (n < N) order[start[mine] + rank] = (int32_t)n;
+}
+
+// Chunked version: positions are cut into chunks of 1024.  (1) rank inside the chunk by comparing
+// against the chunk's ids in smem, and a per-(chunk, id) count; (2) per id, an exclusive prefix of
+// the counts over chunks (and the id's total); (3) after the scan over ids, every position knows its
+// slot: start[id] + earlier-chunks[id] + rank-in-chunk -- ascending position inside every bucket.
+constexpr int kChunk = 1024;
+__global__ void __launch_bounds__(kChunk) chunk_rank_kernel(int64_t N, int V, const int32_t* __restrict__ x,
+                                                            int32_t* __restrict__ local_rank,
+                                                            int32_t* __restrict__ chunk_hist) {
+  __shared__ int32_t ids[kChunk];
+  const int64_t n = (int64_t)blockIdx.x * kChunk + threadIdx.x;
+  const int32_t mine = n < N ? x[n] : -1;
+  ids[threadIdx.x] = mine;
+  __syncthreads();
+  int32_t rank = 0;
+  for (int i = 0; i < (int)threadIdx.x; ++i) rank += (ids[i] == mine);     // smem broadcast reads
+  if (n < N) {
+    local_rank[n] = rank;
+    atomicAdd(&chunk_hist[(int64_t)blockIdx.x * V + mine], 1);           // integer counts: order independent
+  }
+}
+__global__ void chunk_prefix_kernel(int V, int chunks, int32_t* __restrict__ chunk_hist, int32_t* __restrict__ count) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  int32_t run = 0;
+  for (int c = 0; c < chunks; ++c) {
+    const int32_t t = chunk_hist[(int64_t)c * V + v];
+    chunk_hist[(int64_t)c * V + v] = run;                                 // exclusive prefix over chunks
+    run += t;
+  }
+  count[v] = run;
+}
+__global__ void place_kernel(int64_t N, int V, const int32_t* __restrict__ x, const int32_t* __restrict__ local_rank,
+                             const int32_t* __restrict__ chunk_off, const int32_t* __restrict__ start,
+                             int32_t* __restrict__ order) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int32_t id = x[n];
+  order[start[id] + chunk_off[(n / kChunk) * V + id] + local_rank[n]] = (int32_t)n;
 }
 
 __global__ void __launch_bounds__(256) scatter_sum_kernel(int V, int E, const int32_t* __restrict__ start,
@@ -171,23 +212,44 @@ int embed_forward(cudaStream_t st, int B, int S, int E, int V, const int32_t* x,
   return 0;
 }
 
-size_t embed_backward_scratch_ints(int64_t N, int V) { return (size_t)(2 * ((int64_t)V + 1) + N + 8); }
+static bool use_chunked(int64_t N, int V) { return ceil_div(N, kChunk) * (int64_t)V <= ((int64_t)32 << 20); }
+
+size_t embed_backward_scratch_ints(int64_t N, int V) {
+  size_t n = (size_t)(2 * ((int64_t)V + 1) + N + 8);
+  if (use_chunked(N, V)) n += (size_t)N + (size_t)(ceil_div(N, kChunk) * (int64_t)V);
+  return n;
+}
 
 int embed_backward(cudaStream_t st, int64_t N, int E, int V, const int32_t* x_flat, const float* dh, float* dWe,
                    int32_t* scratch) {
   int32_t* count = scratch;
   int32_t* start = scratch + (V + 1);
   int32_t* order = scratch + 2 * ((int64_t)V + 1);
-  NLPS_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * (V + 1), st));
-  if (N > 0) {
-    hist_kernel<<<(unsigned)std::min<int64_t>(ceil_div(N, 256), kNumSMs * 8), 256, 0, st>>>(N, x_flat, count);
+  if (N > 0 && use_chunked(N, V)) {
+    const int chunks = (int)ceil_div(N, kChunk);
+    int32_t* local_rank = order + N;
+    int32_t* chunk_hist = local_rank + N;
+    NLPS_CUDA(cudaMemsetAsync(chunk_hist, 0, sizeof(int32_t) * (size_t)chunks * V, st));
+    chunk_rank_kernel<<<chunks, kChunk, 0, st>>>(N, V, x_flat, local_rank, chunk_hist);
     NLPS_LAUNCH_CHECK();
-  }
-  scan_kernel<<<1, 1024, 0, st>>>(V, count, start);
-  NLPS_LAUNCH_CHECK();
-  if (N > 0) {
-    rank_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(N, x_flat, start, order);
+    chunk_prefix_kernel<<<(unsigned)ceil_div(V, 256), 256, 0, st>>>(V, chunks, chunk_hist, count);
     NLPS_LAUNCH_CHECK();
+    scan_kernel<<<1, 1024, 0, st>>>(V, count, start);
+    NLPS_LAUNCH_CHECK();
+    place_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(N, V, x_flat, local_rank, chunk_hist, start, order);
+    NLPS_LAUNCH_CHECK();
+  } else {
+    NLPS_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * (V + 1), st));
+    if (N > 0) {
+      hist_kernel<<<(unsigned)std::min<int64_t>(ceil_div(N, 256), kNumSMs * 8), 256, 0, st>>>(N, x_flat, count);
+      NLPS_LAUNCH_CHECK();
+    }
+    scan_kernel<<<1, 1024, 0, st>>>(V, count, start);
+    NLPS_LAUNCH_CHECK();
+    if (N > 0) {
+      rank_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(N, x_flat, start, order);
+      NLPS_LAUNCH_CHECK();
+    }
   }
   const int vec = (E % 4 == 0 && aligned16(dh) && aligned16(dWe)) ? 1 : 0;
   scatter_sum_kernel<<<(unsigned)ceil_div(V, 8), 256, 0, st>>>(V, E, start, order, dh, dWe, vec);

@@ -275,33 +275,71 @@ __global__ void __launch_bounds__(1024) sum_to_scalar_kernel(const float* __rest
 }
 
 // ---------------- column sums (bias gradients): two-stage ----------------
-constexpr int kColSlabs = 64;
+constexpr int kColSlabsMax = 256;
+// block = 32 lanes x 8 warps; a lane owns 4 adjacent columns (float4), a warp walks rows of its slab
+// with 4 independent loads in flight; grid = (ceil(cols/128), slabs).  Fixed partition => deterministic.
 __global__ void __launch_bounds__(256) colsum_partial_kernel(int64_t rows, int cols, const float* __restrict__ x,
-                                                             int64_t ld, float* __restrict__ partial) {
-  // block = 32 lanes (columns) x 8 warps (rows); grid = (ceil(cols/32), kColSlabs)
-  __shared__ float sm[8][33];
+                                                             int64_t ld, float* __restrict__ partial, int vec) {
+  __shared__ float4 sm[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + lane;
+  const int col = (blockIdx.x * 32 + lane) * 4;
   const int64_t rows_per = (rows + gridDim.y - 1) / gridDim.y;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
-  float acc = 0.f;
-  if (col < cols)
-    for (int64_t r = r0 + warp; r < r1; r += 8) acc += x[r * ld + col];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec) {
+    if (col < cols) {
+      int64_t r = r0 + warp;
+      for (; r + 24 < r1; r += 32) {
+        const float4 a = *reinterpret_cast<const float4*>(x + r * ld + col);
+        const float4 b = *reinterpret_cast<const float4*>(x + (r + 8) * ld + col);
+        const float4 c = *reinterpret_cast<const float4*>(x + (r + 16) * ld + col);
+        const float4 d = *reinterpret_cast<const float4*>(x + (r + 24) * ld + col);
+        acc.x += (a.x + b.x) + (c.x + d.x); acc.y += (a.y + b.y) + (c.y + d.y);
+        acc.z += (a.z + b.z) + (c.z + d.z); acc.w += (a.w + b.w) + (c.w + d.w);
+      }
+      for (; r < r1; r += 8) {
+        const float4 a = *reinterpret_cast<const float4*>(x + r * ld + col);
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+      }
+    }
+  } else {
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+      if (col + 0 < cols) acc.x += x[r * ld + col + 0];
+      if (col + 1 < cols) acc.y += x[r * ld + col + 1];
+      if (col + 2 < cols) acc.z += x[r * ld + col + 2];
+      if (col + 3 < cols) acc.w += x[r * ld + col + 3];
+    }
+  }
   sm[warp][lane] = acc;
   __syncthreads();
-  if (warp == 0 && col < cols) {
+  if (warp == 0) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const float4 u = sm[w][lane]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    float* dst = partial + (int64_t)blockIdx.y * cols + col;
+    if (col + 0 < cols) dst[0] = t.x;
+    if (col + 1 < cols) dst[1] = t.y;
+    if (col + 2 < cols) dst[2] = t.z;
+    if (col + 3 < cols) dst[3] = t.w;
+  }
+}
+// block = 32 columns x 8 partial-slices
+__global__ void __launch_bounds__(256) colsum_finish_kernel(int nparts, int cols, const float* __restrict__ partial,
+                                                            float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (c < cols)
+    for (int p = warp; p < nparts; p += 8) acc += partial[(int64_t)p * cols + c];
+  sm[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < cols) {
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += sm[w][lane];
-    partial[(int64_t)blockIdx.y * cols + col] = t;
+    out[c] = t;
   }
-}
-__global__ void colsum_finish_kernel(int nparts, int cols, const float* __restrict__ partial, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float acc = 0.f;
-  for (int p = 0; p < nparts; ++p) acc += partial[(int64_t)p * cols + c];
-  out[c] = acc;
 }
 
 // ---------------- sum of squares: two-stage ----------------
@@ -312,7 +350,14 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(int64_t n, const flo
   float acc = 0.f;
   const int64_t n4 = n >> 2;
   const float4* x4 = reinterpret_cast<const float4*>(x);
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {       // 4 independent 16-B loads in flight per thread
+    const float4 a = x4[i], b = x4[i + stride], c = x4[i + 2 * stride], d = x4[i + 3 * stride];
+    acc += ((a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w)) + ((b.x * b.x + b.y * b.y) + (b.z * b.z + b.w * b.w)) +
+           ((c.x * c.x + c.y * c.y) + (c.z * c.z + c.w * c.w)) + ((d.x * d.x + d.y * d.y) + (d.z * d.z + d.w * d.w));
+  }
+  for (; i < n4; i += stride) {
     const float4 v = x4[i];
     acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
   }
@@ -421,15 +466,19 @@ int softmax_xent(cudaStream_t st, const float* logits, int64_t ld, const int32_t
   return 0;
 }
 
-size_t colsum_scratch_floats(int cols) { return (size_t)kColSlabs * cols; }
+size_t colsum_scratch_floats(int cols) { return (size_t)kColSlabsMax * cols; }
 
 int colsum(cudaStream_t st, int64_t rows, int cols, const float* x, int64_t ld, float* out, float* scratch) {
   if (cols <= 0) return 0;
-  const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(kColSlabs, ceil_div(rows, 8)));
-  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)slabs);
-  colsum_partial_kernel<<<grid, 256, 0, st>>>(rows, cols, x, ld, scratch);
+  const int gx = (int)ceil_div(cols, 128);
+  // enough row slabs to put ~4 CTAs on every SM, at least 32 rows each
+  int slabs = (int)std::min<int64_t>(kColSlabsMax, std::max<int64_t>(1, (kNumSMs * 4 + gx - 1) / gx));
+  slabs = (int)std::max<int64_t>(1, std::min<int64_t>(slabs, ceil_div(rows, 32)));
+  const int vec = (ld % 4 == 0 && cols % 4 == 0 && aligned16(x)) ? 1 : 0;
+  dim3 grid((unsigned)gx, (unsigned)slabs);
+  colsum_partial_kernel<<<grid, 256, 0, st>>>(rows, cols, x, ld, scratch, vec);
   NLPS_LAUNCH_CHECK();
-  colsum_finish_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, st>>>(slabs, cols, scratch, out);
+  colsum_finish_kernel<<<(unsigned)ceil_div(cols, 32), 256, 0, st>>>(slabs, cols, scratch, out);
   NLPS_LAUNCH_CHECK();
   return 0;
 }
