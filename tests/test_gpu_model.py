@@ -273,3 +273,46 @@ def test_baseline_model_size_tf32_agrees_with_fp32():
     m.train_step(x, y, grad_scale=0.25, defer_update=True)
     assert rel_err(m.flat("grad").get(), 0.25 * g1) < 1e-6      # linear in the loss scale, bit-stable reductions
     m.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("cfg,B,S", [((13, 6, 2, 10, 1, 5), 1, 1),        # head_dim 3, nothing 4-aligned, S = B = 1
+                                     ((31, 12, 3, 18, 2, 9), 2, 9),       # head_dim 4, ff not a multiple of 4
+                                     ((64, 40, 5, 100, 1, 70), 3, 70),    # head_dim 8, S > one attention tile
+                                     ((257, 96, 3, 200, 2, 33), 2, 33)])  # head_dim 32 (tcgen05 attention), odd vocab
+def test_odd_shapes_against_oracle(cfg, B, S, precision):
+    """Ragged / unaligned dimensions: whatever mix of tensor-core and CUDA-core kernels the shapes
+    allow must still match the oracle (the reference accepts any embed_dim % num_heads == 0)."""
+    rng = np.random.default_rng(sum(cfg) + B + S)
+    np.random.seed(sum(cfg))
+    oracle = OracleTransformer(*cfg, dropout_p=0.0)
+    for n in ("b1", "b2", "b_vocab", "ln1_beta", "ln2_beta"):
+        oracle.params[n][...] = rng.uniform(-0.1, 0.1, oracle.params[n].shape)
+    m = Transformer(*cfg, dropout_p=0.0, precision=precision)
+    m.load_params(oracle.params)
+    x = rng.integers(1, cfg[0], (B, S)).astype(np.int32)
+    if S > 4:
+        x[0, S - 2:] = 0
+    y = rng.integers(0, cfg[0], (B, S)).astype(np.int32)
+    logits, cache = m.forward(x)
+    loss, dlogits = m.calculate_loss_dlogits(logits, y)
+    grads = m.backward(cache, dlogits)
+    lo, co = oracle.forward(x)
+    want_loss, dlo = oracle.calculate_loss_dlogits(lo, y)
+    go = oracle.backward(co, dlo)
+    tol = TOL[precision]
+    assert rel_err(logits.get(), lo) < tol["act"]
+    assert abs(float(loss) - float(want_loss)) < tol["loss"] * max(1.0, abs(float(want_loss)))
+    for k in NAMES:
+        if np.linalg.norm(go[k]) < 1e-12:      # e.g. dWq, dWk at S == 1: exactly zero in exact arithmetic
+            assert np.max(np.abs(grads[k].get())) < 1e-6, k
+        else:
+            assert rel_err(grads[k].get(), go[k]) < tol["grad"], (k, rel_err(grads[k].get(), go[k]))
+    if S == 1:
+        m.close()
+        return                                  # Adam on exactly-zero gradients amplifies round-off signs
+    m.step(grads, 1e-3)
+    oracle.step(go, 1e-3)
+    for k in NAMES:
+        check_params(getattr(m, k).get(), oracle.params[k], tol["param"], 1e-3, 1, k)
+    m.close()
