@@ -38,6 +38,9 @@ WORKLOADS = {
     "c3": (3, 256, 8, 1024, 320, 16, 32768),
     "c2": (3, 256, 8, 1024, 320, 16, 574),
     "tiny": (2, 64, 2, 128, 32, 4, 120),
+    # the reference's own default script (BASELINE.json configs[0]): prefix dataset, last-token loss,
+    # driven through the train_transformer loop; S is max_len, sequences are trimmed per batch
+    "c1": (3, 256, 8, 1024, 320, 16, 574),
 }
 METRIC = "train tokens/s"
 
@@ -365,6 +368,70 @@ def gemm_roofline(torch, _lib, N, E, F, precision):
             "ms_per_launch": ms, "peak_note": "TF32 dense = 1/2 of the %s burst BF16 peak" % peaks["source"]}
 
 
+def synthetic_prefix_dataset(V, max_len, n_sent=69, seed=0):
+    """Every prefix of every sentence, right-padded (transformer_train.py:47-60), on synthetic sentences
+    with the mini corpus' statistics (69 sentences -> ~1.4k prefixes, ~20k non-PAD tokens)."""
+    rng = np.random.default_rng(seed)
+    X, Y = [], []
+    for _ in range(n_sent):
+        n = int(rng.integers(8, 36))
+        ids = [2] + [int(v) for v in rng.integers(3, V, n)]
+        for i in range(1, len(ids)):
+            X.append(ids[:i][-max_len:] + [0] * max(0, max_len - i))
+            Y.append(ids[i])
+    return np.array(X, dtype=np.int32), np.array(Y, dtype=np.int32)
+
+
+def run_driver(args, wl):
+    """Workload c1: one epoch of the reference driver loop (last-token loss, B16, clip 1.0, Adam 1e-4)."""
+    import torch
+    from nlpscratch_b200 import Transformer
+    from nlpscratch_b200.train import train_transformer
+    from oracle.transformer_oracle import OracleTransformer, last_token_step
+    L, E, h, F, S, B, V = wl
+    X, Y = synthetic_prefix_dataset(V, S)
+    nonpad = int((X != 0).sum())
+    if args.impl == "reference":
+        np.random.seed(0)
+        oracle = OracleTransformer(V, E, h, F, L, S, dropout_p=0.1)
+        t0, tok, steps = time.perf_counter(), 0, 0
+        for i in range(0, len(Y), B):
+            last_token_step(oracle, X[i:i + B], Y[i:i + B], lr=1e-4, clip=1.0)
+            tok += int((X[i:i + B] != 0).sum()); steps += 1
+            if time.perf_counter() - t0 > 60:
+                break
+        dt = time.perf_counter() - t0
+        line = {"impl": "reference", "metric": METRIC, "value": tok / dt, "unit": "non-pad tokens/s", "n_gpus": 1,
+                "steps": steps, "warmup": 0, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "c1: reference driver loop, last-token loss, %d prefixes x max_len %d, B%d" % (len(Y), S, B)},
+                "cpu_baseline": {"value": tok / dt, "unit": "non-pad tokens/s", "cores": os.cpu_count(), "kind": "port",
+                                 "sample": "%d batches of the epoch" % steps},
+                "e2e": {"value": tok / dt, "unit": "non-pad tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    np.random.seed(0)
+    model = Transformer(V, E, h, F, L, S, dropout_p=args.dropout, precision=args.precision)
+    quiet = lambda *_a, **_k: None
+    train_transformer(model, X, Y, learning_rate=1e-4, nepoch=1, evaluation_loss_after=1, batch_size=B,
+                      print_every=0, clip_grad_norm=1.0, log=quiet)          # warm-up epoch
+    model.launch_count(reset=True)
+    torch.cuda.synchronize()
+    stats = train_transformer(model, X, Y, learning_rate=1e-4, nepoch=max(1, args.steps // 10), evaluation_loss_after=10 ** 9,
+                              batch_size=B, print_every=0, clip_grad_norm=1.0, log=quiet)
+    tok_s = stats["tokens"] / stats["train_seconds"]
+    line = {"metric": METRIC, "value": tok_s, "unit": "non-pad tokens/s", "n_gpus": 1, "steps": stats["steps"], "warmup": 90,
+            "ms_per_step": 1e3 * stats["train_seconds"] / stats["steps"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "c1: reference driver loop (nlpscratch_b200.train.train_transformer), last-token loss, "
+                                   "%d prefixes x max_len %d (%d non-PAD tokens/epoch), B%d, host->device copy of the dataset "
+                                   "and shuffles inside the timed region" % (len(Y), S, nonpad, B)},
+            "gpu_launches": model.launch_count(),
+            "e2e": {"value": tok_s, "unit": "non-pad tokens/s", "h2d_bytes_per_step": int(X.nbytes / max(1, stats["steps"])),
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -378,6 +445,10 @@ def main():
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (for ncu launch lists)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    if args.workload == "c1":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_driver(args, wl)
+        return
     if args.impl == "reference":
         run_reference(args, wl)
         return

@@ -148,6 +148,12 @@ int nlps_adam_t(nlps_model* m, int64_t* t, int set, int64_t value);
 int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t x_row_stride,
                     const int32_t* d_y, float lr, float max_norm, float grad_scale,
                     int defer_update, float* d_loss);
+/* Fused step of the reference driver's hot loop (utils/train.py:104-131): hidden-only forward on the
+ * trimmed batch, H_last = H[arange(B), t], logits_last = H_last W_vocab + b_vocab, loss on B rows,
+ * backward_last_token, clip, step -- no host synchronisation.  d_t: (B,) int32 = lens - 1. */
+int nlps_train_step_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t x_row_stride,
+                               const int32_t* d_t, const int32_t* d_y, float lr, float max_norm,
+                               float grad_scale, int defer_update, float* d_loss);
 int nlps_launch_count(nlps_model* m, int64_t* launches, int reset);  /* kernels launched so far */
 
 /* ---- stand-alone operators (tests, the array shim and the benchmarks call these) --------- */

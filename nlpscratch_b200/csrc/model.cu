@@ -734,6 +734,35 @@ int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs
   return nlps_step(m, lr, max_norm > 0.f ? 1 : 0);
 }
 
+int nlps_train_step_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_t,
+                               const int32_t* d_y, float lr, float max_norm, float grad_scale, int defer_update,
+                               float* d_loss) {
+  NLPS_REQUIRE(m && c && d_x && d_t && d_y, "nlps_train_step_last_token: null argument");
+  NLPS_TRY(nlps_forward(m, c, d_x, xs, 1, nullptr, 0));
+  const int B = c->B, E = m->E;
+  const float* h_final = m->L > 0 ? c->layers.back().y2 : c->h0;
+  // H_last (B,E) then logits_last (B,ldV) live at the head of the cache's logits buffer (N*ldV >= B*(E+ldV)
+  // does not hold for tiny vocabularies, so use the row scratch)
+  const int64_t off_h = round_up(2 * (int64_t)B * E + B, kAlign);          // after backward_last_token's own use
+  const int64_t off_l = off_h + round_up((int64_t)B * E, kAlign);
+  NLPS_TRY(ensure_rows_tmp(m, off_l + (int64_t)B * m->ldV));
+  float* h_last = m->rows_tmp + off_h;
+  float* logits = m->rows_tmp + off_l;
+  NLPS_TRY(gather_last(m->stream, B, c->S, E, h_final, d_t, h_last));
+  {
+    GemmArgs g = gemm_nn(B, m->V, E, h_last, E, m->P + m->off_Wvocab, m->ldV, logits, m->ldV);
+    g.bias = m->P + m->off_bvocab;
+    NLPS_TRY(gemm_dispatch(m->stream, m->precision, g));
+  }
+  float* loss = d_loss ? d_loss : m->scalars + 3;
+  // row-loss scratch: the first B floats of rows_tmp are free until backward_last_token runs
+  NLPS_TRY(softmax_xent(m->stream, logits, m->ldV, d_y, B, m->V, grad_scale, loss, logits, m->ldV, m->rows_tmp));
+  NLPS_TRY(nlps_backward_last_token(m, c, d_t, logits, m->ldV));
+  if (defer_update) return 0;
+  if (max_norm > 0.f) NLPS_TRY(nlps_clip_compute(m, max_norm));
+  return nlps_step(m, lr, max_norm > 0.f ? 1 : 0);
+}
+
 int nlps_launch_count(nlps_model*, int64_t* launches, int reset) {
   const long long n = launch_count(reset != 0);
   if (launches) *launches = n;

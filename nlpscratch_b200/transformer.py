@@ -415,6 +415,38 @@ class Transformer:
         object.__setattr__(self, "_last_y", yd)
         return DeviceScalar(loss)
 
+    def train_step_last_token(self, xb, yb, lens=None, learning_rate=1e-4, clip_grad_norm: Optional[float] = 1.0,
+                              grad_scale: float = 1.0, defer_update: bool = False) -> DeviceScalar:
+        """One iteration of the reference driver's hot loop (utils/train.py:104-131) as a single call:
+        forward on the (already trimmed) batch, last-real-token vocab head, loss, backward_last_token,
+        clip, Adam -- with no host synchronisation.  ``lens`` = non-PAD length per row (host or device
+        int array); computed on the device when omitted."""
+        xd = self._ids_to_device(xb)
+        yd = yb if isinstance(yb, DeviceArray) else DeviceArray.from_host(np.asarray(yb), np.int32)
+        B, S = xd.shape
+        if yd.shape != (B,):
+            raise ValueError("yb %s must have shape (%d,)" % (yd.shape, B))
+        if yd.bounds is not None and not (0 <= yd.bounds[0] and yd.bounds[1] < self.vocab_size):
+            raise IndexError("target id out of bounds for %d classes" % self.vocab_size)
+        if lens is None:
+            t = b200np.sum(xd != 0, axis=1) - 1
+        elif isinstance(lens, DeviceArray):
+            t = lens - 1
+        else:
+            t = DeviceArray.from_host(np.asarray(lens, dtype=np.int64) - 1, np.int32)
+        t, yd = t.contiguous(), yd.contiguous()
+        ch = C.c_void_p()
+        _lib.call("nlps_cache_create", self._h, C.c_int(B), C.c_int(S), C.byref(ch))
+        cache = Cache(self, ch, B, S, xd)
+        loss = DeviceArray.empty((), np.float32)
+        _lib.call("nlps_train_step_last_token", self._h, ch, _lib.vp(xd.ptr), C.c_int64(xd.strides[0] if B > 1 else S),
+                  _lib.vp(t.ptr), _lib.vp(yd.ptr), C.c_float(float(learning_rate)),
+                  C.c_float(float(clip_grad_norm) if clip_grad_norm else 0.0), C.c_float(float(grad_scale)),
+                  C.c_int(int(defer_update)), _lib.vp(loss.ptr))
+        object.__setattr__(self, "_last_cache", cache)
+        object.__setattr__(self, "_last_y", (yd, t))
+        return DeviceScalar(loss)
+
     def apply_update(self, learning_rate, clip_grad_norm: Optional[float] = 1.0):
         """Second half of a deferred ``train_step`` (after the data-parallel all-reduce)."""
         if clip_grad_norm:

@@ -316,3 +316,68 @@ def test_odd_shapes_against_oracle(cfg, B, S, precision):
     for k in NAMES:
         check_params(getattr(m, k).get(), oracle.params[k], tol["param"], 1e-3, 1, k)
     m.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_fused_last_token_step_golden(precision):
+    """nlps_train_step_last_token (the driver's whole iteration in one call) on the reference fixture."""
+    case = load_case("last_token_clip")
+    tol = TOL[precision]
+    m = build(case, precision)
+    lr, clip = float(case["lr"]), float(case["clip"])
+    x, y = case["x"], case["y"]
+    lens = (x != 0).sum(axis=1)
+    for s in range(2):
+        loss = m.train_step_last_token(x[:, :int(lens.max())], y, lens=lens if s == 0 else None,
+                                       learning_rate=lr, clip_grad_norm=clip)
+        assert abs(float(loss) - float(case["loss%d" % s])) < tol["loss"] * 10
+        for k in NAMES:
+            check_params(getattr(m, k).get(), case["p%d_%s" % (s + 1, k)], tol["param"], lr, s + 1, k)
+    m.close()
+
+
+def test_device_resident_train_loop_learns_and_matches_oracle_loop():
+    """nlpscratch_b200.train.train_transformer (mirror of utils/train.py:30-174) on a synthetic prefix
+    dataset: same eval losses as the oracle running the reference loop's arithmetic, loss goes down."""
+    from nlpscratch_b200.train import train_transformer
+    from oracle.transformer_oracle import last_token_step
+    rng = np.random.default_rng(3)
+    V, max_len, n = 60, 24, 96
+    X = np.zeros((n, max_len), np.int32)
+    for i in range(n):
+        L = int(rng.integers(1, max_len))
+        X[i, :L] = (np.arange(L) * 7 + i) % (V - 2) + 2          # learnable pattern
+    Y = ((X[np.arange(n), (X != 0).sum(1) - 1] + 5) % (V - 2) + 2).astype(np.int32)
+    cfg = (V, 32, 4, 64, 2, max_len)
+    np.random.seed(4)
+    oracle = OracleTransformer(*cfg, dropout_p=0.0)
+    m = Transformer(*cfg, dropout_p=0.0, precision="fp32")
+    m.load_params(oracle.params)
+    np.random.seed(123)
+    logs = []
+    stats = train_transformer(m, X, Y, learning_rate=3e-3, nepoch=3, evaluation_loss_after=1, batch_size=16,
+                              print_every=0, clip_grad_norm=1.0, log=logs.append)
+    evals = [l for _, l in stats["losses"]]
+    assert evals[-1] < evals[0] - 0.2                               # it learns
+    # the oracle, driven by the same loop arithmetic and the same shuffles
+    np.random.seed(123)
+    xs, ys = X.copy(), Y.copy()
+
+    def oracle_eval():
+        tot = 0.0
+        for i in range(0, n, 16):
+            xb, yb = xs[i:i + 16], ys[i:i + 16]
+            lens = (xb != 0).sum(1)
+            H, _ = oracle.forward(xb[:, :lens.max()], return_hidden_only=True)
+            lg = H[np.arange(len(yb)), lens - 1] @ oracle.params["W_vocab"] + oracle.params["b_vocab"]
+            tot += float(oracle.calculate_loss_dlogits(lg, yb)[0]) * len(yb)
+        return tot / n
+    want = []
+    for epoch in range(3):
+        want.append(oracle_eval())
+        perm = np.random.permutation(n)
+        xs, ys = xs[perm], ys[perm]
+        for i in range(0, n, 16):
+            last_token_step(oracle, xs[i:i + 16], ys[i:i + 16], lr=3e-3, clip=1.0)
+    assert np.allclose(evals, want, rtol=2e-3, atol=2e-3), (evals, want)
+    m.close()
