@@ -197,6 +197,8 @@ def run_ours(args, wl):
     torch.cuda.set_device(local)
     distributed = world > 1
     if distributed:
+        # keep stdout to the one JSON line (NCCL prints its version banner there at VERSION/INFO level)
+        os.environ["NCCL_DEBUG"] = os.environ.get("NLPS_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     L, E, h, F, S, B, V = wl
     np.random.seed(1234)
