@@ -16,6 +16,7 @@
 #include "tc_common.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace nlps {
 namespace {
@@ -25,10 +26,12 @@ constexpr int BQ = 128;         // query rows per CTA == TMEM lanes
 constexpr int BKV = 64;         // keys per block
 constexpr int kThreads = 192;   // warp0 TMA, warp1 MMA + TMEM owner, warps2-5 softmax
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kMaxPadBlocks = 64;
 
 struct Dims {
   int B, S, h, E;
   float scale_log2;   // (1/sqrt(d)) * log2(e)
+  int trace;
 };
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -42,6 +45,10 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// NLPS_ATTN_TRACE=1: CTA (3,0,0) of the forward kernel records clock64() at its pipeline events
+__device__ long long g_attn_trace[4096];
+__device__ __forceinline__ void trace(bool on, int slot) { if (on) g_attn_trace[slot] = clock64(); }
+
 template <int D>
 struct FwdCfg {
   static constexpr int kAtoms = D / 32;                 // 128-byte K atoms per row
@@ -49,7 +56,7 @@ struct FwdCfg {
   static constexpr int kKBytes = kAtoms * BKV * 128;    // [atom][64 rows][128 B]
   static constexpr int kVBytes = kAtoms * BKV * 128;    // [slab of 32 dims][64 key rows][128 B]
   static constexpr int kPBytes = (BKV / 32) * BQ * 128; // [atom of 32 keys][128 rows][128 B]
-  static constexpr int kBarBytes = 128;
+  static constexpr int kBarBytes = 1024;                // barriers (128 B) + PAD bit masks of up to 64 key blocks
   static constexpr int kSmemBytes = kQBytes + kKBytes + kVBytes + kPBytes + kBarBytes + 1024;
   static constexpr int kTmemCols = 128;                 // S: 64 columns, O block: D columns
 };
@@ -74,6 +81,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_fwd_tc(const __grid_constant
   const uint32_t q_full = bar, k_full = bar + 8, k_empty = bar + 16, s_full = bar + 24, p_full = bar + 32,
                  o_full = bar + 40, o_read = bar + 48, v_full = bar + 56, v_empty = bar + 64, tmem_slot = bar + 72;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(p_ptr + Cfg::kPBytes + 72);
+  unsigned long long* padmask_s = reinterpret_cast<unsigned long long*>(p_ptr + Cfg::kPBytes + 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * BQ;
@@ -82,6 +90,8 @@ __global__ void __launch_bounds__(kThreads, 2) attn_fwd_tc(const __grid_constant
   const int n_all = (p.S + BKV - 1) / BKV;
   const int n_kv = deg_block ? n_all : min(n_all, (q0 + BQ - 1) / BKV + 1);
   const int row_base = b * p.S;                       // first row of this sequence in the (B*S, 3E) matrix
+  const bool tr = p.trace && blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0;
+  trace(tr && threadIdx.x == 0, 0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
@@ -108,11 +118,13 @@ __global__ void __launch_bounds__(kThreads, 2) attn_fwd_tc(const __grid_constant
       for (int kb = 0; kb < n_kv; ++kb) {
         const int krow = row_base + kb * BKV;
         mbar_wait(k_empty, (uint32_t)(kb & 1) ^ 1u);
+        trace(tr, 100 + kb * 2);
         mbar_expect_tx(k_full, Cfg::kKBytes);
 #pragma unroll
         for (int a = 0; a < Cfg::kAtoms; ++a)
           tma_load_2d(k_s + a * (BKV * 128), &map_k, k_full, p.E + head * D + a * 32, krow);
         mbar_wait(v_empty, (uint32_t)(kb & 1) ^ 1u);
+        trace(tr, 101 + kb * 2);
         mbar_expect_tx(v_full, Cfg::kVBytes);
 #pragma unroll
         for (int a = 0; a < Cfg::kAtoms; ++a)
@@ -129,6 +141,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_fwd_tc(const __grid_constant
       for (int kb = 0; kb < n_kv; ++kb) {
         const uint32_t ph = (uint32_t)(kb & 1);
         mbar_wait(k_full, ph);
+        trace(tr, 200 + kb * 4);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < D / 8; ++kk) {
@@ -138,9 +151,12 @@ __global__ void __launch_bounds__(kThreads, 2) attn_fwd_tc(const __grid_constant
         }
         umma_commit(s_full);
         umma_commit(k_empty);                          // K tile free once S retires
+        trace(tr, 201 + kb * 4);
         mbar_wait(v_full, ph);
+        trace(tr, 202 + kb * 4);
         mbar_wait(p_full, ph);                         // P written (and S consumed) by all 128 rows
         if (kb > 0) mbar_wait(o_read, (uint32_t)((kb - 1) & 1));   // previous O block folded into registers
+        trace(tr, 203 + kb * 4);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < BKV / 8; ++kk) {
@@ -164,13 +180,27 @@ __global__ void __launch_bounds__(kThreads, 2) attn_fwd_tc(const __grid_constant
     float o[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) o[c] = 0.f;
+    // PAD bits of every key block of this sequence, built once by the four softmax warps
+    // (two ballots per block) instead of a dependent global load at the top of every iteration
+    if (n_kv <= kMaxPadBlocks) {
+      for (int kb = q; kb < n_kv; kb += 4) {
+        const int ka = kb * BKV + lane, kb2 = ka + 32;
+        const bool pa = ka < p.S ? (x[(int64_t)b * p.S + ka] == 0) : true;
+        const bool pb = kb2 < p.S ? (x[(int64_t)b * p.S + kb2] == 0) : true;
+        const unsigned long long bits = (unsigned long long)__ballot_sync(0xffffffffu, pa) |
+                                        ((unsigned long long)__ballot_sync(0xffffffffu, pb) << 32);
+        if (lane == 0) padmask_s[kb] = bits;
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+    }
     for (int kb = 0; kb < n_kv; ++kb) {
       const uint32_t ph = (uint32_t)(kb & 1);
       const int k0 = kb * BKV;
       // visibility bits of this row for the 64 keys of the block
-      unsigned long long padbits = 0ull;
-      {
-        // each of the 4 warps builds the block's PAD mask with two ballots (cheap, avoids a CTA sync)
+      unsigned long long padbits;
+      if (n_kv <= kMaxPadBlocks) {
+        padbits = padmask_s[kb];
+      } else {
         const int ka = k0 + lane, kb2 = k0 + 32 + lane;
         const bool pa = ka < p.S ? (x[(int64_t)b * p.S + ka] == 0) : true;
         const bool pb = kb2 < p.S ? (x[(int64_t)b * p.S + kb2] == 0) : true;
@@ -187,46 +217,73 @@ __global__ void __launch_bounds__(kThreads, 2) attn_fwd_tc(const __grid_constant
         const unsigned long long causal = upto < 0 ? 0ull : (upto >= 63 ? ~0ull : ((1ull << (upto + 1)) - 1ull));
         vis = causal & ~padbits & range_bits;
       }
+      const bool trs = tr && threadIdx.x == 64;
+      trace(trs, 300 + kb * 5);
       mbar_wait(s_full, ph);
+      trace(trs, 301 + kb * 5);
       tc_fence_after();
       uint32_t s0[32], s1[32];
       tmem_ld_32x32(tmem_s + lane_addr, s0);
       tmem_ld_32x32(tmem_s + lane_addr + 32, s1);
+      // running max in the exp2 domain: scores are multiplied by scale*log2(e) > 0, so the max of the raw
+      // scores decides; p = exp2(fma(s, scale_log2, -m)) is one FFMA + one MUFU per element
+      const bool all_vis = __all_sync(0xffffffffu, vis == ~0ull);      // interior block: no mask tests at all
       float mx = -INFINITY;
+      if (all_vis) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float a = __uint_as_float(s0[c]) * p.scale_log2, bb = __uint_as_float(s1[c]) * p.scale_log2;
-        s0[c] = __float_as_uint(a); s1[c] = __float_as_uint(bb);
-        if ((vis >> c) & 1ull) mx = fmaxf(mx, a);
-        if ((vis >> (c + 32)) & 1ull) mx = fmaxf(mx, bb);
+        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if ((vis >> c) & 1ull) mx = fmaxf(mx, __uint_as_float(s0[c]));
+          if ((vis >> (c + 32)) & 1ull) mx = fmaxf(mx, __uint_as_float(s1[c]));
+        }
       }
-      const float m_new = fmaxf(m, mx);
+      const float m_new = fmaxf(m, mx * p.scale_log2);
       const float m_use = m_new == -INFINITY ? 0.f : m_new;      // row with no visible key yet
       const float alpha = fast_exp2(m - m_use);                   // exp2(-inf) = 0 when m was -inf
+      const float neg_m = -m_use;
       float rsum = 0.f;
       // P row -> smem, K-major SWIZZLE_128B: [atom of 32 keys][row][8 chunks of 16 B, chunk ^= row & 7]
       uint8_t* prow = p_ptr + r * 128;
+      if (all_vis) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float pv[4];
+        for (int i = 0; i < 16; ++i) {
+          float pv[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = i * 4 + j;
-          const float sv = __uint_as_float(c < 32 ? s0[c & 31] : s1[c & 31]);
-          pv[j] = ((vis >> c) & 1ull) ? fast_exp2(sv - m_use) : 0.f;
-          rsum += pv[j];
+          for (int j = 0; j < 4; ++j) {
+            const int c = i * 4 + j;
+            pv[j] = fast_exp2(fmaf(__uint_as_float(c < 32 ? s0[c & 31] : s1[c & 31]), p.scale_log2, neg_m));
+            rsum += pv[j];
+          }
+          uint4 w = make_uint4(to_tf32(pv[0]), to_tf32(pv[1]), to_tf32(pv[2]), to_tf32(pv[3]));
+          *reinterpret_cast<uint4*>(prow + (i >> 3) * (BQ * 128) + (((i & 7) ^ (r & 7)) << 4)) = w;
         }
-        uint4 w = make_uint4(to_tf32(pv[0]), to_tf32(pv[1]), to_tf32(pv[2]), to_tf32(pv[3]));
-        *reinterpret_cast<uint4*>(prow + (i >> 3) * (BQ * 128) + (((i & 7) ^ (r & 7)) << 4)) = w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float pv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = i * 4 + j;
+            const float e = fast_exp2(fmaf(__uint_as_float(c < 32 ? s0[c & 31] : s1[c & 31]), p.scale_log2, neg_m));
+            pv[j] = ((vis >> c) & 1ull) ? e : 0.f;
+            rsum += pv[j];
+          }
+          uint4 w = make_uint4(to_tf32(pv[0]), to_tf32(pv[1]), to_tf32(pv[2]), to_tf32(pv[3]));
+          *reinterpret_cast<uint4*>(prow + (i >> 3) * (BQ * 128) + (((i & 7) ^ (r & 7)) << 4)) = w;
+        }
       }
       l = l * alpha + rsum;
       m = m_new;
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_full);
+      trace(trs, 302 + kb * 5);
 #pragma unroll
       for (int c = 0; c < D; ++c) o[c] *= alpha;
       mbar_wait(o_full, ph);
+      trace(trs, 303 + kb * 5);
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < D / 32; ++cc) {
@@ -237,7 +294,9 @@ __global__ void __launch_bounds__(kThreads, 2) attn_fwd_tc(const __grid_constant
       }
       tc_fence_before();
       mbar_arrive(o_read);
+      trace(trs, 304 + kb * 5);
     }
+    trace(tr && threadIdx.x == 64, 1);
     if (row < p.S) {
       const float inv = 1.f / l;
       float4* dst = reinterpret_cast<float4*>(ctx + ((int64_t)b * p.S + row) * p.E + head * D);
@@ -270,10 +329,27 @@ int launch_fwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int
     NLPS_CUDA(cudaFuncSetAttribute(attn_fwd_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     once = true;
   }
-  Dims p{B, S, h, E, (float)(1.0 / std::sqrt((double)D)) * kLog2e};
+  static int trace_on = -1;
+  if (trace_on < 0) { const char* e = getenv("NLPS_ATTN_TRACE"); trace_on = (e && e[0] == '1') ? 1 : 0; }
+  Dims p{B, S, h, E, (float)(1.0 / std::sqrt((double)D)) * kLog2e, trace_on};
   dim3 grid((unsigned)ceil_div(S, BQ), (unsigned)h, (unsigned)B);
   attn_fwd_tc<D><<<grid, kThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, p, x, fnp, ctx, lse);
   NLPS_LAUNCH_CHECK();
+  if (trace_on) {
+    static int printed = 0;
+    if (printed++ == 3) {
+      long long h[4096];
+      cudaStreamSynchronize(st);
+      cudaMemcpyFromSymbol(h, g_attn_trace, sizeof(h));
+      const long long t0 = h[0];
+      printf("attn_fwd trace (cycles since CTA start), CTA end of loop at %lld\n", h[1] - t0);
+      for (int kb = 0; kb < 8; ++kb)
+        printf("kb %d | TMA K issue %6lld V issue %6lld | MMA k_full %6lld S issued %6lld v_full %6lld p+o ready %6lld | softmax wait_s %6lld s_full %6lld P arrived %6lld o_full %6lld o done %6lld\n",
+               kb, h[100 + kb * 2] - t0, h[101 + kb * 2] - t0, h[200 + kb * 4] - t0, h[201 + kb * 4] - t0, h[202 + kb * 4] - t0,
+               h[203 + kb * 4] - t0, h[300 + kb * 5] - t0, h[301 + kb * 5] - t0, h[302 + kb * 5] - t0, h[303 + kb * 5] - t0, h[304 + kb * 5] - t0);
+      fflush(stdout);
+    }
+  }
   return 0;
 }
 
@@ -696,7 +772,7 @@ int launch_bwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int
     NLPS_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemDq));
     once = true;
   }
-  Dims p{B, S, h, E, (float)(1.0 / std::sqrt((double)D)) * kLog2e};
+  Dims p{B, S, h, E, (float)(1.0 / std::sqrt((double)D)) * kLog2e, 0};
   dim3 grid((unsigned)ceil_div(S, 128), (unsigned)h, (unsigned)B);
   attn_bwd_dkdv_tc<D><<<grid, kThreads, Cfg::kSmemDkdv, st>>>(res, qk, qmn, dok, domn, p, x, fnp, lse, delta, dqkv);
   NLPS_LAUNCH_CHECK();
