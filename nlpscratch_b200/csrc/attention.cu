@@ -524,10 +524,11 @@ int check_dims(int B, int S, int h, int d) {
 
 }  // namespace
 
-// NLPS_ATTN=mma forces the mma.sync kernels where the tcgen05 ones would run (A/B measurements)
+// NLPS_ATTN=mma forces the mma.sync kernels where the tcgen05 ones would run, NLPS_ATTN=ss the first-generation
+// tcgen05 kernels (operands in shared memory) where the TMEM-operand ones would run (A/B measurements)
 static int attn_impl() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("NLPS_ATTN"); v = (e && e[0] == 'm') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("NLPS_ATTN"); v = (e && e[0] == 'm') ? 1 : ((e && e[0] == 's') ? 2 : 0); }
   return v;
 }
 
@@ -540,7 +541,7 @@ int first_nonpad(cudaStream_t st, int B, int S, const int32_t* x, int32_t* out) 
 int attention_forward(cudaStream_t st, int precision, int B, int S, int h, int d, const float* qkv,
                       const int32_t* x, const int32_t* fnp, float* ctx, float* lse) {
   NLPS_TRY(check_dims(B, S, h, d));
-  if (precision == 1 && attention_tc_supported(d, h * d, qkv) && attn_impl() == 0)
+  if (precision == 1 && attention_tc_supported(d, h * d, qkv) && attn_impl() != 1)
     return attention_forward_tc(st, B, S, h, d, qkv, x, fnp, ctx, lse);
   if (precision == 1 && d <= 64 && d % 4 == 0) return attention_forward_mma(st, B, S, h, d, qkv, x, fnp, ctx, lse);
   AttnDims p{B, S, h, d, h * d, (float)(1.0 / sqrt((double)d))};
@@ -566,9 +567,11 @@ int attention_backward(cudaStream_t st, int precision, int B, int S, int h, int 
   else if (vec && d == 8) attn_delta_vec_kernel<2><<<vgrid, 256, 0, st>>>(p, ntok, ctx, dctx, delta);
   else attn_delta_kernel<<<(unsigned)ntok, std::min(1024, 32 * h), 0, st>>>(p, ctx, dctx, delta);
   NLPS_LAUNCH_CHECK();
-  if (precision == 1 && attention_tc_supported(d, h * d, qkv) && attn_impl() == 0 &&
-      (reinterpret_cast<uintptr_t>(dctx) & 15u) == 0)
-    return attention_backward_tc(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv);
+  if (precision == 1 && attention_tc_supported(d, h * d, qkv) && attn_impl() != 1 &&
+      (reinterpret_cast<uintptr_t>(dctx) & 15u) == 0) {
+    if (attn_impl() == 2) return attention_backward_tc(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv);
+    return attention_backward_ts(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv);
+  }
   if (precision == 1 && d <= 64 && d % 4 == 0) return attention_backward_mma(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv);
   if (d <= 8) return bwd_launch<8>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
   if (d <= 16) return bwd_launch<16>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);

@@ -1,0 +1,774 @@
+// Fused causal + key-padding attention BACKWARD on tcgen05 with the A operands in tensor memory
+// ("TS" form of tcgen05.mma), head_dim 32 or 64.  Replaces transformer.py:427-441 (recomputed P@V,
+// softmax_backward, dQ/dK/dV) together with the masks of :116-118; same outputs as attention.cu.
+//
+// Why TS: with FP32 (TF32) operands an SS-mode M=128,N=64 MMA reads 6 KB of shared memory per 32-cycle
+// instruction -- more than the 128 B/clk the SM has -- and the P / dS tiles have to bounce through shared
+// memory.  Here every A operand lives in TMEM:
+//   * the CTA's resident tile (K and V in the dK/dV kernel, Q and dO in the dQ kernel) is copied
+//     smem -> TMEM once in the prologue;
+//   * the softmax threads overwrite S with P (and dP with dS) in place in TMEM (tcgen05.st), FA4 style.
+// Shared memory then only holds the streamed B operands, NS stages deep, and the tensor pipe, the TMA
+// and the 8 softmax warps run concurrently: S/dP accumulators are double-buffered in TMEM so the MMA
+// warp issues the products of block it+1 / it+2 while the threads work on block it.
+//
+//   dK/dV kernel: CTA = (batch, head, 128 keys); thread (r, half) owns key r and 32 of the 64 queries of a
+//     block.  S^T = K Q^T and dP^T = V dO^T (M = keys), P^T and dS^T = P^T o (dP^T - delta) in place,
+//     dV += P^T dO and dK += dS^T Q accumulate in TMEM over the whole loop.  No atomics.
+//   dQ kernel:    CTA = (batch, head, 128 queries); S = Q K^T, dP = dO V^T, dS in place, dQ += dS K.
+#include "tc_common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+namespace nlps {
+namespace {
+using namespace tc;
+
+constexpr int kThreads = 320;   // warp0 TMA + lse/delta staging, warp1 MMA + TMEM owner, warps 2-9 softmax
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kTraceSlots = 4096;
+
+struct Dims {
+  int B, S, h, E;
+  float scale_log2;   // (1/sqrt(d)) * log2(e)
+  int trace;
+};
+
+__device__ long long g_ts_trace[kTraceSlots];
+__device__ __forceinline__ void trace(bool on, int slot) { if (on && slot < kTraceSlots) g_ts_trace[slot] = clock64(); }
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t low_bits32(int n) {   // n lowest bits set, n clamped to [0,32]
+  return n <= 0 ? 0u : (n >= 32 ? ~0u : ((1u << n) - 1u));
+}
+
+// one lane of a converged warp (lets the compiler issue tcgen05.mma without a per-instruction election loop)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// packed FP32x2 arithmetic (FFMA2 / FADD2 / FMUL2 on sm_100): halves the issue slots of the per-element math
+__device__ __forceinline__ uint64_t pack2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) { return pack2(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ void unpack2(uint64_t v, uint32_t& lo, uint32_t& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// round-to-nearest (ties away) onto the TF32 grid for finite values: the tensor core ignores the low 13
+// mantissa bits, so adding half a TF32 ulp to the bit pattern is all cvt.rna.tf32 would do
+__device__ __forceinline__ uint32_t rna_tf32_bits(uint32_t bits) { return bits + 0x1000u; }
+
+// P (optional) and dS for two adjacent columns.  s2/dp2: raw scores and dP; nl2: -lse*log2e; ndl2: -delta
+template <bool MASKED, bool WANT_P>
+__device__ __forceinline__ void p_ds_pair(uint32_t& s_lo, uint32_t& s_hi, uint32_t& d_lo, uint32_t& d_hi, uint64_t scale2,
+                                          uint64_t nl2, uint64_t ndl2, uint32_t vis, int c) {
+  uint32_t x_lo, x_hi;
+  unpack2(ffma2(pack2(s_lo, s_hi), scale2, nl2), x_lo, x_hi);
+  float e0 = fast_exp2(__uint_as_float(x_lo)), e1 = fast_exp2(__uint_as_float(x_hi));
+  if (MASKED) {
+    e0 = (vis & (1u << c)) ? e0 : 0.f;
+    e1 = (vis & (2u << c)) ? e1 : 0.f;
+  }
+  uint32_t r_lo, r_hi;
+  unpack2(fmul2(pack2f(e0, e1), fadd2(pack2(d_lo, d_hi), ndl2)), r_lo, r_hi);
+  if (WANT_P) {
+    s_lo = rna_tf32_bits(__float_as_uint(e0));
+    s_hi = rna_tf32_bits(__float_as_uint(e1));
+  }
+  d_lo = rna_tf32_bits(r_lo);
+  d_hi = rna_tf32_bits(r_hi);
+}
+
+// [128 rows][D floats] tile in shared memory, 16-byte chunks XOR-swizzled by (row & 7): thread-per-row writes and
+// warp-per-row reads are both bank-conflict free
+template <int D>
+__device__ __forceinline__ void tile_put_row32(uint8_t* tile, int r, int col0, const uint32_t (&v)[32], float scale) {
+  uint8_t* row = tile + r * (D * 4);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int chunk = (col0 >> 2) + j;
+    *reinterpret_cast<float4*>(row + ((chunk ^ (r & 7)) << 4)) =
+        make_float4(__uint_as_float(v[4 * j]) * scale, __uint_as_float(v[4 * j + 1]) * scale,
+                    __uint_as_float(v[4 * j + 2]) * scale, __uint_as_float(v[4 * j + 3]) * scale);
+  }
+}
+// rows [0, n_rows) of the tile -> global rows of stride ld floats, one coalesced row per warp instruction
+template <int D>
+__device__ __forceinline__ void tile_store_rows(const uint8_t* tile, float* out, int64_t ld, int n_rows, int warp8, int lane) {
+  for (int r = warp8; r < n_rows; r += 8) {
+    const uint8_t* row = tile + r * (D * 4);
+    if (D == 64) {
+      const float2 v = *reinterpret_cast<const float2*>(row + (((lane >> 1) ^ (r & 7)) << 4) + ((lane & 1) << 3));
+      *reinterpret_cast<float2*>(out + r * ld + 2 * lane) = v;
+    } else {
+      const float v = *reinterpret_cast<const float*>(row + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+      out[r * ld + lane] = v;
+    }
+  }
+}
+
+// one 128-byte row (32 floats) of a K-major SWIZZLE_128B tile [rows][128 B] -> registers
+__device__ __forceinline__ void load_swizzled_row(const uint8_t* tile, int r, uint32_t (&v)[32]) {
+  const uint8_t* row = tile + r * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint4 w = *reinterpret_cast<const uint4*>(row + ((j ^ (r & 7)) << 4));
+    v[4 * j] = w.x; v[4 * j + 1] = w.y; v[4 * j + 2] = w.z; v[4 * j + 3] = w.w;
+  }
+}
+
+template <int D, int NS>
+struct Cfg {
+  static constexpr int kAtoms = D / 32;                      // 128-byte atoms per row
+  static constexpr int kBlk = kAtoms * 64 * 128;             // a streamed 64-row operand tile
+  static constexpr int kStage = 2 * kBlk;                    // two tiles per stage (also = one resident 128-row tile)
+  static constexpr int kCtl = 2048;                          // barriers (256 B) + lse/delta stages (2 x 2 x 64 floats)
+  static constexpr int kSmemDkdv = 2 * NS * kStage + kCtl + 1024;
+  static constexpr int kSmemDq = NS * kStage + NS * kBlk + kCtl + 1024;
+  static constexpr int kTmemCols = 512;
+};
+
+// ============================================================================================
+// dK / dV
+// ============================================================================================
+template <int D, int NS>
+__global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ts(const __grid_constant__ CUtensorMap map_res,   // qkv, box {32,128}, K-major
+                                                              const __grid_constant__ CUtensorMap map_qk,    // qkv, box {32,64}, K-major
+                                                              const __grid_constant__ CUtensorMap map_qmn,   // qkv, box {32,64}, MN-major
+                                                              const __grid_constant__ CUtensorMap map_dok,   // dctx, box {32,64}, K-major
+                                                              const __grid_constant__ CUtensorMap map_domn,  // dctx, box {32,64}, MN-major
+                                                              const Dims p, const int32_t* __restrict__ x,
+                                                              const int32_t* __restrict__ fnp,
+                                                              const float* __restrict__ lse,
+                                                              const float* __restrict__ delta,
+                                                              float* __restrict__ dqkv) {
+  using C = Cfg<D, NS>;
+  static_assert(NS >= 2, "the prologue parks K and V in the first two MN stages");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t kst = base;                                  // NS stages of [Q K-major | dO K-major]
+  const uint32_t mst = base + NS * C::kStage;                 // NS stages of [Q MN-major | dO MN-major]
+  uint8_t* mst_ptr = base_ptr + NS * C::kStage;
+  const uint32_t bar = base + 2 * NS * C::kStage;
+  uint8_t* ctl_ptr = base_ptr + 2 * NS * C::kStage;
+  // barriers
+  auto kfull = [&](int s) { return bar + 8u * s; };
+  auto kfree = [&](int s) { return bar + 8u * (4 + s); };
+  auto mfull = [&](int s) { return bar + 8u * (8 + s); };
+  auto mfree = [&](int s) { return bar + 8u * (12 + s); };
+  auto sdp_full = [&](int b2) { return bar + 8u * (16 + b2); };
+  auto pds_full = [&](int b2) { return bar + 8u * (18 + b2); };
+  auto ld_full = [&](int b2) { return bar + 8u * (20 + b2); };
+  const uint32_t kv_full = bar + 8u * 22, kv_done = bar + 8u * 23, acc_full = bar + 8u * 24, tmem_slot = bar + 8u * 25;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ctl_ptr + 8 * 25);
+  float* lse_s = reinterpret_cast<float*>(ctl_ptr + 256);     // [2][64]  -lse*log2e
+  float* delta_s = lse_s + 128;                               // [2][64]  -delta
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, head = blockIdx.y;
+  const int k0 = ((int)gridDim.x - 1 - (int)blockIdx.x) * 128;   // heavy (early-key) tiles are scheduled first
+  const int first_real = fnp[b];
+  const int row_base = b * p.S;
+  const int n_q = (p.S + 63) / 64;
+  const int first_causal = k0 / 64;                               // first query block with q >= some key here
+  const int n_deg = min(min((first_real + 63) / 64, n_q), first_causal);
+  const int n_it = n_deg + (n_q - first_causal);
+  auto block_of = [&](int it) { return it < n_deg ? it : it - n_deg + first_causal; };
+  const bool tr = p.trace && blockIdx.x == gridDim.x - 1 && blockIdx.y == 0 && blockIdx.z == 0;
+  trace(tr && threadIdx.x == 0, 0);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(kfull(s), 1); mbar_init(kfree(s), 1); mbar_init(mfull(s), 1); mbar_init(mfree(s), 1); }
+    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(sdp_full(b2), 1); mbar_init(pds_full(b2), 256); mbar_init(ld_full(b2), 32); }
+    mbar_init(kv_full, 1); mbar_init(kv_done, 256); mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+    // the resident K and V tiles start moving before the TMEM allocation / setup barrier
+    mbar_expect_tx(kv_full, 2 * C::kStage);
+#pragma unroll
+    for (int a = 0; a < C::kAtoms; ++a) {
+      tma_load_2d(mst + a * (128 * 128), &map_res, kv_full, p.E + head * D + a * 32, row_base + k0);
+      tma_load_2d(mst + C::kStage + a * (128 * 128), &map_res, kv_full, 2 * p.E + head * D + a * 32, row_base + k0);
+    }
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t t_k = tmem, t_v = tmem + D, t_st = tmem + 2 * D, t_dpt = t_st + 128, t_dv = t_dpt + 128, t_dk = t_dv + D;
+
+  if (warp == 0) {
+    // ---------------- producer: TMA + lse/delta staging ----------------
+    const int64_t so = ((int64_t)b * p.h + head) * p.S;
+    // lse/delta of a block are fetched one iteration ahead so that their latency never stalls the TMA lane
+    // (raw values only: any arithmetic on them here would make the warp wait for the loads right away)
+    float nl_r[2], nd_r[2];
+    auto fetch_ld = [&](int it) {
+      const int q0 = block_of(it) * 64;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int qi = min(q0 + lane + 32 * j, p.S - 1);
+        nl_r[j] = __ldg(lse + so + qi);
+        nd_r[j] = __ldg(delta + so + qi);
+      }
+    };
+    fetch_ld(0);
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % NS;
+      const uint32_t free_par = (uint32_t)((it / NS) & 1) ^ 1u;
+      const int q0 = block_of(it) * 64;
+      if (lane == 0) {
+        const int qrow = row_base + q0;
+        mbar_wait(kfree(s), free_par);
+        trace(tr, 100 + it * 2);
+        mbar_expect_tx(kfull(s), C::kStage);
+#pragma unroll
+        for (int a = 0; a < C::kAtoms; ++a) {
+          tma_load_2d(kst + s * C::kStage + a * (64 * 128), &map_qk, kfull(s), head * D + a * 32, qrow);
+          tma_load_2d(kst + s * C::kStage + C::kBlk + a * (64 * 128), &map_dok, kfull(s), head * D + a * 32, qrow);
+        }
+        if (it == 0) mbar_wait(kv_done, 0);          // K and V have left the first two MN stages
+        mbar_wait(mfree(s), free_par);
+        trace(tr, 101 + it * 2);
+        mbar_expect_tx(mfull(s), C::kStage);
+#pragma unroll
+        for (int a = 0; a < C::kAtoms; ++a) {
+          tma_load_2d(mst + s * C::kStage + a * (64 * 128), &map_qmn, mfull(s), head * D + a * 32, qrow);
+          tma_load_2d(mst + s * C::kStage + C::kBlk + a * (64 * 128), &map_domn, mfull(s), head * D + a * 32, qrow);
+        }
+      }
+      __syncwarp();
+      // lse / delta of the 64 queries of this block (2 per lane), exp2 domain, negated for the FFMA
+      const int b2 = it & 1;
+      if (it >= 2) mbar_wait(pds_full(b2), (uint32_t)(((it - 2) >> 1) & 1));   // threads are done with this stage
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        lse_s[b2 * 64 + lane + 32 * j] = -nl_r[j] * kLog2e;     // columns past the sequence end are masked by vis
+        delta_s[b2 * 64 + lane + 32 * j] = -nd_r[j];
+      }
+      mbar_arrive(ld_full(b2));
+      if (it + 1 < n_it) fetch_ld(it + 1);
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: the warp stays converged, one elected lane issues ----------------
+    constexpr uint32_t idesc_t = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    auto issue_sdp = [&](int it) {        // S^T = K Q^T ; dP^T = V dO^T   (A = K / V in TMEM)
+      const int s = it % NS, b2 = it & 1;
+      mbar_wait(kfull(s), (uint32_t)((it / NS) & 1));
+      tc_fence_after();
+      trace(tr && lane == 0, 200 + it * 4);
+      if (elect_one_sync()) {
+        const uint64_t qk = make_desc(kst + s * C::kStage, 16, 1024, 2), dok = make_desc(kst + s * C::kStage + C::kBlk, 16, 1024, 2);
+#pragma unroll
+        for (int kk = 0; kk < D / 8; ++kk) {
+          const uint64_t bo = (uint64_t)(((kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4);
+          umma_tf32_ts(t_st + b2 * 64, t_k + kk * 8, qk + bo, idesc_t, kk > 0 ? 1u : 0u);
+          umma_tf32_ts(t_dpt + b2 * 64, t_v + kk * 8, dok + bo, idesc_t, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(sdp_full(b2));
+        umma_commit(kfree(s));
+      }
+      __syncwarp();
+      trace(tr && lane == 0, 201 + it * 4);
+    };
+    mbar_wait(kv_done, 0);
+    tc_fence_after();
+    issue_sdp(0);
+    if (n_it > 1) issue_sdp(1);
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % NS, b2 = it & 1;
+      mbar_wait(mfull(s), (uint32_t)((it / NS) & 1));
+      trace(tr && lane == 0, 500 + it);
+      mbar_wait(pds_full(b2), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      trace(tr && lane == 0, 202 + it * 4);
+      if (elect_one_sync()) {
+        const uint64_t qmn = make_desc(mst + s * C::kStage, 64 * 128, 512, 1), domn = make_desc(mst + s * C::kStage + C::kBlk, 64 * 128, 512, 1);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {      // dV += P^T dO ; dK += dS^T Q   (K = 64 queries, A = P^T / dS^T in TMEM)
+          const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+          umma_tf32_ts(t_dv, t_st + b2 * 64 + kk * 8, domn + (uint64_t)(kk * 64), idesc_a, acc);
+          umma_tf32_ts(t_dk, t_dpt + b2 * 64 + kk * 8, qmn + (uint64_t)(kk * 64), idesc_a, acc);
+        }
+        umma_commit(mfree(s));
+      }
+      __syncwarp();
+      trace(tr && lane == 0, 203 + it * 4);
+      if (it + 2 < n_it) issue_sdp(it + 2);  // reuses the S^T/dP^T buffer just consumed: same-thread MMAs retire in order
+    }
+    if (elect_one_sync()) umma_commit(acc_full);
+    __syncwarp();
+  } else {
+    // ---------------- softmax threads: (key row r, query half) ----------------
+    const int cw = warp - 2;
+    const int q = warp & 3;                         // TMEM lane quarter this warp may touch
+    const int half = cw >> 2;
+    const int r = q * 32 + lane;
+    const int key = k0 + r;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const bool key_ok = key < p.S;
+    const bool key_pad = key_ok ? (x[(int64_t)b * p.S + key] == 0) : true;
+    const bool trs = tr && threadIdx.x == 64;
+
+    // prologue: resident K and V tiles smem -> TMEM (32 columns per thread)
+    mbar_wait(kv_full, 0);
+    {
+      uint32_t v[32];
+      if (D == 64) {
+        load_swizzled_row(mst_ptr + half * (128 * 128), r, v);
+        tmem_st32(t_k + lane_addr + half * 32, v);
+        load_swizzled_row(mst_ptr + C::kStage + half * (128 * 128), r, v);
+        tmem_st32(t_v + lane_addr + half * 32, v);
+      } else {
+        load_swizzled_row(mst_ptr + half * C::kStage, r, v);
+        tmem_st32((half ? t_v : t_k) + lane_addr, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(kv_done);
+    }
+
+    for (int it = 0; it < n_it; ++it) {
+      const int b2 = it & 1;
+      const uint32_t ph = (uint32_t)((it >> 1) & 1);
+      const int qb = block_of(it) * 64 + half * 32;   // first query of this thread's 32 columns
+      // visibility of (query qb+c, this key): causal & not PAD, or the query is a fully-masked row
+      const uint32_t range_bits = low_bits32(p.S - qb);
+      const uint32_t causal = (key_ok && !key_pad) ? ~low_bits32(key - qb) : 0u;
+      const uint32_t degq = key_ok ? low_bits32(first_real - qb) : 0u;
+      const uint32_t vis = (causal | degq) & range_bits;
+      trace(trs, 300 + it * 3);
+      mbar_wait(ld_full(b2), ph);
+      mbar_wait(sdp_full(b2), ph);
+      tc_fence_after();
+      trace(trs, 301 + it * 3);
+      uint32_t sv[32], dv[32];
+      const uint32_t a_s = t_st + b2 * 64 + half * 32 + lane_addr, a_d = t_dpt + b2 * 64 + half * 32 + lane_addr;
+      tmem_ld32_nowait(a_s, sv);
+      tmem_ld32_nowait(a_d, dv);
+      tmem_ld_wait();
+      const float4* l4 = reinterpret_cast<const float4*>(lse_s + b2 * 64 + half * 32);
+      const float4* d4 = reinterpret_cast<const float4*>(delta_s + b2 * 64 + half * 32);
+      const uint64_t scale2 = pack2f(p.scale_log2, p.scale_log2);
+      if (__all_sync(0xffffffffu, vis == ~0u)) {      // interior block: no mask tests
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 nl = l4[i], nd = d4[i];
+          p_ds_pair<false, true>(sv[4 * i], sv[4 * i + 1], dv[4 * i], dv[4 * i + 1], scale2, pack2f(nl.x, nl.y), pack2f(nd.x, nd.y), vis, 4 * i);
+          p_ds_pair<false, true>(sv[4 * i + 2], sv[4 * i + 3], dv[4 * i + 2], dv[4 * i + 3], scale2, pack2f(nl.z, nl.w), pack2f(nd.z, nd.w), vis, 4 * i + 2);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 nl = l4[i], nd = d4[i];
+          p_ds_pair<true, true>(sv[4 * i], sv[4 * i + 1], dv[4 * i], dv[4 * i + 1], scale2, pack2f(nl.x, nl.y), pack2f(nd.x, nd.y), vis, 4 * i);
+          p_ds_pair<true, true>(sv[4 * i + 2], sv[4 * i + 3], dv[4 * i + 2], dv[4 * i + 3], scale2, pack2f(nl.z, nl.w), pack2f(nd.z, nd.w), vis, 4 * i + 2);
+        }
+      }
+      tmem_st32(a_s, sv);
+      tmem_st32(a_d, dv);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(pds_full(b2));
+      trace(trs, 302 + it * 3);
+      trace(tr && lane == 0, 400 + it * 8 + cw);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    trace(trs, 1);
+    {
+      // accumulators -> swizzled smem tiles (the operand stages are idle now) -> coalesced row stores
+      const float scale = p.scale_log2 * (1.f / kLog2e);
+      uint8_t* dv_tile = base_ptr;
+      uint8_t* dk_tile = base_ptr + 128 * D * 4;
+      uint32_t a[32];
+      if (D == 64) {
+        tmem_ld32_nowait(t_dv + lane_addr + half * 32, a);
+        tmem_ld_wait();
+        tile_put_row32<D>(dv_tile, r, half * 32, a, 1.f);
+        tmem_ld32_nowait(t_dk + lane_addr + half * 32, a);
+        tmem_ld_wait();
+        tile_put_row32<D>(dk_tile, r, half * 32, a, scale);
+      } else {
+        tmem_ld32_nowait((half ? t_dk : t_dv) + lane_addr, a);
+        tmem_ld_wait();
+        tile_put_row32<D>(half ? dk_tile : dv_tile, r, 0, a, half ? scale : 1.f);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int n_rows = min(128, p.S - k0);
+      float* out = dqkv + ((int64_t)b * p.S + k0) * 3 * p.E + head * D;
+      tile_store_rows<D>(dv_tile, out + 2 * p.E, 3 * (int64_t)p.E, n_rows, cw, lane);
+      tile_store_rows<D>(dk_tile, out + p.E, 3 * (int64_t)p.E, n_rows, cw, lane);
+    }
+    trace(trs, 2);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, C::kTmemCols);
+  }
+}
+
+// ============================================================================================
+// dQ
+// ============================================================================================
+template <int D, int NS>
+__global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ts(const __grid_constant__ CUtensorMap map_qres,   // qkv, box {32,128}, K-major
+                                                            const __grid_constant__ CUtensorMap map_dores,  // dctx, box {32,128}, K-major
+                                                            const __grid_constant__ CUtensorMap map_kk,     // qkv, box {32,64}, K-major
+                                                            const __grid_constant__ CUtensorMap map_kmn,    // qkv, box {32,64}, MN-major
+                                                            const Dims p, const int32_t* __restrict__ x,
+                                                            const int32_t* __restrict__ fnp,
+                                                            const float* __restrict__ lse,
+                                                            const float* __restrict__ delta,
+                                                            float* __restrict__ dqkv) {
+  using C = Cfg<D, NS>;
+  static_assert(NS >= 2, "the prologue parks Q and dO in the first two K-major stages");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t kst = base;                                  // NS stages of [K K-major | V K-major]
+  const uint32_t mst = base + NS * C::kStage;                 // NS stages of [K MN-major]
+  const uint32_t bar = mst + NS * C::kBlk;
+  uint8_t* ctl_ptr = base_ptr + NS * C::kStage + NS * C::kBlk;
+  auto kfull = [&](int s) { return bar + 8u * s; };
+  auto kfree = [&](int s) { return bar + 8u * (4 + s); };
+  auto mfull = [&](int s) { return bar + 8u * (8 + s); };
+  auto mfree = [&](int s) { return bar + 8u * (12 + s); };
+  auto sdp_full = [&](int b2) { return bar + 8u * (16 + b2); };
+  auto ds_full = [&](int b2) { return bar + 8u * (18 + b2); };
+  const uint32_t res_full = bar + 8u * 22, res_done = bar + 8u * 23, acc_full = bar + 8u * 24, tmem_slot = bar + 8u * 25;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ctl_ptr + 8 * 25);
+  unsigned long long* padmask_s = reinterpret_cast<unsigned long long*>(ctl_ptr + 256);   // up to 64 key blocks
+  constexpr int kMaxPadBlocks = 64;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, head = blockIdx.y;
+  const int q0 = ((int)gridDim.x - 1 - (int)blockIdx.x) * 128;    // heavy (late-query) tiles first
+  const int first_real = fnp[b];
+  const bool deg_block = q0 < first_real;
+  const int n_all = (p.S + 63) / 64;
+  const int n_kv = deg_block ? n_all : min(n_all, (q0 + 127) / 64 + 1);
+  const int row_base = b * p.S;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(kfull(s), 1); mbar_init(kfree(s), 1); mbar_init(mfull(s), 1); mbar_init(mfree(s), 1); }
+    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(sdp_full(b2), 1); mbar_init(ds_full(b2), 256); }
+    mbar_init(res_full, 1); mbar_init(res_done, 256); mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+    mbar_expect_tx(res_full, 2 * C::kStage);
+#pragma unroll
+    for (int a = 0; a < C::kAtoms; ++a) {
+      tma_load_2d(kst + a * (128 * 128), &map_qres, res_full, head * D + a * 32, row_base + q0);
+      tma_load_2d(kst + C::kStage + a * (128 * 128), &map_dores, res_full, head * D + a * 32, row_base + q0);
+    }
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t t_q = tmem, t_do = tmem + D, t_s = tmem + 2 * D, t_dp = t_s + 128, t_dq = t_dp + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < n_kv; ++kb) {
+        const int s = kb % NS;
+        const uint32_t free_par = (uint32_t)((kb / NS) & 1) ^ 1u;
+        const int krow = row_base + kb * 64;
+        // the MN-major K tile does not depend on the prologue: issue it first
+        mbar_wait(mfree(s), free_par);
+        mbar_expect_tx(mfull(s), C::kBlk);
+#pragma unroll
+        for (int a = 0; a < C::kAtoms; ++a)
+          tma_load_2d(mst + s * C::kBlk + a * (64 * 128), &map_kmn, mfull(s), p.E + head * D + a * 32, krow);
+        if (kb == 0) mbar_wait(res_done, 0);          // Q and dO have left the first two K-major stages
+        mbar_wait(kfree(s), free_par);
+        mbar_expect_tx(kfull(s), C::kStage);
+#pragma unroll
+        for (int a = 0; a < C::kAtoms; ++a) {
+          tma_load_2d(kst + s * C::kStage + a * (64 * 128), &map_kk, kfull(s), p.E + head * D + a * 32, krow);
+          tma_load_2d(kst + s * C::kStage + C::kBlk + a * (64 * 128), &map_kk, kfull(s), 2 * p.E + head * D + a * 32, krow);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_t = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    auto issue_sdp = [&](int kb) {        // S = Q K^T ; dP = dO V^T   (A = Q / dO in TMEM)
+      const int s = kb % NS, b2 = kb & 1;
+      mbar_wait(kfull(s), (uint32_t)((kb / NS) & 1));
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t kk_d = make_desc(kst + s * C::kStage, 16, 1024, 2), vk_d = make_desc(kst + s * C::kStage + C::kBlk, 16, 1024, 2);
+#pragma unroll
+        for (int kk = 0; kk < D / 8; ++kk) {
+          const uint64_t bo = (uint64_t)(((kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4);
+          umma_tf32_ts(t_s + b2 * 64, t_q + kk * 8, kk_d + bo, idesc_t, kk > 0 ? 1u : 0u);
+          umma_tf32_ts(t_dp + b2 * 64, t_do + kk * 8, vk_d + bo, idesc_t, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(sdp_full(b2));
+        umma_commit(kfree(s));
+      }
+      __syncwarp();
+    };
+    mbar_wait(res_done, 0);
+    tc_fence_after();
+    issue_sdp(0);
+    if (n_kv > 1) issue_sdp(1);
+    for (int kb = 0; kb < n_kv; ++kb) {
+      const int s = kb % NS, b2 = kb & 1;
+      mbar_wait(mfull(s), (uint32_t)((kb / NS) & 1));
+      mbar_wait(ds_full(b2), (uint32_t)((kb >> 1) & 1));
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t kmn = make_desc(mst + s * C::kBlk, 64 * 128, 512, 1);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)        // dQ += dS K   (K = 64 keys, A = dS in TMEM)
+          umma_tf32_ts(t_dq, t_dp + b2 * 64 + kk * 8, kmn + (uint64_t)(kk * 64), idesc_a, (kb > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(mfree(s));
+      }
+      __syncwarp();
+      if (kb + 2 < n_kv) issue_sdp(kb + 2);
+    }
+    if (elect_one_sync()) umma_commit(acc_full);
+    __syncwarp();
+  } else {
+    const int cw = warp - 2;
+    const int q = warp & 3;
+    const int half = cw >> 2;
+    const int r = q * 32 + lane;
+    const int row = q0 + r;
+    const bool deg = row < first_real;
+    const bool row_ok = row < p.S;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int64_t so = ((int64_t)b * p.h + head) * p.S;
+    const float nls = row_ok ? -lse[so + row] * kLog2e : 0.f;
+    const float ndl = row_ok ? -delta[so + row] : 0.f;
+
+    // PAD bits of every key block of this sequence, built once (two ballots per block)
+    const bool pads_staged = n_kv <= kMaxPadBlocks;
+    if (pads_staged) {
+      for (int kb = cw; kb < n_kv; kb += 8) {
+        const int ka = kb * 64 + lane, kb2 = ka + 32;
+        const bool pa = ka < p.S ? (x[(int64_t)b * p.S + ka] == 0) : true;
+        const bool pb = kb2 < p.S ? (x[(int64_t)b * p.S + kb2] == 0) : true;
+        const unsigned long long bits = (unsigned long long)__ballot_sync(0xffffffffu, pa) |
+                                        ((unsigned long long)__ballot_sync(0xffffffffu, pb) << 32);
+        if (lane == 0) padmask_s[kb] = bits;
+      }
+    }
+    // prologue: resident Q and dO tiles smem -> TMEM
+    mbar_wait(res_full, 0);
+    {
+      uint32_t v[32];
+      if (D == 64) {
+        load_swizzled_row(base_ptr + half * (128 * 128), r, v);
+        tmem_st32(t_q + lane_addr + half * 32, v);
+        load_swizzled_row(base_ptr + C::kStage + half * (128 * 128), r, v);
+        tmem_st32(t_do + lane_addr + half * 32, v);
+      } else {
+        load_swizzled_row(base_ptr + half * C::kStage, r, v);
+        tmem_st32((half ? t_do : t_q) + lane_addr, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(res_done);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // padmask_s visible to all softmax warps
+
+    for (int kb = 0; kb < n_kv; ++kb) {
+      const int b2 = kb & 1;
+      const uint32_t ph = (uint32_t)((kb >> 1) & 1);
+      const int kbase = kb * 64 + half * 32;          // first key of this thread's 32 columns
+      uint32_t padbits;
+      if (pads_staged) {
+        padbits = (uint32_t)(padmask_s[kb] >> (half * 32));
+      } else {
+        const int ka = kbase + lane;
+        padbits = __ballot_sync(0xffffffffu, ka < p.S ? (x[(int64_t)b * p.S + ka] == 0) : true);
+      }
+      const uint32_t range_bits = low_bits32(p.S - kbase);
+      uint32_t vis;
+      if (!row_ok) vis = 0u;
+      else if (deg) vis = range_bits;
+      else vis = low_bits32(row - kbase + 1) & ~padbits & range_bits;
+      mbar_wait(sdp_full(b2), ph);
+      tc_fence_after();
+      uint32_t sv[32], dv[32];
+      const uint32_t a_s = t_s + b2 * 64 + half * 32 + lane_addr, a_d = t_dp + b2 * 64 + half * 32 + lane_addr;
+      tmem_ld32_nowait(a_s, sv);
+      tmem_ld32_nowait(a_d, dv);
+      tmem_ld_wait();
+      const uint64_t scale2 = pack2f(p.scale_log2, p.scale_log2), nl2 = pack2f(nls, nls), ndl2 = pack2f(ndl, ndl);
+      if (__all_sync(0xffffffffu, vis == ~0u)) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) p_ds_pair<false, false>(sv[c], sv[c + 1], dv[c], dv[c + 1], scale2, nl2, ndl2, vis, c);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) p_ds_pair<true, false>(sv[c], sv[c + 1], dv[c], dv[c + 1], scale2, nl2, ndl2, vis, c);
+      }
+      tmem_st32(a_d, dv);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(ds_full(b2));
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const float scale = p.scale_log2 * (1.f / kLog2e);
+    uint8_t* dq_tile = base_ptr;                      // the operand stages are idle now
+    if (D == 64 || half == 0) {
+      uint32_t a[32];
+      tmem_ld32_nowait(t_dq + lane_addr + (D == 64 ? half * 32 : 0), a);
+      tmem_ld_wait();
+      tile_put_row32<D>(dq_tile, r, D == 64 ? half * 32 : 0, a, scale);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    tile_store_rows<D>(dq_tile, dqkv + ((int64_t)b * p.S + q0) * 3 * p.E + head * D, 3 * (int64_t)p.E, min(128, p.S - q0), cw, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, C::kTmemCols);
+  }
+}
+
+template <int D>
+int launch_bwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int32_t* x, const int32_t* fnp,
+               const float* dctx, const float* lse, const float* delta, float* dqkv) {
+  constexpr int NS = 3;
+  using C = Cfg<D, NS>;
+  const int E = h * D;
+  const uint64_t rows = (uint64_t)B * S;
+  CUtensorMap res, qk, qmn, dok, domn, dores;
+  NLPS_TRY(make_map(&res, qkv, 3 * (uint64_t)E, rows, 3 * (int64_t)E, 32, 128, true, false));
+  NLPS_TRY(make_map(&qk, qkv, 3 * (uint64_t)E, rows, 3 * (int64_t)E, 32, 64, true, false));
+  NLPS_TRY(make_map(&qmn, qkv, 3 * (uint64_t)E, rows, 3 * (int64_t)E, 32, 64, true, true));
+  NLPS_TRY(make_map(&dok, dctx, (uint64_t)E, rows, (int64_t)E, 32, 64, true, false));
+  NLPS_TRY(make_map(&domn, dctx, (uint64_t)E, rows, (int64_t)E, 32, 64, true, true));
+  NLPS_TRY(make_map(&dores, dctx, (uint64_t)E, rows, (int64_t)E, 32, 128, true, false));
+  static bool once = false;
+  if (!once) {
+    NLPS_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_ts<D, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemDkdv));
+    NLPS_CUDA(cudaFuncSetAttribute(attn_bwd_dq_ts<D, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemDq));
+    once = true;
+  }
+  static int trace_on = -1;
+  if (trace_on < 0) { const char* e = getenv("NLPS_ATTN_TRACE"); trace_on = (e && e[0] == '2') ? 1 : 0; }
+  Dims p{B, S, h, E, (float)(1.0 / std::sqrt((double)D)) * kLog2e, trace_on};
+  dim3 grid((unsigned)ceil_div(S, 128), (unsigned)h, (unsigned)B);
+  attn_bwd_dkdv_ts<D, NS><<<grid, kThreads, C::kSmemDkdv, st>>>(res, qk, qmn, dok, domn, p, x, fnp, lse, delta, dqkv);
+  NLPS_LAUNCH_CHECK();
+  attn_bwd_dq_ts<D, NS><<<grid, kThreads, C::kSmemDq, st>>>(res, dores, qk, qmn, p, x, fnp, lse, delta, dqkv);
+  NLPS_LAUNCH_CHECK();
+  if (trace_on) {
+    static int printed = 0;
+    if (printed++ == 3) {
+      static long long hbuf[kTraceSlots];
+      cudaStreamSynchronize(st);
+      cudaMemcpyFromSymbol(hbuf, g_ts_trace, sizeof(hbuf));
+      const long long t0 = hbuf[0];
+      printf("attn_bwd_dkdv_ts trace, key tile 0 (cycles since CTA start): accumulators ready %lld, stores done %lld\n", hbuf[1] - t0, hbuf[2] - t0);
+      const int n_it = std::min(8, (S + 63) / 64);
+      for (int it = 0; it < n_it; ++it)
+        printf("it %d | TMA K-major issue %6lld MN issue %6lld | MMA sdp start %6lld issued %6lld acc start %6lld issued %6lld | thread top %6lld sdp ready %6lld P/dS stored %6lld\n",
+               it, hbuf[100 + it * 2] - t0, hbuf[101 + it * 2] - t0, hbuf[200 + it * 4] - t0, hbuf[201 + it * 4] - t0,
+               hbuf[202 + it * 4] - t0, hbuf[203 + it * 4] - t0, hbuf[300 + it * 3] - t0, hbuf[301 + it * 3] - t0, hbuf[302 + it * 3] - t0);
+      for (int it = 0; it < n_it; ++it) {
+        printf("it %d | mfull passed %6lld | per-warp P/dS stored:", it, hbuf[500 + it] - t0);
+        for (int w = 0; w < 8; ++w) printf(" %6lld", hbuf[400 + it * 8 + w] - t0);
+        printf("\n");
+      }
+      fflush(stdout);
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+int attention_backward_ts(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
+                          const int32_t* fnp, const float* dctx, const float* lse, const float* delta, float* dqkv) {
+  if (d == 64) return launch_bwd<64>(st, B, S, h, qkv, x, fnp, dctx, lse, delta, dqkv);
+  return launch_bwd<32>(st, B, S, h, qkv, x, fnp, dctx, lse, delta, dqkv);
+}
+
+}  // namespace nlps

@@ -71,7 +71,10 @@ def _attention_case(B, S, h, d, pad_mode, seed):
 
 @pytest.mark.parametrize("B,S,h,d,pad", [(2, 5, 8, 8, "none"), (3, 10, 4, 8, "tail"), (3, 8, 4, 8, "lead"),
                                          (2, 77, 2, 32, "tail"), (1, 130, 2, 64, "none"), (2, 65, 1, 16, "lead"),
-                                         (1, 64, 1, 128, "none"), (2, 33, 3, 20, "tail")])
+                                         (1, 64, 1, 128, "none"), (2, 33, 3, 20, "tail"),
+                                         # multi-block shapes for the tcgen05 kernels (head_dim 32 / 64)
+                                         (2, 320, 2, 32, "tail"), (3, 300, 2, 64, "lead"), (2, 512, 2, 64, "none"),
+                                         (1, 1100, 1, 64, "tail"), (3, 257, 3, 32, "lead")])
 @pytest.mark.parametrize("prec", ["fp32", "tf32"])
 def test_attention_forward_backward(B, S, h, d, pad, prec):
     # fp32: CUDA-core kernels (attention.cu); tf32: mma.sync tensor-core kernels (attention_mma.cu,
