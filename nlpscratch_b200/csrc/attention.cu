@@ -541,8 +541,10 @@ int first_nonpad(cudaStream_t st, int B, int S, const int32_t* x, int32_t* out) 
 int attention_forward(cudaStream_t st, int precision, int B, int S, int h, int d, const float* qkv,
                       const int32_t* x, const int32_t* fnp, float* ctx, float* lse) {
   NLPS_TRY(check_dims(B, S, h, d));
-  if (precision == 1 && attention_tc_supported(d, h * d, qkv) && attn_impl() != 1)
-    return attention_forward_tc(st, B, S, h, d, qkv, x, fnp, ctx, lse);
+  if (precision == 1 && attention_tc_supported(d, h * d, qkv) && attn_impl() != 1) {
+    if (attn_impl() == 2) return attention_forward_tc(st, B, S, h, d, qkv, x, fnp, ctx, lse);
+    return attention_forward_ts(st, B, S, h, d, qkv, x, fnp, ctx, lse);
+  }
   if (precision == 1 && d <= 64 && d % 4 == 0) return attention_forward_mma(st, B, S, h, d, qkv, x, fnp, ctx, lse);
   AttnDims p{B, S, h, d, h * d, (float)(1.0 / sqrt((double)d))};
   if (d <= 8) return fwd_launch<8>(st, p, qkv, x, fnp, ctx, lse);

@@ -48,6 +48,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// pins the first USE of a value whose load was issued earlier: the empty volatile asm cannot move above the
+// barrier waits around it, so the scoreboard wait for the load lands here and not at the top of the kernel
+__device__ __forceinline__ int use_here(int v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
 __device__ __forceinline__ uint32_t low_bits32(int n) {   // n lowest bits set, n clamped to [0,32]
   return n <= 0 ? 0u : (n >= 32 ? ~0u : ((1u << n) - 1u));
 }
@@ -161,17 +167,31 @@ __device__ __forceinline__ void tile_put_row32(uint8_t* tile, int r, int col0, c
                     __uint_as_float(v[4 * j + 2]) * scale, __uint_as_float(v[4 * j + 3]) * scale);
   }
 }
-// rows [0, n_rows) of the tile -> global rows of stride ld floats, one coalesced row per warp instruction
-template <int D>
-__device__ __forceinline__ void tile_store_rows(const uint8_t* tile, float* out, int64_t ld, int n_rows, int warp8, int lane) {
-  for (int r = warp8; r < n_rows; r += 8) {
-    const uint8_t* row = tile + r * (D * 4);
+// rows [0, n_rows) of the tile -> global rows of stride ld floats, one coalesced row per warp instruction;
+// NW warps share the rows, four loads in flight per warp
+template <int D, int NW = 8>
+__device__ __forceinline__ void tile_store_rows(const uint8_t* tile, float* out, int64_t ld, int n_rows, int w, int lane) {
+  for (int r0 = w; r0 < n_rows; r0 += 4 * NW) {
     if (D == 64) {
-      const float2 v = *reinterpret_cast<const float2*>(row + (((lane >> 1) ^ (r & 7)) << 4) + ((lane & 1) << 3));
-      *reinterpret_cast<float2*>(out + r * ld + 2 * lane) = v;
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = min(r0 + u * NW, 127);
+        v[u] = *reinterpret_cast<const float2*>(tile + r * (D * 4) + (((lane >> 1) ^ (r & 7)) << 4) + ((lane & 1) << 3));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r0 + u * NW < n_rows) *reinterpret_cast<float2*>(out + (r0 + u * NW) * ld + 2 * lane) = v[u];
     } else {
-      const float v = *reinterpret_cast<const float*>(row + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
-      out[r * ld + lane] = v;
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = min(r0 + u * NW, 127);
+        v[u] = *reinterpret_cast<const float*>(tile + r * (D * 4) + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r0 + u * NW < n_rows) out[(r0 + u * NW) * ld + lane] = v[u];
     }
   }
 }
@@ -238,14 +258,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ts(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, head = blockIdx.y;
   const int k0 = ((int)gridDim.x - 1 - (int)blockIdx.x) * 128;   // heavy (early-key) tiles are scheduled first
-  const int first_real = fnp[b];
+  // first_real is requested here and first consumed after the causal blocks (global loads take thousands of
+  // cycles while TMA traffic saturates the L2): query blocks [first_causal, n_q) first, then the fully-masked
+  // leading blocks [0, n_deg) whose rows attend to every key
+  const int first_real = __ldg(fnp + b);
   const int row_base = b * p.S;
   const int n_q = (p.S + 63) / 64;
   const int first_causal = k0 / 64;                               // first query block with q >= some key here
-  const int n_deg = min(min((first_real + 63) / 64, n_q), first_causal);
-  const int n_it = n_deg + (n_q - first_causal);
-  auto block_of = [&](int it) { return it < n_deg ? it : it - n_deg + first_causal; };
-  const bool tr = p.trace && blockIdx.x == gridDim.x - 1 && blockIdx.y == 0 && blockIdx.z == 0;
+  const int n_causal = n_q - first_causal;
+  auto more_blocks = [&](int it) { return it < n_causal || it - n_causal < min(min((use_here(first_real) + 63) / 64, n_q), first_causal); };
+  auto block_of = [&](int it) { return it < n_causal ? first_causal + it : it - n_causal; };
+  const bool tr = p.trace && blockIdx.x == gridDim.x - 1 && blockIdx.y == 0 && blockIdx.z == gridDim.z / 2;
   trace(tr && threadIdx.x == 0, 0);
 
   if (warp == 0 && lane == 0) {
@@ -285,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ts(const __grid_con
       }
     };
     fetch_ld(0);
-    for (int it = 0; it < n_it; ++it) {
+    for (int it = 0; more_blocks(it); ++it) {
       const int s = it % NS;
       const uint32_t free_par = (uint32_t)((it / NS) & 1) ^ 1u;
       const int q0 = block_of(it) * 64;
@@ -319,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ts(const __grid_con
         delta_s[b2 * 64 + lane + 32 * j] = -nd_r[j];
       }
       mbar_arrive(ld_full(b2));
-      if (it + 1 < n_it) fetch_ld(it + 1);
+      if (more_blocks(it + 1)) fetch_ld(it + 1);
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer: the warp stays converged, one elected lane issues ----------------
@@ -347,8 +370,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ts(const __grid_con
     mbar_wait(kv_done, 0);
     tc_fence_after();
     issue_sdp(0);
-    if (n_it > 1) issue_sdp(1);
-    for (int it = 0; it < n_it; ++it) {
+    if (more_blocks(1)) issue_sdp(1);
+    for (int it = 0; more_blocks(it); ++it) {
       const int s = it % NS, b2 = it & 1;
       mbar_wait(mfull(s), (uint32_t)((it / NS) & 1));
       trace(tr && lane == 0, 500 + it);
@@ -367,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ts(const __grid_con
       }
       __syncwarp();
       trace(tr && lane == 0, 203 + it * 4);
-      if (it + 2 < n_it) issue_sdp(it + 2);  // reuses the S^T/dP^T buffer just consumed: same-thread MMAs retire in order
+      if (more_blocks(it + 2)) issue_sdp(it + 2);  // reuses the S^T/dP^T buffer just consumed: same-thread MMAs retire in order
     }
     if (elect_one_sync()) umma_commit(acc_full);
     __syncwarp();
@@ -380,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ts(const __grid_con
     const int key = k0 + r;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const bool key_ok = key < p.S;
-    const bool key_pad = key_ok ? (x[(int64_t)b * p.S + key] == 0) : true;
+    const bool key_pad = key_ok ? (__ldg(x + (int64_t)b * p.S + key) == 0) : true;
     const bool trs = tr && threadIdx.x == 64;
 
     // prologue: resident K and V tiles smem -> TMEM (32 columns per thread)
@@ -401,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ts(const __grid_con
       mbar_arrive(kv_done);
     }
 
-    for (int it = 0; it < n_it; ++it) {
+    for (int it = 0; more_blocks(it); ++it) {
       const int b2 = it & 1;
       const uint32_t ph = (uint32_t)((it >> 1) & 1);
       const int qb = block_of(it) * 64 + half * 32;   // first query of this thread's 32 columns
@@ -520,10 +543,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ts(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, head = blockIdx.y;
   const int q0 = ((int)gridDim.x - 1 - (int)blockIdx.x) * 128;    // heavy (late-query) tiles first
-  const int first_real = fnp[b];
-  const bool deg_block = q0 < first_real;
+  const int first_real = __ldg(fnp + b);           // first consumed after the causal blocks (see the dK/dV kernel)
   const int n_all = (p.S + 63) / 64;
-  const int n_kv = deg_block ? n_all : min(n_all, (q0 + 127) / 64 + 1);
+  const int n_causal = min(n_all, (q0 + 127) / 64 + 1);
+  auto more_blocks = [&](int kb) { return kb < n_causal || (q0 < use_here(first_real) && kb < n_all); };
   const int row_base = b * p.S;
 
   if (warp == 0 && lane == 0) {
@@ -548,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ts(const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < n_kv; ++kb) {
+      for (int kb = 0; more_blocks(kb); ++kb) {
         const int s = kb % NS;
         const uint32_t free_par = (uint32_t)((kb / NS) & 1) ^ 1u;
         const int krow = row_base + kb * 64;
@@ -592,8 +615,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ts(const __grid_const
     mbar_wait(res_done, 0);
     tc_fence_after();
     issue_sdp(0);
-    if (n_kv > 1) issue_sdp(1);
-    for (int kb = 0; kb < n_kv; ++kb) {
+    if (more_blocks(1)) issue_sdp(1);
+    for (int kb = 0; more_blocks(kb); ++kb) {
       const int s = kb % NS, b2 = kb & 1;
       mbar_wait(mfull(s), (uint32_t)((kb / NS) & 1));
       mbar_wait(ds_full(b2), (uint32_t)((kb >> 1) & 1));
@@ -606,7 +629,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ts(const __grid_const
         umma_commit(mfree(s));
       }
       __syncwarp();
-      if (kb + 2 < n_kv) issue_sdp(kb + 2);
+      if (more_blocks(kb + 2)) issue_sdp(kb + 2);
     }
     if (elect_one_sync()) umma_commit(acc_full);
     __syncwarp();
@@ -616,7 +639,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ts(const __grid_const
     const int half = cw >> 2;
     const int r = q * 32 + lane;
     const int row = q0 + r;
-    const bool deg = row < first_real;
     const bool row_ok = row < p.S;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int64_t so = ((int64_t)b * p.h + head) * p.S;
@@ -624,15 +646,22 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ts(const __grid_const
     const float ndl = row_ok ? -delta[so + row] : 0.f;
 
     // PAD bits of every key block of this sequence, built once (two ballots per block)
-    const bool pads_staged = n_kv <= kMaxPadBlocks;
-    if (pads_staged) {
-      for (int kb = cw; kb < n_kv; kb += 8) {
-        const int ka = kb * 64 + lane, kb2 = ka + 32;
-        const bool pa = ka < p.S ? (x[(int64_t)b * p.S + ka] == 0) : true;
-        const bool pb = kb2 < p.S ? (x[(int64_t)b * p.S + kb2] == 0) : true;
-        const unsigned long long bits = (unsigned long long)__ballot_sync(0xffffffffu, pa) |
-                                        ((unsigned long long)__ballot_sync(0xffffffffu, pb) << 32);
-        if (lane == 0) padmask_s[kb] = bits;
+    const bool pads_staged = n_all <= kMaxPadBlocks;
+    if (pads_staged) {                                // 32 keys per ballot, all loads of a warp in flight together
+      uint32_t* pad32 = reinterpret_cast<uint32_t*>(padmask_s);
+      const int n_words = 2 * n_all;
+      for (int w0 = cw; w0 < n_words; w0 += 32) {
+        int32_t id[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int key = (w0 + 8 * u) * 32 + lane;
+          id[u] = key < p.S ? __ldg(x + (int64_t)b * p.S + key) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t bits = __ballot_sync(0xffffffffu, id[u] == 0);
+          if (lane == 0 && w0 + 8 * u < n_words) pad32[w0 + 8 * u] = bits;
+        }
       }
     }
     // prologue: resident Q and dO tiles smem -> TMEM
@@ -654,7 +683,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ts(const __grid_const
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");   // padmask_s visible to all softmax warps
 
-    for (int kb = 0; kb < n_kv; ++kb) {
+    const bool deg = row < first_real;
+    for (int kb = 0; more_blocks(kb); ++kb) {
       const int b2 = kb & 1;
       const uint32_t ph = (uint32_t)((kb >> 1) & 1);
       const int kbase = kb * 64 + half * 32;          // first key of this thread's 32 columns
@@ -763,12 +793,402 @@ int launch_bwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int
   return 0;
 }
 
+
+// ============================================================================================
+// Forward (transformer.py:116-141).  One CTA per (batch, head, 128 queries), TWO CTAs per SM (256 TMEM
+// columns, ~99 KB of shared memory each): while one CTA is in its prologue / epilogue or waits for the
+// tensor pipe, the other one's softmax warps run.
+//   Q is copied smem -> TMEM once and is the A operand of S = Q K^T; thread r of the 4 softmax warps owns
+//   query row r (= TMEM lane r): it reads its 64 scores, does the online max/sum with no cross-thread
+//   traffic, overwrites S with P in TMEM (the A operand of O_blk = P V), and folds O_blk(j-1) into its
+//   register accumulator only AFTER P(j) is handed over -- S is double-buffered, so the thread never
+//   waits for the P V product it has just enabled.
+// ============================================================================================
+constexpr int kFwdThreads = 192;   // warp0 TMA, warp1 MMA + TMEM owner, warps 2-5 softmax
+
+template <int D, int NS>
+struct FwdCfg {
+  static constexpr int kAtoms = D / 32;
+  static constexpr int kBlk = kAtoms * 64 * 128;             // K (K-major) or V (MN-major) block of 64 keys
+  static constexpr int kStage = 2 * kBlk;
+  static constexpr int kTile = 128 * D * 4;                  // Q image, later the normalised output tile
+  static constexpr int kCtl = 1024;                          // barriers (256 B) | pad masks 64 x 8 B
+  static constexpr int kSmem = NS * kStage + kTile + kCtl + 1024;
+  static constexpr int kTmemCols = 256;
+};
+
+template <int D, int NS>
+__global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_ts(const __grid_constant__ CUtensorMap map_q,    // qkv, box {32,128}, K-major
+                                                            const __grid_constant__ CUtensorMap map_k,    // qkv, box {32,64}, K-major
+                                                            const __grid_constant__ CUtensorMap map_v,    // qkv, box {32,64}, MN-major
+                                                            const Dims p, const int32_t* __restrict__ x,
+                                                            const int32_t* __restrict__ fnp, float* __restrict__ ctx,
+                                                            float* __restrict__ lse) {
+  using C = FwdCfg<D, NS>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t kv_s = base;                                 // NS stages of [K block | V block]
+  const uint32_t q_s = base + NS * C::kStage;
+  uint8_t* q_ptr = base_ptr + NS * C::kStage;
+  uint8_t* ctl_ptr = q_ptr + C::kTile;
+  const uint32_t bar = q_s + C::kTile;
+  auto kfull = [&](int s) { return bar + 8u * s; };
+  auto kfree = [&](int s) { return bar + 8u * (4 + s); };
+  auto vfull = [&](int s) { return bar + 8u * (8 + s); };
+  auto vfree = [&](int s) { return bar + 8u * (12 + s); };
+  auto s_full = [&](int b2) { return bar + 8u * (16 + b2); };
+  auto p_full = [&](int b2) { return bar + 8u * (18 + b2); };
+  const uint32_t o_full = bar + 8u * 20, o_read = bar + 8u * 21, q_full = bar + 8u * 22, q_done = bar + 8u * 23, tmem_slot = bar + 8u * 24;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ctl_ptr + 8 * 24);
+  unsigned long long* padmask_s = reinterpret_cast<unsigned long long*>(ctl_ptr + 256);   // [64]
+  constexpr int kMaxPadBlocks = 64;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, head = blockIdx.y;
+  const int q0 = ((int)gridDim.x - 1 - (int)blockIdx.x) * 128;     // heavy (late-query) tiles are scheduled first
+  // Global loads take thousands of cycles while the TMA traffic of 296 CTAs saturates the L2: first_real is
+  // requested here and first consumed after the causal blocks (a fully-masked leading tile appends the rest).
+  const int first_real = __ldg(fnp + b);
+  const int n_all = (p.S + 63) / 64;
+  const int n_causal = min(n_all, (q0 + 127) / 64 + 1);
+  auto more_blocks = [&](int kb) { return kb < n_causal || (q0 < use_here(first_real) && kb < n_all); };
+  const int row_base = b * p.S;
+  const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == gridDim.z / 2;   // a mid-grid CTA (warm caches)
+  trace(tr && threadIdx.x == 0, 0);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(kfull(s), 1); mbar_init(kfree(s), 1); mbar_init(vfull(s), 1); mbar_init(vfree(s), 1); }
+    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(s_full(b2), 1); mbar_init(p_full(b2), 128); }
+    mbar_init(o_full, 1); mbar_init(o_read, 128); mbar_init(q_full, 1); mbar_init(q_done, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+    trace(tr, 9);
+    mbar_expect_tx(q_full, C::kTile);                         // Q starts moving before the TMEM allocation / setup barrier
+#pragma unroll
+    for (int a = 0; a < C::kAtoms; ++a)
+      tma_load_2d(q_s + a * (128 * 128), &map_q, q_full, head * D + a * 32, row_base + q0);
+    trace(tr, 10);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+    }
+    tmem_alloc(tmem_slot, C::kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  trace(tr && threadIdx.x == 64, 4);
+  const uint32_t t_q = tmem, t_o = tmem + D + 128;
+  auto t_s = [&](int b2) { return tmem + D + 64 * b2; };
+
+  if (warp == 0) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      for (int kb = 0; more_blocks(kb); ++kb) {
+        const int s = kb % NS;
+        const uint32_t free_par = (uint32_t)((kb / NS) & 1) ^ 1u;
+        const int krow = row_base + kb * 64;
+        mbar_wait(kfree(s), free_par);
+        trace(tr && kb < 16, 100 + kb * 2);
+        mbar_expect_tx(kfull(s), C::kBlk);
+#pragma unroll
+        for (int a = 0; a < C::kAtoms; ++a)
+          tma_load_2d(kv_s + s * C::kStage + a * (64 * 128), &map_k, kfull(s), p.E + head * D + a * 32, krow);
+        mbar_wait(vfree(s), free_par);
+        trace(tr && kb < 16, 101 + kb * 2);
+        mbar_expect_tx(vfull(s), C::kBlk);
+#pragma unroll
+        for (int a = 0; a < C::kAtoms; ++a)
+          tma_load_2d(kv_s + s * C::kStage + C::kBlk + a * (64 * 128), &map_v, vfull(s), 2 * p.E + head * D + a * 32, krow);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (converged warp, elected lane) ----------------
+    constexpr uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    auto issue_s = [&](int j) {            // S = Q K^T (A = Q in TMEM)
+      const int s = j % NS, b2 = j & 1;
+      mbar_wait(kfull(s), (uint32_t)((j / NS) & 1));
+      tc_fence_after();
+      trace(tr && lane == 0 && j < 16, 200 + j * 4);
+      if (elect_one_sync()) {
+        const uint64_t kd = make_desc(kv_s + s * C::kStage, 16, 1024, 2);
+#pragma unroll
+        for (int kk = 0; kk < D / 8; ++kk)
+          umma_tf32_ts(t_s(b2), t_q + kk * 8, kd + (uint64_t)(((kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4), idesc_s, kk > 0 ? 1u : 0u);
+        umma_commit(s_full(b2));
+        umma_commit(kfree(s));
+      }
+      __syncwarp();
+      trace(tr && lane == 0 && j < 16, 201 + j * 4);
+    };
+    mbar_wait(q_done, 0);
+    tc_fence_after();
+    issue_s(0);
+    if (more_blocks(1)) issue_s(1);
+    for (int j = 0; more_blocks(j); ++j) {
+      const int s = j % NS, b2 = j & 1;
+      mbar_wait(vfull(s), (uint32_t)((j / NS) & 1));
+      mbar_wait(p_full(b2), (uint32_t)((j >> 1) & 1));
+      if (j > 0) mbar_wait(o_read, (uint32_t)((j - 1) & 1));       // the previous O block has been folded into registers
+      tc_fence_after();
+      trace(tr && lane == 0 && j < 16, 202 + j * 4);
+      if (elect_one_sync()) {
+        const uint64_t vd = make_desc(kv_s + s * C::kStage + C::kBlk, 64 * 128, 512, 1);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)          // O_blk = P V (A = P in TMEM, K = 64 keys)
+          umma_tf32_ts(t_o, t_s(b2) + kk * 8, vd + (uint64_t)(kk * 64), idesc_o, kk > 0 ? 1u : 0u);
+        umma_commit(o_full);
+        umma_commit(vfree(s));
+      }
+      __syncwarp();
+      trace(tr && lane == 0 && j < 16, 203 + j * 4);
+      if (more_blocks(j + 2)) issue_s(j + 2);    // overwrites the P just consumed: same-thread MMAs retire in order
+    }
+  } else {
+    // ---------------- softmax warps: thread == query row ----------------
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int row = q0 + r;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint64_t scale2 = pack2f(p.scale_log2, p.scale_log2);
+    const bool pads_staged = n_all <= kMaxPadBlocks;
+    const bool trs = tr && q == 2 && lane == 0;
+    // PAD bits of every key of this sequence, built once: 32 keys per ballot, all loads of a warp in flight together
+    if (pads_staged) {
+      uint32_t* pad32 = reinterpret_cast<uint32_t*>(padmask_s);
+      const int n_words = 2 * n_all;                     // words [2kb, 2kb+1] = keys of block kb
+      for (int w0 = warp - 2; w0 < n_words; w0 += 16) {
+        int32_t id[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int key = (w0 + 4 * u) * 32 + lane;
+          id[u] = key < p.S ? __ldg(x + (int64_t)b * p.S + key) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t bits = __ballot_sync(0xffffffffu, id[u] == 0);
+          if (lane == 0 && w0 + 4 * u < n_words) pad32[w0 + 4 * u] = bits;
+        }
+      }
+    }
+    // Q image -> TMEM (this thread's row)
+    trace(trs, 5);
+    mbar_wait(q_full, 0);
+    trace(trs, 6);
+#pragma unroll
+    for (int a = 0; a < C::kAtoms; ++a) {
+      uint32_t v[32];
+      load_swizzled_row(q_ptr + a * (128 * 128), r, v);
+      tmem_st32(t_q + lane_addr + a * 32, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(q_done);
+    asm volatile("bar.sync 1, 128;" ::: "memory");          // pad masks visible; every row of the Q image has been read
+    trace(trs, 1);
+
+    float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
+    uint32_t o[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) o[c] = 0u;
+    auto fold = [&](int j, float alpha) {                    // o = o * alpha + O_blk(j)
+      const uint64_t alpha2 = pack2f(alpha, alpha);
+      mbar_wait(o_full, (uint32_t)(j & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < D / 32; ++cc) {
+        uint32_t ov[32];
+        tmem_ld32_nowait(t_o + lane_addr + cc * 32, ov);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; c += 2)
+          unpack2(ffma2(pack2(o[cc * 32 + c], o[cc * 32 + c + 1]), alpha2, pack2(ov[c], ov[c + 1])), o[cc * 32 + c], o[cc * 32 + c + 1]);
+      }
+      tc_fence_before();
+      mbar_arrive(o_read);
+    };
+    const bool deg = row < first_real;
+    int n_kv = 0;
+    for (int j = 0; more_blocks(j); ++j) {
+      n_kv = j + 1;
+      const int b2 = j & 1;
+      const int k0 = j * 64;
+      unsigned long long padbits;
+      if (pads_staged) {
+        padbits = padmask_s[j];
+      } else {
+        const int ka = k0 + lane, kb2 = k0 + 32 + lane;
+        const bool pa = ka < p.S ? (x[(int64_t)b * p.S + ka] == 0) : true;
+        const bool pb = kb2 < p.S ? (x[(int64_t)b * p.S + kb2] == 0) : true;
+        padbits = (unsigned long long)__ballot_sync(0xffffffffu, pa) | ((unsigned long long)__ballot_sync(0xffffffffu, pb) << 32);
+      }
+      const int in_range = min(64, p.S - k0);
+      const unsigned long long range_bits = in_range >= 64 ? ~0ull : ((1ull << in_range) - 1ull);
+      unsigned long long vis;
+      if (row >= p.S) vis = 0ull;
+      else if (deg) vis = range_bits;
+      else {
+        const int upto = row - k0;
+        const unsigned long long causal = upto < 0 ? 0ull : (upto >= 63 ? ~0ull : ((1ull << (upto + 1)) - 1ull));
+        vis = causal & ~padbits & range_bits;
+      }
+      trace(trs && j < 16, 300 + j * 4);
+      mbar_wait(s_full(b2), (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      trace(trs && j < 16, 301 + j * 4);
+      uint32_t s0[32], s1[32];
+      tmem_ld32_nowait(t_s(b2) + lane_addr, s0);
+      tmem_ld32_nowait(t_s(b2) + lane_addr + 32, s1);
+      tmem_ld_wait();
+      const bool all_vis = __all_sync(0xffffffffu, vis == ~0ull);
+      float mx = -INFINITY;
+      if (all_vis) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (vis & (1ull << c)) mx = fmaxf(mx, __uint_as_float(s0[c]));
+          if (vis & (1ull << (c + 32))) mx = fmaxf(mx, __uint_as_float(s1[c]));
+        }
+      }
+      const float m_new = fmaxf(m, mx * p.scale_log2);
+      const float m_use = m_new == -INFINITY ? 0.f : m_new;      // row with no visible key yet
+      const float alpha = fast_exp2(m - m_use);                   // exp2(-inf) = 0 when m was -inf
+      const uint64_t negm2 = pack2f(-m_use, -m_use);
+      uint64_t rsum2 = 0ull;
+      const uint32_t vlo = (uint32_t)vis, vhi = (uint32_t)(vis >> 32);
+      if (all_vis) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          uint32_t xa, xb, ya, yb;
+          unpack2(ffma2(pack2(s0[c], s0[c + 1]), scale2, negm2), xa, xb);
+          unpack2(ffma2(pack2(s1[c], s1[c + 1]), scale2, negm2), ya, yb);
+          const float e0 = fast_exp2(__uint_as_float(xa)), e1 = fast_exp2(__uint_as_float(xb));
+          const float f0 = fast_exp2(__uint_as_float(ya)), f1 = fast_exp2(__uint_as_float(yb));
+          rsum2 = fadd2(rsum2, fadd2(pack2f(e0, e1), pack2f(f0, f1)));
+          s0[c] = rna_tf32_bits(__float_as_uint(e0)); s0[c + 1] = rna_tf32_bits(__float_as_uint(e1));
+          s1[c] = rna_tf32_bits(__float_as_uint(f0)); s1[c + 1] = rna_tf32_bits(__float_as_uint(f1));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          uint32_t xa, xb, ya, yb;
+          unpack2(ffma2(pack2(s0[c], s0[c + 1]), scale2, negm2), xa, xb);
+          unpack2(ffma2(pack2(s1[c], s1[c + 1]), scale2, negm2), ya, yb);
+          const float e0 = (vlo & (1u << c)) ? fast_exp2(__uint_as_float(xa)) : 0.f, e1 = (vlo & (2u << c)) ? fast_exp2(__uint_as_float(xb)) : 0.f;
+          const float f0 = (vhi & (1u << c)) ? fast_exp2(__uint_as_float(ya)) : 0.f, f1 = (vhi & (2u << c)) ? fast_exp2(__uint_as_float(yb)) : 0.f;
+          rsum2 = fadd2(rsum2, fadd2(pack2f(e0, e1), pack2f(f0, f1)));
+          s0[c] = rna_tf32_bits(__float_as_uint(e0)); s0[c + 1] = rna_tf32_bits(__float_as_uint(e1));
+          s1[c] = rna_tf32_bits(__float_as_uint(f0)); s1[c + 1] = rna_tf32_bits(__float_as_uint(f1));
+        }
+      }
+      tmem_st32(t_s(b2) + lane_addr, s0);
+      tmem_st32(t_s(b2) + lane_addr + 32, s1);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full(b2));
+      trace(trs && j < 16, 302 + j * 4);
+      uint32_t ra, rb;
+      unpack2(rsum2, ra, rb);
+      l = l * alpha + (__uint_as_float(ra) + __uint_as_float(rb));
+      m = m_new;
+      if (j > 0) fold(j - 1, alpha_prev);        // the product this thread enabled one block ago has long retired
+      alpha_prev = alpha;
+      trace(trs && j < 16, 303 + j * 4);
+    }
+    fold(n_kv - 1, alpha_prev);
+    trace(trs, 2);
+
+    // normalise -> swizzled smem tile (the Q image is dead) -> coalesced row stores
+    {
+      const float inv = 1.f / l;
+#pragma unroll
+      for (int cc = 0; cc < D / 32; ++cc) {
+        uint32_t part[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) part[c] = o[cc * 32 + c];
+        tile_put_row32<D>(q_ptr, r, cc * 32, part, inv);
+      }
+      // natural-log LSE of the scaled scores (m, l are in the exp2 domain)
+      if (row < p.S) lse[((int64_t)b * p.h + head) * p.S + row] = (m + log2f(l)) * (1.f / kLog2e);
+      trace(trs, 7);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      trace(trs, 8);
+      tile_store_rows<D, 4>(q_ptr, ctx + ((int64_t)b * p.S + q0) * p.E + head * D, (int64_t)p.E, min(128, p.S - q0), warp - 2, lane);
+    }
+    trace(trs, 3);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, C::kTmemCols);
+  }
+}
+
+template <int D>
+int launch_fwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int32_t* x, const int32_t* fnp, float* ctx,
+               float* lse) {
+  constexpr int NS = 2;
+  using C = FwdCfg<D, NS>;
+  const int E = h * D;
+  CUtensorMap mq, mk, mv;
+  const uint64_t rows = (uint64_t)B * S;
+  NLPS_TRY(make_map(&mq, qkv, 3 * (uint64_t)E, rows, 3 * (int64_t)E, 32, 128, true, false));
+  NLPS_TRY(make_map(&mk, qkv, 3 * (uint64_t)E, rows, 3 * (int64_t)E, 32, 64, true, false));
+  NLPS_TRY(make_map(&mv, qkv, 3 * (uint64_t)E, rows, 3 * (int64_t)E, 32, 64, true, true));
+  static bool once = false;
+  if (!once) {
+    NLPS_CUDA(cudaFuncSetAttribute(attn_fwd_ts<D, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    once = true;
+  }
+  static int trace_on = -1;
+  if (trace_on < 0) { const char* e = getenv("NLPS_ATTN_TRACE"); trace_on = (e && e[0] == '1') ? 1 : 0; }
+  Dims p{B, S, h, E, (float)(1.0 / std::sqrt((double)D)) * kLog2e, trace_on};
+  dim3 grid((unsigned)ceil_div(S, 128), (unsigned)h, (unsigned)B);
+  attn_fwd_ts<D, NS><<<grid, kFwdThreads, C::kSmem, st>>>(mq, mk, mv, p, x, fnp, ctx, lse);
+  NLPS_LAUNCH_CHECK();
+  if (trace_on) {
+    static int printed = 0;
+    if (printed++ == 3) {
+      static long long hbuf[kTraceSlots];
+      cudaStreamSynchronize(st);
+      cudaMemcpyFromSymbol(hbuf, g_ts_trace, sizeof(hbuf));
+      const long long t0 = hbuf[0];
+      printf("attn_fwd_ts trace, last query tile of (b0,h0) (cycles since CTA start): Q TMA issue %lld..%lld, setup sync %lld, pad masks built %lld, Q landed %lld, Q in TMEM %lld, "
+             "loop done %lld, tile in smem %lld, barrier %lld, stores done %lld\n",
+             hbuf[9] - t0, hbuf[10] - t0, hbuf[4] - t0, hbuf[5] - t0, hbuf[6] - t0, hbuf[1] - t0, hbuf[2] - t0, hbuf[7] - t0, hbuf[8] - t0, hbuf[3] - t0);
+      const int n = std::min(8, (S + 63) / 64);
+      for (int j = 0; j < n; ++j)
+        printf("kb %2d | TMA K %6lld V %6lld | MMA S start %6lld issued %6lld PV start %6lld issued %6lld | thread top %6lld s_full %6lld P stored %6lld prev O folded %6lld\n",
+               j, hbuf[100 + j * 2] - t0, hbuf[101 + j * 2] - t0, hbuf[200 + j * 4] - t0, hbuf[201 + j * 4] - t0, hbuf[202 + j * 4] - t0,
+               hbuf[203 + j * 4] - t0, hbuf[300 + j * 4] - t0, hbuf[301 + j * 4] - t0, hbuf[302 + j * 4] - t0, hbuf[303 + j * 4] - t0);
+      fflush(stdout);
+    }
+  }
+  return 0;
+}
+
 }  // namespace
 
 int attention_backward_ts(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
                           const int32_t* fnp, const float* dctx, const float* lse, const float* delta, float* dqkv) {
   if (d == 64) return launch_bwd<64>(st, B, S, h, qkv, x, fnp, dctx, lse, delta, dqkv);
   return launch_bwd<32>(st, B, S, h, qkv, x, fnp, dctx, lse, delta, dqkv);
+}
+
+int attention_forward_ts(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
+                         const int32_t* fnp, float* ctx, float* lse) {
+  if (d == 64) return launch_fwd<64>(st, B, S, h, qkv, x, fnp, ctx, lse);
+  return launch_fwd<32>(st, B, S, h, qkv, x, fnp, ctx, lse);
 }
 
 }  // namespace nlps

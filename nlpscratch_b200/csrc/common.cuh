@@ -181,6 +181,8 @@ int attention_backward_tc(cudaStream_t st, int B, int S, int h, int d, const flo
                           const int32_t* first_nonpad, const float* dctx, const float* lse, const float* delta,
                           float* dqkv);
 // attention_ts.cu (tcgen05 with the A operands in TMEM, head_dim 32 or 64)
+int attention_forward_ts(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
+                         const int32_t* fnp, float* ctx, float* lse);
 int attention_backward_ts(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
                           const int32_t* fnp, const float* dctx, const float* lse, const float* delta, float* dqkv);
 

@@ -21,13 +21,20 @@ def bwd():
     _lib.call("nlps_attention_backward", S0, C.c_int(1), C.c_int(B), C.c_int(S), C.c_int(h), C.c_int(d),
               _lib.vp(qkv.ptr), _lib.vp(x.ptr), _lib.vp(ctx.ptr), _lib.vp(lse.ptr), _lib.vp(dctx.ptr), _lib.vp(dqkv.ptr))
 def t(fn):
-    for _ in range(3): fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps): fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+    # median of 5 trials of `reps` launches after a generous warm-up (first launches pay module load and clocks)
+    import time
+    t0 = time.time()
+    while time.time() - t0 < 0.4:
+        for _ in range(10): fn()
+        torch.cuda.synchronize()
+    out = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps): fn()
+        e1.record(); torch.cuda.synchronize()
+        out.append(e0.elapsed_time(e1) / reps)
+    return sorted(out)[2]
 flops_fwd = 2.0 * 2 * B * h * S * S * d / 2      # causal half
 tf, tb = t(fwd), t(bwd)
 print("attention B=%d S=%d h=%d d=%d: fwd %.3f ms (%.1f TFLOP/s causal), bwd %.3f ms (%.1f TFLOP/s, 2.5x fwd flops)" % (
