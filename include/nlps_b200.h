@@ -211,6 +211,28 @@ int nlps_reduce_i32(void* stream, int op, int64_t n, const int32_t* d_a, int32_t
 int nlps_compare_ne_i32(void* stream, int64_t n, const int32_t* d_a, int32_t value, int32_t* d_out);
 int nlps_cast_i32_f32(void* stream, int64_t n, const int32_t* d_a, float* d_out);
 
+/* ---- dataset construction in front of the loop ---------------------------------
+ * generate_sequence_data / generate_bpe_sequence_data (Transformer/transformer_train.py:47-60,
+ * Transformer/transformer_train_bpe.py:52-65) with pad_sequence (Transformer/transformer.py:575-582).
+ * Sentences are a ragged int32 array: ids d_ids[d_sent_off[s] .. d_sent_off[s+1]).  Row r of X is the
+ * r-th proper prefix in sentence order (d_row_off[s] = sum over earlier sentences of max(len-1, 0),
+ * n_sent+1 entries, d_row_off[n_sent] = n_rows), right-padded with `pad`, keeping the LAST max_len
+ * ids of longer prefixes; Y[r] is the id that follows the prefix.  X is (n_rows, max_len) int32. */
+int nlps_prefix_dataset(void* stream, int n_sent, int64_t n_rows, int max_len, int32_t pad,
+                        const int32_t* d_ids, const int64_t* d_sent_off, const int64_t* d_row_off,
+                        int32_t* d_X, int32_t* d_Y);
+/* BPEEncoder.encode_ids over a batch of sentences (Transformer/bpe_encoder.py:225-249): word-type id w
+ * expands to d_tab_ids[d_tab_off[w] .. d_tab_off[w+1]) (the host builds this table once per word type,
+ * the reference's encode_word cache); bos/eos < 0 = not added.  Two calls: _offsets writes the n_sent+1
+ * output offsets (d_len_scratch: n_sent int32), the caller reads d_out_off[n_sent] to size d_out_ids,
+ * then _fill writes the ids. */
+int nlps_expand_tokens_offsets(void* stream, int n_sent, const int32_t* d_words, const int64_t* d_sent_off,
+                               const int32_t* d_tab_off, int32_t bos, int32_t eos, int32_t* d_len_scratch,
+                               int64_t* d_out_off);
+int nlps_expand_tokens_fill(void* stream, int n_sent, const int32_t* d_words, const int64_t* d_sent_off,
+                            const int32_t* d_tab_off, const int32_t* d_tab_ids, int32_t bos, int32_t eos,
+                            const int64_t* d_out_off, int32_t* d_out_ids);
+
 #ifdef __cplusplus
 }
 #endif

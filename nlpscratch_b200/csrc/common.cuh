@@ -166,6 +166,14 @@ int gemm_tf32x3(cudaStream_t st, const GemmArgs& g);     // 3-pass split, FP32-l
 bool gemm_tf32_supported(const GemmArgs& g);
 int gemm_dispatch(cudaStream_t st, int precision, const GemmArgs& g);
 
+// dataset.cu
+int prefix_dataset(cudaStream_t st, int n_sent, int64_t n_rows, int max_len, int32_t pad, const int32_t* ids,
+                   const int64_t* sent_off, const int64_t* row_off, int32_t* X, int32_t* Y);
+int expand_tokens_offsets(cudaStream_t st, int n_sent, const int32_t* words, const int64_t* sent_off, const int32_t* tab_off,
+                          int32_t bos, int32_t eos, int32_t* len_scratch, int64_t* out_off);
+int expand_tokens_fill(cudaStream_t st, int n_sent, const int32_t* words, const int64_t* sent_off, const int32_t* tab_off,
+                       const int32_t* tab_ids, int32_t bos, int32_t eos, const int64_t* out_off, int32_t* out_ids);
+
 // attention.cu
 int attention_forward(cudaStream_t st, int precision, int B, int S, int h, int d, const float* qkv,
                       const int32_t* x, const int32_t* first_nonpad, float* ctx, float* lse);

@@ -893,4 +893,21 @@ int nlps_cast_i32_f32(void* stream, int64_t n, const int32_t* a, float* out) {
   return cast_i32_f32((cudaStream_t)stream, n, a, out);
 }
 
+int nlps_prefix_dataset(void* stream, int n_sent, int64_t n_rows, int max_len, int32_t pad, const int32_t* d_ids,
+                        const int64_t* d_sent_off, const int64_t* d_row_off, int32_t* d_X, int32_t* d_Y) {
+  NLPS_REQUIRE(n_rows == 0 || (d_ids && d_sent_off && d_row_off && d_X && d_Y), "nlps_prefix_dataset: null argument");
+  return prefix_dataset((cudaStream_t)stream, n_sent, n_rows, max_len, pad, d_ids, d_sent_off, d_row_off, d_X, d_Y);
+}
+int nlps_expand_tokens_offsets(void* stream, int n_sent, const int32_t* d_words, const int64_t* d_sent_off,
+                               const int32_t* d_tab_off, int32_t bos, int32_t eos, int32_t* d_len_scratch, int64_t* d_out_off) {
+  NLPS_REQUIRE(d_words && d_sent_off && d_tab_off && d_len_scratch && d_out_off, "nlps_expand_tokens_offsets: null argument");
+  return expand_tokens_offsets((cudaStream_t)stream, n_sent, d_words, d_sent_off, d_tab_off, bos, eos, d_len_scratch, d_out_off);
+}
+int nlps_expand_tokens_fill(void* stream, int n_sent, const int32_t* d_words, const int64_t* d_sent_off,
+                            const int32_t* d_tab_off, const int32_t* d_tab_ids, int32_t bos, int32_t eos,
+                            const int64_t* d_out_off, int32_t* d_out_ids) {
+  NLPS_REQUIRE(d_words && d_sent_off && d_tab_off && d_tab_ids && d_out_off && d_out_ids, "nlps_expand_tokens_fill: null argument");
+  return expand_tokens_fill((cudaStream_t)stream, n_sent, d_words, d_sent_off, d_tab_off, d_tab_ids, bos, eos, d_out_off, d_out_ids);
+}
+
 }  // extern "C"
