@@ -25,7 +25,8 @@ namespace nlps {
 namespace {
 using namespace tc;
 
-constexpr int kThreads = 320;   // warp0 TMA + lse/delta staging, warp1 MMA + TMEM owner, warps 2-9 softmax
+constexpr int kThreads = 448;   // warp0 TMA + lse/delta staging, warp1 MMA + TMEM owner, warps 2-9 softmax, warps 10-13 re-swizzle
+constexpr int kSwzWarps = 4;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kTraceSlots = 4096;
 
@@ -206,6 +207,28 @@ __device__ __forceinline__ void load_swizzled_row(const uint8_t* tile, int r, ui
   }
 }
 
+// A streamed tile is needed in both operand majors (contracted over head_dim for S / dP, over its rows for
+// dK / dV / dQ).  For FP32 the two shared-memory images hold the same row-major rows of 128 B and differ only
+// in the swizzle: K-major SWIZZLE_128B stores 16-B chunk i of row r at i ^ (r & 7), the MN-major
+// SWIZZLE_128B_BASE32B image stores 32-B chunk j at j ^ (r & 3).  Two warps permute the chunks of the landed
+// K-major image into the second image -- the L2 -> SM traffic of the backward kernels (their bound) halves.
+__device__ __forceinline__ void reswizzle_rows(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int n_rows, int w, int lane) {
+  const int i = lane & 7;                                      // logical 16-B chunk of the row
+  for (int r0 = w * 4 + (lane >> 3); r0 < n_rows; r0 += 32 * kSwzWarps) {   // 8 loads in flight, then 8 stores
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = min(r0 + 4 * kSwzWarps * u, n_rows - 1);
+      v[u] = *reinterpret_cast<const uint4*>(src + r * 128 + ((i ^ (r & 7)) << 4));
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = r0 + 4 * kSwzWarps * u;
+      if (r < n_rows) *reinterpret_cast<uint4*>(dst + r * 128 + (((((i >> 1) ^ (r & 3)) << 1) | (i & 1)) << 4)) = v[u];
+    }
+  }
+}
+
 template <int D, int NS>
 struct Cfg {
   static constexpr int kAtoms = D / 32;                      // 128-byte atoms per row
@@ -272,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ts(const __grid_con
   trace(tr && threadIdx.x == 0, 0);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(kfull(s), 1); mbar_init(kfree(s), 1); mbar_init(mfull(s), 1); mbar_init(mfree(s), 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(kfull(s), 1); mbar_init(kfree(s), 1 + kSwzWarps); mbar_init(mfull(s), kSwzWarps); mbar_init(mfree(s), 1); }
     for (int b2 = 0; b2 < 2; ++b2) { mbar_init(sdp_full(b2), 1); mbar_init(pds_full(b2), 256); mbar_init(ld_full(b2), 32); }
     mbar_init(kv_full, 1); mbar_init(kv_done, 256); mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -321,15 +344,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ts(const __grid_con
         for (int a = 0; a < C::kAtoms; ++a) {
           tma_load_2d(kst + s * C::kStage + a * (64 * 128), &map_qk, kfull(s), head * D + a * 32, qrow);
           tma_load_2d(kst + s * C::kStage + C::kBlk + a * (64 * 128), &map_dok, kfull(s), head * D + a * 32, qrow);
-        }
-        if (it == 0) mbar_wait(kv_done, 0);          // K and V have left the first two MN stages
-        mbar_wait(mfree(s), free_par);
-        trace(tr, 101 + it * 2);
-        mbar_expect_tx(mfull(s), C::kStage);
-#pragma unroll
-        for (int a = 0; a < C::kAtoms; ++a) {
-          tma_load_2d(mst + s * C::kStage + a * (64 * 128), &map_qmn, mfull(s), head * D + a * 32, qrow);
-          tma_load_2d(mst + s * C::kStage + C::kBlk + a * (64 * 128), &map_domn, mfull(s), head * D + a * 32, qrow);
         }
       }
       __syncwarp();
@@ -394,6 +408,24 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ts(const __grid_con
     }
     if (elect_one_sync()) umma_commit(acc_full);
     __syncwarp();
+  } else if (warp >= 10) {
+    // ---------------- re-swizzle warps: MN-major images of the landed Q / dO tiles ----------------
+    const int w2 = warp - 10;
+    mbar_wait(kv_done, 0);                             // K and V have left the first two MN stages
+    for (int it = 0; more_blocks(it); ++it) {
+      const int s = it % NS;
+      const bool trc = tr && w2 == 0 && lane == 0 && it < 16;
+      trace(trc, 600 + it * 4);
+      mbar_wait(mfree(s), (uint32_t)((it / NS) & 1) ^ 1u);
+      trace(trc, 601 + it * 4);
+      mbar_wait(kfull(s), (uint32_t)((it / NS) & 1));
+      trace(trc, 602 + it * 4);
+      reswizzle_rows(base_ptr + s * C::kStage, mst_ptr + s * C::kStage, 2 * C::kAtoms * 64, w2, lane);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(mfull(s)); mbar_arrive(kfree(s)); }
+      trace(trc, 603 + it * 4);
+    }
   } else {
     // ---------------- softmax threads: (key row r, query half) ----------------
     const int cw = warp - 2;
@@ -550,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ts(const __grid_const
   const int row_base = b * p.S;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(kfull(s), 1); mbar_init(kfree(s), 1); mbar_init(mfull(s), 1); mbar_init(mfree(s), 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(kfull(s), 1); mbar_init(kfree(s), 1 + kSwzWarps); mbar_init(mfull(s), kSwzWarps); mbar_init(mfree(s), 1); }
     for (int b2 = 0; b2 < 2; ++b2) { mbar_init(sdp_full(b2), 1); mbar_init(ds_full(b2), 256); }
     mbar_init(res_full, 1); mbar_init(res_done, 256); mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -575,12 +607,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ts(const __grid_const
         const int s = kb % NS;
         const uint32_t free_par = (uint32_t)((kb / NS) & 1) ^ 1u;
         const int krow = row_base + kb * 64;
-        // the MN-major K tile does not depend on the prologue: issue it first
-        mbar_wait(mfree(s), free_par);
-        mbar_expect_tx(mfull(s), C::kBlk);
-#pragma unroll
-        for (int a = 0; a < C::kAtoms; ++a)
-          tma_load_2d(mst + s * C::kBlk + a * (64 * 128), &map_kmn, mfull(s), p.E + head * D + a * 32, krow);
         if (kb == 0) mbar_wait(res_done, 0);          // Q and dO have left the first two K-major stages
         mbar_wait(kfree(s), free_par);
         mbar_expect_tx(kfull(s), C::kStage);
@@ -633,6 +659,19 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ts(const __grid_const
     }
     if (elect_one_sync()) umma_commit(acc_full);
     __syncwarp();
+  } else if (warp >= 10) {
+    // re-swizzle warps: MN-major image of the landed K tile (B operand of dQ += dS K)
+    const int w2 = warp - 10;
+    uint8_t* mst_ptr = base_ptr + NS * C::kStage;
+    for (int kb = 0; more_blocks(kb); ++kb) {
+      const int s = kb % NS;
+      mbar_wait(mfree(s), (uint32_t)((kb / NS) & 1) ^ 1u);
+      mbar_wait(kfull(s), (uint32_t)((kb / NS) & 1));
+      reswizzle_rows(base_ptr + s * C::kStage, mst_ptr + s * C::kBlk, C::kAtoms * 64, w2, lane);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(mfull(s)); mbar_arrive(kfree(s)); }
+    }
   } else {
     const int cw = warp - 2;
     const int q = warp & 3;
@@ -779,9 +818,12 @@ int launch_bwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int
       printf("attn_bwd_dkdv_ts trace, key tile 0 (cycles since CTA start): accumulators ready %lld, stores done %lld\n", hbuf[1] - t0, hbuf[2] - t0);
       const int n_it = std::min(8, (S + 63) / 64);
       for (int it = 0; it < n_it; ++it)
-        printf("it %d | TMA K-major issue %6lld MN issue %6lld | MMA sdp start %6lld issued %6lld acc start %6lld issued %6lld | thread top %6lld sdp ready %6lld P/dS stored %6lld\n",
-               it, hbuf[100 + it * 2] - t0, hbuf[101 + it * 2] - t0, hbuf[200 + it * 4] - t0, hbuf[201 + it * 4] - t0,
+        printf("it %d | TMA issue %6lld | MMA sdp start %6lld issued %6lld acc start %6lld issued %6lld | thread top %6lld sdp ready %6lld P/dS stored %6lld\n",
+               it, hbuf[100 + it * 2] - t0, hbuf[200 + it * 4] - t0, hbuf[201 + it * 4] - t0,
                hbuf[202 + it * 4] - t0, hbuf[203 + it * 4] - t0, hbuf[300 + it * 3] - t0, hbuf[301 + it * 3] - t0, hbuf[302 + it * 3] - t0);
+      for (int it = 0; it < n_it; ++it)
+        printf("it %d | re-swizzle warp: top %6lld mfree %6lld kfull %6lld done %6lld\n", it, hbuf[600 + it * 4] - t0, hbuf[601 + it * 4] - t0,
+               hbuf[602 + it * 4] - t0, hbuf[603 + it * 4] - t0);
       for (int it = 0; it < n_it; ++it) {
         printf("it %d | mfull passed %6lld | per-warp P/dS stored:", it, hbuf[500 + it] - t0);
         for (int w = 0; w < 8; ++w) printf(" %6lld", hbuf[400 + it * 8 + w] - t0);
