@@ -780,6 +780,392 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ts(const __grid_const
   }
 }
 
+
+// ============================================================================================
+// Persistent dK / dV: one CTA per SM walks a heaviest-first list of (batch, head, 128-key) tiles.
+// Same per-block pipeline as attn_bwd_dkdv_ts; what changes is the tile boundary, which cost ~40 % of a
+// 5-block tile there (K/V load -> TMEM copy in front, accumulator drain behind, nothing overlapped):
+//   * K and V of tile i+1 are fetched into their own 64 KB buffer while tile i runs and are copied to TMEM
+//     BEFORE tile i's accumulators are drained, so the MMA warp forms S^T / dP^T of the next tile's first
+//     two query blocks while the threads store dV / dK;
+//   * the producer / re-swizzle warps simply keep going: stage and barrier parities run on a global
+//     block counter, the per-tile block count travels through a small ring in shared memory;
+//   * dV / dK leave as 256-bit row stores straight from registers (full 32-B sectors, no staging tile).
+// ============================================================================================
+template <int D>
+struct PsCfg {
+  static constexpr int NSK = 3;                              // K-major [Q | dO] stages (filled by TMA, latency-critical)
+  static constexpr int NSM = 2;                              // MN-major stages (filled by the re-swizzle warps)
+  static constexpr int kAtoms = D / 32;
+  static constexpr int kBlk = kAtoms * 64 * 128;
+  static constexpr int kStage = 2 * kBlk;                    // [Q | dO] block pair, also one resident 128-row tile
+  static constexpr int kKv = 2 * kStage;                     // K and V of the next tile
+  static constexpr int kCtl = 2048;
+  static constexpr int kSmemDkdv = (NSK + NSM) * kStage + kKv + kCtl + 1024;   // 227 KB for head_dim 64: the SM's limit
+  static constexpr int kTmemCols = 512;
+};
+
+// 32 floats of row r -> one 128-byte atom of a TMA SWIZZLE_128B tile [128 rows][128 B]
+__device__ __forceinline__ void put_row_sw128(uint8_t* atom, int r, const uint32_t (&v)[32], float scale) {
+  uint8_t* row = atom + r * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(row + ((j ^ (r & 7)) << 4)) =
+        make_float4(__uint_as_float(v[4 * j]) * scale, __uint_as_float(v[4 * j + 1]) * scale,
+                    __uint_as_float(v[4 * j + 2]) * scale, __uint_as_float(v[4 * j + 3]) * scale);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_constant__ CUtensorMap map_res,   // qkv, box {32,128}, K-major
+                                                              const __grid_constant__ CUtensorMap map_qk,    // qkv, box {32,64}, K-major
+                                                              const __grid_constant__ CUtensorMap map_dok,   // dctx, box {32,64}, K-major
+                                                              const __grid_constant__ CUtensorMap map_out,   // dqkv as (3E, S, B), box {32,128,1}
+                                                              const Dims p, const int n_tiles, const int32_t* __restrict__ x,
+                                                              const int32_t* __restrict__ fnp,
+                                                              const float* __restrict__ lse,
+                                                              const float* __restrict__ delta,
+                                                              float* __restrict__ dqkv) {
+  using C = PsCfg<D>;
+  constexpr int NSK = C::NSK, NSM = C::NSM;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t kst = base;                                  // NSK stages of [Q K-major | dO K-major]
+  uint8_t* mst_ptr = base_ptr + NSK * C::kStage;              // NSM stages of [Q MN-major | dO MN-major]
+  const uint32_t mst = base + NSK * C::kStage;
+  const uint32_t kvb = base + (NSK + NSM) * C::kStage;        // K | V of the upcoming tile
+  uint8_t* kvb_ptr = base_ptr + (NSK + NSM) * C::kStage;
+  const uint32_t bar = kvb + C::kKv;
+  uint8_t* ctl_ptr = kvb_ptr + C::kKv;
+  auto kfull = [&](int s) { return bar + 8u * s; };
+  auto kfree = [&](int s) { return bar + 8u * (4 + s); };
+  auto mfull = [&](int s) { return bar + 8u * (8 + s); };
+  auto mfree = [&](int s) { return bar + 8u * (12 + s); };
+  auto sdp_full = [&](int b2) { return bar + 8u * (16 + b2); };
+  auto pds_full = [&](int b2) { return bar + 8u * (18 + b2); };
+  auto ld_full = [&](int b2) { return bar + 8u * (20 + b2); };
+  const uint32_t kv_full = bar + 8u * 22, kv_done = bar + 8u * 23, acc_full = bar + 8u * 24, st_done = bar + 8u * 25, tmem_slot = bar + 8u * 26;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ctl_ptr + 8 * 26);
+  float* lse_s = reinterpret_cast<float*>(ctl_ptr + 256);     // [2][64]  -lse*log2e
+  float* delta_s = lse_s + 128;                               // [2][64]  -delta
+  volatile int* meta_s = reinterpret_cast<volatile int*>(ctl_ptr + 1280);   // ring of 4 x {block count, first_real}
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_bh = p.B * p.h;
+  const int n_q = (p.S + 63) / 64;
+  struct Tile { int b, head, k0; };
+  auto tile_of = [&](int t) {
+    Tile tl;
+    const int kt = t / n_bh, bh = t - kt * n_bh;              // key tile 0 has the most query blocks: first
+    tl.k0 = kt * 128;
+    tl.b = bh / p.h;
+    tl.head = bh - tl.b * p.h;
+    return tl;
+  };
+  // blocks of a tile: the causal ones [first_causal, n_q) first, then the fully-masked leading blocks [0, n_deg)
+  auto n_blocks = [&](const Tile& tl, int first_real) {
+    const int first_causal = tl.k0 / 64;
+    return (n_q - first_causal) + min(min((first_real + 63) / 64, n_q), first_causal);
+  };
+  auto block_of = [&](const Tile& tl, int it) {
+    const int first_causal = tl.k0 / 64, n_causal = n_q - first_causal;
+    return it < n_causal ? first_causal + it : it - n_causal;
+  };
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NSK; ++s) { mbar_init(kfull(s), 1); mbar_init(kfree(s), 1 + kSwzWarps); }
+    for (int s = 0; s < NSM; ++s) { mbar_init(mfull(s), kSwzWarps); mbar_init(mfree(s), 1); }
+    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(sdp_full(b2), 1); mbar_init(pds_full(b2), 256); mbar_init(ld_full(b2), 32); }
+    mbar_init(kv_full, 1); mbar_init(kv_done, 256); mbar_init(acc_full, 1); mbar_init(st_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t t_k = tmem, t_v = tmem + D, t_st = tmem + 2 * D, t_dpt = t_st + 128, t_dv = t_dpt + 128, t_dk = t_dv + D;
+
+  if (warp == 0) {
+    // ---------------- producer: TMA + lse/delta staging + tile metadata ----------------
+    auto issue_kv = [&](const Tile& tl, int idx, int first_real) {      // lane 0 only
+      meta_s[(idx & 3) * 2] = n_blocks(tl, first_real);
+      meta_s[(idx & 3) * 2 + 1] = first_real;
+      mbar_expect_tx(kv_full, C::kKv);                                   // (release: the ring entry is visible to every waiter)
+#pragma unroll
+      for (int a = 0; a < C::kAtoms; ++a) {
+        tma_load_2d(kvb + a * (128 * 128), &map_res, kv_full, p.E + tl.head * D + a * 32, tl.b * p.S + tl.k0);
+        tma_load_2d(kvb + C::kStage + a * (128 * 128), &map_res, kv_full, 2 * p.E + tl.head * D + a * 32, tl.b * p.S + tl.k0);
+      }
+    };
+    float nl_r[2], nd_r[2];
+    auto fetch_ld = [&](const Tile& tl, int it) {                        // raw values only (see attn_bwd_dkdv_ts)
+      const int64_t so = ((int64_t)tl.b * p.h + tl.head) * p.S;
+      const int q0 = block_of(tl, it) * 64;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int qi = min(q0 + lane + 32 * j, p.S - 1);
+        nl_r[j] = __ldg(lse + so + qi);
+        nd_r[j] = __ldg(delta + so + qi);
+      }
+    };
+    Tile tl = tile_of(blockIdx.x);
+    int first_real = __ldg(fnp + tl.b);
+    if (lane == 0) issue_kv(tl, 0, first_real);
+    fetch_ld(tl, 0);
+    int g = 0, i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const int n_it = n_blocks(tl, first_real);
+      const int t_next = t + gridDim.x;
+      Tile tn = tl;
+      int fr_next = 0;
+      if (t_next < n_tiles) { tn = tile_of(t_next); fr_next = __ldg(fnp + tn.b); }
+      for (int it = 0; it < n_it; ++it, ++g) {
+        const int s = g % NSK;
+        if (lane == 0) {
+          const int qrow = tl.b * p.S + block_of(tl, it) * 64;
+          mbar_wait(kfree(s), (uint32_t)((g / NSK) & 1) ^ 1u);
+          mbar_expect_tx(kfull(s), C::kStage);
+#pragma unroll
+          for (int a = 0; a < C::kAtoms; ++a) {
+            tma_load_2d(kst + s * C::kStage + a * (64 * 128), &map_qk, kfull(s), tl.head * D + a * 32, qrow);
+            tma_load_2d(kst + s * C::kStage + C::kBlk + a * (64 * 128), &map_dok, kfull(s), tl.head * D + a * 32, qrow);
+          }
+          if (it == min(1, n_it - 1) && t_next < n_tiles) {
+            mbar_wait(kv_done, (uint32_t)(i & 1));             // this tile's K / V have left the buffer ...
+            if (i > 0) mbar_wait(st_done, (uint32_t)((i - 1) & 1));   // ... and so has the previous tile's dV / dK (it doubles as their store staging)
+            issue_kv(tn, i + 1, fr_next);
+          }
+        }
+        __syncwarp();
+        const int b2 = g & 1;
+        if (g >= 2) mbar_wait(pds_full(b2), (uint32_t)(((g - 2) >> 1) & 1));   // threads are done with this lse/delta stage
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          lse_s[b2 * 64 + lane + 32 * j] = -nl_r[j] * kLog2e;
+          delta_s[b2 * 64 + lane + 32 * j] = -nd_r[j];
+        }
+        mbar_arrive(ld_full(b2));
+        if (it + 1 < n_it) fetch_ld(tl, it + 1);
+        else if (t_next < n_tiles) fetch_ld(tn, 0);
+      }
+      tl = tn;
+      first_real = fr_next;
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc_t = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int g0 = 0, i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      mbar_wait(kv_done, (uint32_t)(i & 1));                   // K and V of this tile are in TMEM
+      tc_fence_after();
+      const int n_it = meta_s[(i & 3) * 2];
+      auto issue_sdp = [&](int it) {        // S^T = K Q^T ; dP^T = V dO^T   (A = K / V in TMEM)
+        const int g = g0 + it, s = g % NSK, b2 = g & 1;
+        mbar_wait(kfull(s), (uint32_t)((g / NSK) & 1));
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t qk = make_desc(kst + s * C::kStage, 16, 1024, 2), dok = make_desc(kst + s * C::kStage + C::kBlk, 16, 1024, 2);
+#pragma unroll
+          for (int kk = 0; kk < D / 8; ++kk) {
+            const uint64_t bo = (uint64_t)(((kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4);
+            umma_tf32_ts(t_st + b2 * 64, t_k + kk * 8, qk + bo, idesc_t, kk > 0 ? 1u : 0u);
+            umma_tf32_ts(t_dpt + b2 * 64, t_v + kk * 8, dok + bo, idesc_t, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(sdp_full(b2));
+          umma_commit(kfree(s));
+        }
+        __syncwarp();
+      };
+      issue_sdp(0);
+      if (n_it > 1) issue_sdp(1);
+      for (int it = 0; it < n_it; ++it) {
+        const int g = g0 + it, s = g % NSM, b2 = g & 1;
+        mbar_wait(mfull(s), (uint32_t)((g / NSM) & 1));
+        mbar_wait(pds_full(b2), (uint32_t)((g >> 1) & 1));
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t qmn = make_desc(mst + s * C::kStage, 64 * 128, 512, 1), domn = make_desc(mst + s * C::kStage + C::kBlk, 64 * 128, 512, 1);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {      // dV += P^T dO ; dK += dS^T Q   (K = 64 queries, A = P^T / dS^T in TMEM)
+            const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+            umma_tf32_ts(t_dv, t_st + b2 * 64 + kk * 8, domn + (uint64_t)(kk * 64), idesc_a, acc);
+            umma_tf32_ts(t_dk, t_dpt + b2 * 64 + kk * 8, qmn + (uint64_t)(kk * 64), idesc_a, acc);
+          }
+          umma_commit(mfree(s));
+          if (it == n_it - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
+        if (it + 2 < n_it) issue_sdp(it + 2);
+      }
+      g0 += n_it;
+    }
+  } else if (warp >= 10) {
+    // ---------------- re-swizzle warps ----------------
+    const int w4 = warp - 10;
+    int g = 0, i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      mbar_wait(kv_full, (uint32_t)(i & 1));                   // (acquire) this tile's ring entry is visible
+      const int n_it = meta_s[(i & 3) * 2];
+      for (int it = 0; it < n_it; ++it, ++g) {
+        const int sk = g % NSK, sm = g % NSM;
+        mbar_wait(mfree(sm), (uint32_t)((g / NSM) & 1) ^ 1u);
+        mbar_wait(kfull(sk), (uint32_t)((g / NSK) & 1));
+        reswizzle_rows(base_ptr + sk * C::kStage, mst_ptr + sm * C::kStage, 2 * C::kAtoms * 64, w4, lane);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(mfull(sm)); mbar_arrive(kfree(sk)); }
+      }
+    }
+  } else {
+    // ---------------- softmax threads: (key row r, query half) ----------------
+    const int cw = warp - 2;
+    const int q = warp & 3;
+    const int half = cw >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint64_t scale2 = pack2f(p.scale_log2, p.scale_log2);
+    const float scale = p.scale_log2 * (1.f / kLog2e);
+    const bool storer = cw == 0 && lane == 0;
+
+    auto stage_kv = [&](int idx) {                             // resident K and V: buffer -> TMEM (32 columns per thread)
+      mbar_wait(kv_full, (uint32_t)(idx & 1));
+      uint32_t v[32];
+      if (D == 64) {
+        load_swizzled_row(kvb_ptr + half * (128 * 128), r, v);
+        tmem_st32(t_k + lane_addr + half * 32, v);
+        load_swizzled_row(kvb_ptr + C::kStage + half * (128 * 128), r, v);
+        tmem_st32(t_v + lane_addr + half * 32, v);
+      } else {
+        load_swizzled_row(kvb_ptr + half * C::kStage, r, v);
+        tmem_st32((half ? t_v : t_k) + lane_addr, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(kv_done);
+    };
+
+    Tile tl = tile_of(blockIdx.x);
+    int key_id = (tl.k0 + r < p.S) ? __ldg(x + (int64_t)tl.b * p.S + tl.k0 + r) : 0;
+    const bool trs = p.trace && blockIdx.x == 5 && cw == 0 && lane == 0;
+    trace(trs, 0);
+    stage_kv(0);
+    int g0 = 0, i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const int n_it = meta_s[(i & 3) * 2], first_real = meta_s[(i & 3) * 2 + 1];
+      const int key = tl.k0 + r;
+      const bool key_ok = key < p.S;
+      const bool key_pad = key_id == 0;
+      const int t_next = t + gridDim.x;
+      Tile tn = tl;
+      int key_id_next = 0;
+      if (t_next < n_tiles) {                                  // requested now, consumed a whole tile later
+        tn = tile_of(t_next);
+        key_id_next = (tn.k0 + r < p.S) ? __ldg(x + (int64_t)tn.b * p.S + tn.k0 + r) : 0;
+      }
+      trace(trs && i < 16, 700 + i * 8);
+      if (trs && i < 16) g_ts_trace[707 + i * 8] = n_it;
+      for (int it = 0; it < n_it; ++it) {
+        const int g = g0 + it, b2 = g & 1;
+        const uint32_t ph = (uint32_t)((g >> 1) & 1);
+        const int qb = block_of(tl, it) * 64 + half * 32;     // first query of this thread's 32 columns
+        const uint32_t range_bits = low_bits32(p.S - qb);
+        const uint32_t causal = (key_ok && !key_pad) ? ~low_bits32(key - qb) : 0u;
+        const uint32_t degq = key_ok ? low_bits32(first_real - qb) : 0u;
+        const uint32_t vis = (causal | degq) & range_bits;
+        mbar_wait(ld_full(b2), ph);
+        mbar_wait(sdp_full(b2), ph);
+        tc_fence_after();
+        if (it == 0) trace(trs && i < 16, 701 + i * 8);
+        uint32_t sv[32], dv[32];
+        const uint32_t a_s = t_st + b2 * 64 + half * 32 + lane_addr, a_d = t_dpt + b2 * 64 + half * 32 + lane_addr;
+        tmem_ld32_nowait(a_s, sv);
+        tmem_ld32_nowait(a_d, dv);
+        tmem_ld_wait();
+        const float4* l4 = reinterpret_cast<const float4*>(lse_s + b2 * 64 + half * 32);
+        const float4* d4 = reinterpret_cast<const float4*>(delta_s + b2 * 64 + half * 32);
+        if (__all_sync(0xffffffffu, vis == ~0u)) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 nl = l4[c], nd = d4[c];
+            p_ds_pair<false, true>(sv[4 * c], sv[4 * c + 1], dv[4 * c], dv[4 * c + 1], scale2, pack2f(nl.x, nl.y), pack2f(nd.x, nd.y), vis, 4 * c);
+            p_ds_pair<false, true>(sv[4 * c + 2], sv[4 * c + 3], dv[4 * c + 2], dv[4 * c + 3], scale2, pack2f(nl.z, nl.w), pack2f(nd.z, nd.w), vis, 4 * c + 2);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 nl = l4[c], nd = d4[c];
+            p_ds_pair<true, true>(sv[4 * c], sv[4 * c + 1], dv[4 * c], dv[4 * c + 1], scale2, pack2f(nl.x, nl.y), pack2f(nd.x, nd.y), vis, 4 * c);
+            p_ds_pair<true, true>(sv[4 * c + 2], sv[4 * c + 3], dv[4 * c + 2], dv[4 * c + 3], scale2, pack2f(nl.z, nl.w), pack2f(nd.z, nd.w), vis, 4 * c + 2);
+          }
+        }
+        tmem_st32(a_s, sv);
+        tmem_st32(a_d, dv);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(pds_full(b2));
+        if (it == 0 && i > 0 && storer) {                      // the previous tile's bulk store has had a whole block to read its staging
+          bulk_wait_read0();
+          mbar_arrive(st_done);
+        }
+      }
+      g0 += n_it;
+      trace(trs && i < 16, 702 + i * 8);
+      // every S^T / dP^T product of this tile has retired (its results were read above): K / V of the next tile
+      // go to TMEM now, so the tensor pipe has work while this tile's accumulators drain
+      if (t_next < n_tiles) stage_kv(i + 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // every thread has left the K/V buffer: it becomes the store staging
+      trace(trs && i < 16, 703 + i * 8);
+      mbar_wait(acc_full, (uint32_t)(i & 1));
+      tc_fence_after();
+      trace(trs && i < 16, 704 + i * 8);
+      {
+        // accumulators -> SWIZZLE_128B tiles in shared memory -> asynchronous TMA stores (rows past the end of the
+        // sequence are clipped by the 3-D tensor map); the threads go straight on to the next tile
+        uint8_t* dv_tile = kvb_ptr;
+        uint8_t* dk_tile = kvb_ptr + C::kStage;
+        uint32_t a[32];
+        if (D == 64) {
+          tmem_ld32_nowait(t_dv + lane_addr + half * 32, a);
+          tmem_ld_wait();
+          put_row_sw128(dv_tile + half * (128 * 128), r, a, 1.f);
+          tmem_ld32_nowait(t_dk + lane_addr + half * 32, a);
+          tmem_ld_wait();
+          put_row_sw128(dk_tile + half * (128 * 128), r, a, scale);
+        } else {
+          tmem_ld32_nowait((half ? t_dk : t_dv) + lane_addr, a);
+          tmem_ld_wait();
+          put_row_sw128(half ? dk_tile : dv_tile, r, a, half ? scale : 1.f);
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (storer) {
+#pragma unroll
+          for (int at = 0; at < C::kAtoms; ++at) {
+            tma_store_3d(&map_out, kvb + at * (128 * 128), 2 * p.E + tl.head * D + at * 32, tl.k0, tl.b);
+            tma_store_3d(&map_out, kvb + C::kStage + at * (128 * 128), p.E + tl.head * D + at * 32, tl.k0, tl.b);
+          }
+          bulk_commit();
+        }
+      }
+      tc_fence_before();                                       // the drain is ordered before the next tile's pds_full arrivals
+      trace(trs && i < 16, 705 + i * 8);
+      tl = tn;
+      key_id = key_id_next;
+    }
+    if (storer) bulk_wait_read0();                             // the last tile's staging must outlive its store
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, C::kTmemCols);
+  }
+}
+
 template <int D>
 int launch_bwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int32_t* x, const int32_t* fnp,
                const float* dctx, const float* lse, const float* delta, float* dqkv) {
@@ -804,7 +1190,36 @@ int launch_bwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int
   if (trace_on < 0) { const char* e = getenv("NLPS_ATTN_TRACE"); trace_on = (e && e[0] == '2') ? 1 : 0; }
   Dims p{B, S, h, E, (float)(1.0 / std::sqrt((double)D)) * kLog2e, trace_on};
   dim3 grid((unsigned)ceil_div(S, 128), (unsigned)h, (unsigned)B);
-  attn_bwd_dkdv_ts<D, NS><<<grid, kThreads, C::kSmemDkdv, st>>>(res, qk, qmn, dok, domn, p, x, fnp, lse, delta, dqkv);
+  static int persistent = -1;
+  if (persistent < 0) { const char* e = getenv("NLPS_ATTN_PS"); persistent = (e && e[0] == '0') ? 0 : 1; }
+  const int64_t n_tiles = ceil_div(S, 128) * (int64_t)B * h;
+  if (persistent && (reinterpret_cast<uintptr_t>(dqkv) & 31u) == 0 && n_tiles < (1ll << 30)) {
+    static bool once_ps = false;
+    if (!once_ps) {
+      NLPS_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_ps<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, PsCfg<D>::kSmemDkdv));
+      once_ps = true;
+    }
+    CUtensorMap out3;
+    NLPS_TRY(make_map3(&out3, dqkv, 3 * (uint64_t)E, (uint64_t)S, (uint64_t)B, 3 * (int64_t)E, (int64_t)S * 3 * E, 32, 128));
+    attn_bwd_dkdv_ps<D><<<(unsigned)std::min<int64_t>(n_tiles, kNumSMs), kThreads, PsCfg<D>::kSmemDkdv, st>>>(
+        res, qk, dok, out3, p, (int)n_tiles, x, fnp, lse, delta, dqkv);
+    if (trace_on) {
+      static int printed_ps = 0;
+      if (printed_ps++ == 3) {
+        static long long hb[kTraceSlots];
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(hb, g_ts_trace, sizeof(hb));
+        const long long t0 = hb[0];
+        printf("attn_bwd_dkdv_ps trace, CTA 5 (cycles since the threads started)\n");
+        for (int i = 0; i < 14; ++i)
+          printf("tile %2d (%lld blocks) | loop top %7lld first S^T ready %7lld loop done %7lld next K/V in TMEM %7lld acc_full %7lld drained %7lld\n", i,
+                 hb[707 + i * 8], hb[700 + i * 8] - t0, hb[701 + i * 8] - t0, hb[702 + i * 8] - t0, hb[703 + i * 8] - t0, hb[704 + i * 8] - t0, hb[705 + i * 8] - t0);
+        fflush(stdout);
+      }
+    }
+  } else {
+    attn_bwd_dkdv_ts<D, NS><<<grid, kThreads, C::kSmemDkdv, st>>>(res, qk, qmn, dok, domn, p, x, fnp, lse, delta, dqkv);
+  }
   NLPS_LAUNCH_CHECK();
   attn_bwd_dq_ts<D, NS><<<grid, kThreads, C::kSmemDq, st>>>(res, dores, qk, qmn, p, x, fnp, lse, delta, dqkv);
   NLPS_LAUNCH_CHECK();

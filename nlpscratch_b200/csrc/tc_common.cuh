@@ -172,6 +172,28 @@ inline int make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t
   return 0;
 }
 
+// 3-D fp32 tensor map (inner, rows, batches) for TMA STORES of per-sequence tiles: rows past `rows` are clipped,
+// so a 128-row tile that overhangs the end of one sequence never touches the next one.
+inline int make_map3(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t rows, uint64_t batches, int64_t ld_row,
+                     int64_t ld_batch, uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  NLPS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  cuuint64_t dims[3] = {inner, rows, batches};
+  cuuint64_t strides[2] = {(cuuint64_t)ld_row * 4, (cuuint64_t)ld_batch * 4};
+  cuuint32_t box[3] = {box_inner, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NLPS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+  return 0;
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 }  // namespace tc
 }  // namespace nlps
