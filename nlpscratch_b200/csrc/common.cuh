@@ -211,7 +211,10 @@ int layernorm_backward(cudaStream_t st, int64_t rows, int E, const float* dy, co
 size_t layernorm_backward_scratch_floats(int E);
 int softmax_xent(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
                  float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss_scratch);
-int colsum(cudaStream_t st, int64_t rows, int cols, const float* x, int64_t ld, float* out, float* scratch);
+// tickets: ceil(cols/128) zero-initialised counters (self-resetting) -> the reduction finishes inside the one kernel;
+// nullptr -> separate finish kernel
+int colsum(cudaStream_t st, int64_t rows, int cols, const float* x, int64_t ld, float* out, float* scratch,
+           unsigned int* tickets = nullptr);
 size_t colsum_scratch_floats(int cols);
 int sumsq(cudaStream_t st, int64_t n, const float* x, float* out, float* scratch);
 size_t sumsq_scratch_floats();

@@ -609,6 +609,38 @@ __global__ void splitk_reduce_kernel(const KernelArgs ka) {
   }
 }
 
+// weight-gradient case (no fused epilogue operands, 16-B aligned rows): float4 lanes, all split loads of a thread in
+// flight before the adds; same split order as the scalar kernel => same bits
+__global__ void __launch_bounds__(256) splitk_reduce_vec_kernel(const KernelArgs ka) {
+  const GemmArgs& g = ka.g;
+  const int n4 = g.N >> 2;
+  const int64_t total = (int64_t)g.M * n4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / n4), col = (int)(i - (int64_t)row * n4) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* src = ka.ws + (int64_t)row * ka.ws_ld + col;
+    const int64_t sstride = (int64_t)g.M * ka.ws_ld;
+    int s = 0;
+    for (; s + 4 <= ka.splits; s += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(src + (s + 0) * sstride);
+      const float4 b = *reinterpret_cast<const float4*>(src + (s + 1) * sstride);
+      const float4 c = *reinterpret_cast<const float4*>(src + (s + 2) * sstride);
+      const float4 d = *reinterpret_cast<const float4*>(src + (s + 3) * sstride);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+      acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+      acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+      acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+    }
+    for (; s < ka.splits; ++s) {
+      const float4 a = *reinterpret_cast<const float4*>(src + s * sstride);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(g.C + (int64_t)row * g.ldc + col);
+    if (g.accumulate) { const float4 o = *dst; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+    *dst = acc;
+  }
+}
+
 // hi = round-to-nearest TF32 of x (low 13 mantissa bits zero), lo = x - hi (exact in FP32)
 __global__ void split_hi_lo_kernel(const float* __restrict__ src, int64_t ld, int rows, int cols, int64_t ldo,
                                    float* __restrict__ hi, float* __restrict__ lo) {
@@ -764,8 +796,15 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
   }
   if (splits > 1) {
     const int64_t total = (int64_t)g.M * g.N;
-    const int rgrid = (int)std::min<int64_t>(ceil_div(total, 256), kNumSMs * 8);
-    splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(ka);
+    const bool plain = !g.bias && !g.relu && !g.gate && !g.gate_bits && !g.relu_bits_out && g.drop.p <= 0.f && !g.residual &&
+                       g.N % 4 == 0 && ka.ws_ld % 4 == 0 && g.ldc % 4 == 0 && aligned16(g.C) && aligned16(ka.ws);
+    if (plain) {
+      const int rgrid = (int)std::min<int64_t>(ceil_div(total / 4, 256), kNumSMs * 8);
+      splitk_reduce_vec_kernel<<<rgrid, 256, 0, st>>>(ka);
+    } else {
+      const int rgrid = (int)std::min<int64_t>(ceil_div(total, 256), kNumSMs * 8);
+      splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(ka);
+    }
     NLPS_LAUNCH_CHECK();
   }
   return 0;

@@ -77,6 +77,7 @@ struct nlps_model {
   int64_t rows_tmp_cap = 0;
   // fixed scratch
   float *ln_partial = nullptr, *colsum_scratch = nullptr, *sumsq_scratch = nullptr;
+  unsigned int* colsum_tickets = nullptr;     // 4096 self-resetting counters: one per 128-column group of a colsum
   float* scalars = nullptr;          // [0]=sumsq [1]=clip scale [2]=norm [3]=loss
   int32_t* err_flag = nullptr;
 
@@ -164,6 +165,8 @@ DropoutParams drop_for(const nlps_model* m, const nlps_cache* c, int layer, int 
   return make_dropout(c->drop_p, m->seed, (uint32_t)(layer * 2 + which), c->drop_step);
 }
 
+inline unsigned int* colsum_tickets_for(nlps_model* m, int64_t cols) { return ceil_div(cols, 128) <= 4096 ? m->colsum_tickets : nullptr; }
+
 int record_bucket(nlps_model* m, int bucket) {
   NLPS_CUDA(cudaEventRecord(m->bucket_ev[bucket], m->stream));
   return 0;
@@ -190,7 +193,7 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
       GemmArgs g = gemm_nn(F, E, N, a.hid, F, d_f, E, m->G + o.w2, E);
       g.trans_a = true;
       NLPS_TRY(gemm_dispatch(st, prec, g));
-      NLPS_TRY(colsum(st, N, E, d_f, E, m->G + o.b2, m->colsum_scratch));
+      NLPS_TRY(colsum(st, N, E, d_f, E, m->G + o.b2, m->colsum_scratch, colsum_tickets_for(m, E)));
     }
     {  // dz = (d_f W2^T) * (hid > 0)
       GemmArgs g = gemm_nn(N, F, E, d_f, E, m->P + o.w2, E, m->dhid, F);
@@ -203,7 +206,7 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
       GemmArgs g = gemm_nn(E, F, N, a.y1, E, m->dhid, F, m->G + o.w1, F);
       g.trans_a = true;
       NLPS_TRY(gemm_dispatch(st, prec, g));
-      NLPS_TRY(colsum(st, N, F, m->dhid, F, m->G + o.b1, m->colsum_scratch));
+      NLPS_TRY(colsum(st, N, F, m->dhid, F, m->G + o.b1, m->colsum_scratch, colsum_tickets_for(m, F)));
     }
     {  // d(y1) = dz W1^T + d_r2
       GemmArgs g = gemm_nn(N, E, F, m->dhid, F, m->P + o.w1, F, m->g0, E);
@@ -363,6 +366,8 @@ int nlps_create(const nlps_config* cfg, int device, nlps_model** out) {
   }
   NLPS_CUDA(cudaMalloc(&m->ln_partial, sizeof(float) * layernorm_backward_scratch_floats(m->E)));
   NLPS_CUDA(cudaMalloc(&m->colsum_scratch, sizeof(float) * colsum_scratch_floats(std::max<int64_t>(std::max(m->E, m->F), m->ldV))));
+  NLPS_CUDA(cudaMalloc(&m->colsum_tickets, sizeof(unsigned int) * 4096));
+  NLPS_CUDA(cudaMemset(m->colsum_tickets, 0, sizeof(unsigned int) * 4096));
   NLPS_CUDA(cudaMalloc(&m->sumsq_scratch, sizeof(float) * sumsq_scratch_floats()));
   NLPS_CUDA(cudaMalloc(&m->scalars, sizeof(float) * 16));
   NLPS_CUDA(cudaMemset(m->scalars, 0, sizeof(float) * 16));
@@ -385,6 +390,7 @@ int nlps_destroy(nlps_model* m) {
   for (float* b : bufs) if (b) cudaFree(b);
   if (m->iscratch) cudaFree(m->iscratch);
   if (m->err_flag) cudaFree(m->err_flag);
+  if (m->colsum_tickets) cudaFree(m->colsum_tickets);
   for (auto& e : m->bucket_ev) cudaEventDestroy(e);
   if (m->aux_ev) cudaEventDestroy(m->aux_ev);
   delete m;
@@ -647,7 +653,7 @@ int nlps_backward(nlps_model* m, nlps_cache* c, const float* d_dlogits, int64_t 
     GemmArgs g = gemm_nn(E, m->V, N, h_final, E, d_dlogits, ldd, m->G + m->off_Wvocab, m->ldV);
     g.trans_a = true;
     NLPS_TRY(gemm_dispatch(st, m->precision, g));
-    NLPS_TRY(colsum(st, N, m->V, d_dlogits, ldd, m->G + m->off_bvocab, m->colsum_scratch));
+    NLPS_TRY(colsum(st, N, m->V, d_dlogits, ldd, m->G + m->off_bvocab, m->colsum_scratch, colsum_tickets_for(m, m->V)));
   }
   {  // dH = dlogits W_vocab^T                                          (:355)
     GemmArgs g = gemm_nn(N, E, m->V, d_dlogits, ldd, m->P + m->off_Wvocab, m->ldV, m->g0, E);
@@ -675,7 +681,7 @@ int nlps_backward_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_t, c
     GemmArgs g = gemm_nn(E, m->V, B, h_last, E, d_dl, ldd, m->G + m->off_Wvocab, m->ldV);
     g.trans_a = true;
     NLPS_TRY(gemm_dispatch(st, m->precision, g));
-    NLPS_TRY(colsum(st, B, m->V, d_dl, ldd, m->G + m->off_bvocab, m->colsum_scratch));
+    NLPS_TRY(colsum(st, B, m->V, d_dl, ldd, m->G + m->off_bvocab, m->colsum_scratch, colsum_tickets_for(m, m->V)));
   }
   {  // dH[arange(B), t] = dlogits_last W_vocab^T, zero elsewhere       (:239-240)
     GemmArgs g = gemm_nn(B, E, m->V, d_dl, ldd, m->P + m->off_Wvocab, m->ldV, dh_rows, E);

@@ -178,8 +178,15 @@ __global__ void __launch_bounds__(256) ln_bwd_finish_kernel(int nparts, int E, c
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;               // column in the concatenated [dgamma | dbeta] row
   float acc = 0.f;
-  if (c < 2 * E)
-    for (int p = warp; p < nparts; p += 8) acc += partial[(int64_t)p * 2 * E + c];
+  if (c < 2 * E) {
+    int p = warp;
+    for (; p + 24 < nparts; p += 32) {                  // four loads in flight, added in slice order
+      const float a = partial[(int64_t)p * 2 * E + c], b = partial[(int64_t)(p + 8) * 2 * E + c];
+      const float d = partial[(int64_t)(p + 16) * 2 * E + c], e = partial[(int64_t)(p + 24) * 2 * E + c];
+      acc += a; acc += b; acc += d; acc += e;
+    }
+    for (; p < nparts; p += 8) acc += partial[(int64_t)p * 2 * E + c];
+  }
   sm[warp][lane] = acc;
   __syncthreads();
   if (warp == 0 && c < 2 * E) {
@@ -278,9 +285,13 @@ __global__ void __launch_bounds__(1024) sum_to_scalar_kernel(const float* __rest
 constexpr int kColSlabsMax = 256;
 // block = 32 lanes x 8 warps; a lane owns 4 adjacent columns (float4), a warp walks rows of its slab
 // with 4 independent loads in flight; grid = (ceil(cols/128), slabs).  Fixed partition => deterministic.
+// The LAST slab CTA of a 128-column group (ticket counter in global memory, reset by its taker) adds the slab
+// partials in the fixed order of colsum_finish_kernel: same bits, one launch and one drain/fill bubble fewer.
 __global__ void __launch_bounds__(256) colsum_partial_kernel(int64_t rows, int cols, const float* __restrict__ x,
-                                                             int64_t ld, float* __restrict__ partial, int vec) {
+                                                             int64_t ld, float* __restrict__ partial, int vec,
+                                                             unsigned int* __restrict__ tickets, float* __restrict__ out) {
   __shared__ float4 sm[8][32];
+  __shared__ unsigned int ticket_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + lane) * 4;
   const int64_t rows_per = (rows + gridDim.y - 1) / gridDim.y;
@@ -322,6 +333,36 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(int64_t rows, int c
     if (col + 2 < cols) dst[2] = t.z;
     if (col + 3 < cols) dst[3] = t.w;
   }
+  if (tickets == nullptr) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ticket_s = atomicAdd(tickets + blockIdx.x, 1u);
+  __syncthreads();
+  if (ticket_s != gridDim.y - 1) return;
+  __threadfence();
+  // slab-major sums exactly like colsum_finish_kernel: warp w adds slabs w, w+8, ..., then the 8 warp sums in order
+  const int nparts = (int)gridDim.y;
+  float4 acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = warp; p < nparts; p += 8) {
+    const volatile float* src = partial + (int64_t)p * cols + col;
+    if (col + 0 < cols) acc2.x += src[0];
+    if (col + 1 < cols) acc2.y += src[1];
+    if (col + 2 < cols) acc2.z += src[2];
+    if (col + 3 < cols) acc2.w += src[3];
+  }
+  __syncthreads();
+  sm[warp][lane] = acc2;
+  __syncthreads();
+  if (warp == 0) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const float4 u = sm[w][lane]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    if (col + 0 < cols) out[col + 0] = t.x;
+    if (col + 1 < cols) out[col + 1] = t.y;
+    if (col + 2 < cols) out[col + 2] = t.z;
+    if (col + 3 < cols) out[col + 3] = t.w;
+  }
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;     // ready for the next launch on this scratch
 }
 // block = 32 columns x 8 partial-slices
 __global__ void __launch_bounds__(256) colsum_finish_kernel(int nparts, int cols, const float* __restrict__ partial,
@@ -468,7 +509,8 @@ int softmax_xent(cudaStream_t st, const float* logits, int64_t ld, const int32_t
 
 size_t colsum_scratch_floats(int cols) { return (size_t)kColSlabsMax * cols; }
 
-int colsum(cudaStream_t st, int64_t rows, int cols, const float* x, int64_t ld, float* out, float* scratch) {
+int colsum(cudaStream_t st, int64_t rows, int cols, const float* x, int64_t ld, float* out, float* scratch,
+           unsigned int* tickets) {
   if (cols <= 0) return 0;
   const int gx = (int)ceil_div(cols, 128);
   // enough row slabs to put ~4 CTAs on every SM, at least 32 rows each
@@ -476,7 +518,12 @@ int colsum(cudaStream_t st, int64_t rows, int cols, const float* x, int64_t ld, 
   slabs = (int)std::max<int64_t>(1, std::min<int64_t>(slabs, ceil_div(rows, 32)));
   const int vec = (ld % 4 == 0 && cols % 4 == 0 && aligned16(x)) ? 1 : 0;
   dim3 grid((unsigned)gx, (unsigned)slabs);
-  colsum_partial_kernel<<<grid, 256, 0, st>>>(rows, cols, x, ld, scratch, vec);
+  if (tickets != nullptr) {
+    colsum_partial_kernel<<<grid, 256, 0, st>>>(rows, cols, x, ld, scratch, vec, tickets, out);
+    NLPS_LAUNCH_CHECK();
+    return 0;
+  }
+  colsum_partial_kernel<<<grid, 256, 0, st>>>(rows, cols, x, ld, scratch, vec, nullptr, nullptr);
   NLPS_LAUNCH_CHECK();
   colsum_finish_kernel<<<(unsigned)ceil_div(cols, 32), 256, 0, st>>>(slabs, cols, scratch, out);
   NLPS_LAUNCH_CHECK();
