@@ -1166,6 +1166,356 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
   }
 }
 
+
+// ============================================================================================
+// Persistent dQ: same boundary treatment as attn_bwd_dkdv_ps.  Tile = (batch, head, 128 queries), latest
+// (heaviest) query tiles first.  Resident Q / dO of the next tile are prefetched to their own buffer, the
+// PAD words and lse / delta of the next tile are requested a whole tile ahead, dQ leaves by TMA store.
+// ============================================================================================
+template <int D>
+struct PsDqCfg {
+  static constexpr int NSK = 3;                              // [K | V] K-major stages (TMA)
+  static constexpr int NSM = 2;                              // K MN-major stages (re-swizzle warps)
+  static constexpr int kAtoms = D / 32;
+  static constexpr int kBlk = kAtoms * 64 * 128;
+  static constexpr int kStage = 2 * kBlk;                    // [K | V] block pair, also one resident 128-row tile
+  static constexpr int kRes = 2 * kStage;                    // Q and dO of the next tile; later the dQ store staging
+  static constexpr int kCtl = 2048;                          // barriers 256 B | pad masks 2 x 64 x 8 B | ring
+  static constexpr int kSmem = NSK * kStage + NSM * kBlk + kRes + kCtl + 1024;
+  static constexpr int kTmemCols = 512;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_constant__ CUtensorMap map_qres,   // qkv, box {32,128}, K-major
+                                                            const __grid_constant__ CUtensorMap map_dores,  // dctx, box {32,128}, K-major
+                                                            const __grid_constant__ CUtensorMap map_kk,     // qkv, box {32,64}, K-major
+                                                            const __grid_constant__ CUtensorMap map_out,    // dqkv as (3E, S, B), box {32,128,1}
+                                                            const Dims p, const int n_tiles, const int32_t* __restrict__ x,
+                                                            const int32_t* __restrict__ fnp,
+                                                            const float* __restrict__ lse,
+                                                            const float* __restrict__ delta) {
+  using C = PsDqCfg<D>;
+  constexpr int NSK = C::NSK, NSM = C::NSM;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t kst = base;                                  // NSK stages of [K K-major | V K-major]
+  const uint32_t mst = base + NSK * C::kStage;                // NSM stages of [K MN-major]
+  uint8_t* mst_ptr = base_ptr + NSK * C::kStage;
+  const uint32_t resb = mst + NSM * C::kBlk;                  // Q | dO of the upcoming tile
+  uint8_t* res_ptr = mst_ptr + NSM * C::kBlk;
+  const uint32_t bar = resb + C::kRes;
+  uint8_t* ctl_ptr = res_ptr + C::kRes;
+  auto kfull = [&](int s) { return bar + 8u * s; };
+  auto kfree = [&](int s) { return bar + 8u * (4 + s); };
+  auto mfull = [&](int s) { return bar + 8u * (8 + s); };
+  auto mfree = [&](int s) { return bar + 8u * (12 + s); };
+  auto sdp_full = [&](int b2) { return bar + 8u * (16 + b2); };
+  auto ds_full = [&](int b2) { return bar + 8u * (18 + b2); };
+  const uint32_t res_full = bar + 8u * 22, res_done = bar + 8u * 23, acc_full = bar + 8u * 24, st_done = bar + 8u * 25, tmem_slot = bar + 8u * 26;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ctl_ptr + 8 * 26);
+  uint32_t* pad32 = reinterpret_cast<uint32_t*>(ctl_ptr + 256);             // [2][128] words: 32 keys each
+  volatile int* meta_s = reinterpret_cast<volatile int*>(ctl_ptr + 256 + 1024);   // ring of 4 x {block count, first_real}
+  constexpr int kMaxPadWords = 128;                            // S <= 4096 keeps the staged PAD words; longer: per-block ballots
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_bh = p.B * p.h;
+  const int n_qt = (p.S + 127) / 128;
+  const int n_all = (p.S + 63) / 64;
+  const int n_words = 2 * n_all;
+  struct Tile { int b, head, q0; };
+  auto tile_of = [&](int t) {
+    Tile tl;
+    const int k = t / n_bh, bh = t - k * n_bh;
+    tl.q0 = (n_qt - 1 - k) * 128;                             // latest query tiles have the most key blocks: first
+    tl.b = bh / p.h;
+    tl.head = bh - tl.b * p.h;
+    return tl;
+  };
+  auto n_blocks = [&](const Tile& tl, int first_real) {
+    return tl.q0 < first_real ? n_all : min(n_all, (tl.q0 + 127) / 64 + 1);
+  };
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NSK; ++s) { mbar_init(kfull(s), 1); mbar_init(kfree(s), 1 + kSwzWarps); }
+    for (int s = 0; s < NSM; ++s) { mbar_init(mfull(s), kSwzWarps); mbar_init(mfree(s), 1); }
+    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(sdp_full(b2), 1); mbar_init(ds_full(b2), 256); }
+    mbar_init(res_full, 1); mbar_init(res_done, 256); mbar_init(acc_full, 1); mbar_init(st_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t t_q = tmem, t_do = tmem + D, t_s = tmem + 2 * D, t_dp = t_s + 128, t_dq = t_dp + 128;
+
+  if (warp == 0) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      auto issue_res = [&](const Tile& tl, int idx, int first_real) {
+        meta_s[(idx & 3) * 2] = n_blocks(tl, first_real);
+        meta_s[(idx & 3) * 2 + 1] = first_real;
+        mbar_expect_tx(res_full, C::kRes);                     // (release: the ring entry is visible to every waiter)
+#pragma unroll
+        for (int a = 0; a < C::kAtoms; ++a) {
+          tma_load_2d(resb + a * (128 * 128), &map_qres, res_full, tl.head * D + a * 32, tl.b * p.S + tl.q0);
+          tma_load_2d(resb + C::kStage + a * (128 * 128), &map_dores, res_full, tl.head * D + a * 32, tl.b * p.S + tl.q0);
+        }
+      };
+      Tile tl = tile_of(blockIdx.x);
+      int first_real = __ldg(fnp + tl.b);
+      issue_res(tl, 0, first_real);
+      int g = 0, i = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+        const int n_kv = n_blocks(tl, first_real);
+        const int t_next = t + gridDim.x;
+        Tile tn = tl;
+        int fr_next = 0;
+        if (t_next < n_tiles) { tn = tile_of(t_next); fr_next = __ldg(fnp + tn.b); }
+        for (int kb = 0; kb < n_kv; ++kb, ++g) {
+          const int s = g % NSK;
+          const int krow = tl.b * p.S + kb * 64;
+          mbar_wait(kfree(s), (uint32_t)((g / NSK) & 1) ^ 1u);
+          mbar_expect_tx(kfull(s), C::kStage);
+#pragma unroll
+          for (int a = 0; a < C::kAtoms; ++a) {
+            tma_load_2d(kst + s * C::kStage + a * (64 * 128), &map_kk, kfull(s), p.E + tl.head * D + a * 32, krow);
+            tma_load_2d(kst + s * C::kStage + C::kBlk + a * (64 * 128), &map_kk, kfull(s), 2 * p.E + tl.head * D + a * 32, krow);
+          }
+          if (kb == min(1, n_kv - 1) && t_next < n_tiles) {
+            mbar_wait(res_done, (uint32_t)(i & 1));            // this tile's Q / dO have left the buffer ...
+            if (i > 0) mbar_wait(st_done, (uint32_t)((i - 1) & 1));   // ... and so has the previous tile's dQ staging
+            issue_res(tn, i + 1, fr_next);
+          }
+        }
+        tl = tn;
+        first_real = fr_next;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc_t = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int g0 = 0, i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      mbar_wait(res_done, (uint32_t)(i & 1));                  // Q and dO of this tile are in TMEM
+      tc_fence_after();
+      const int n_kv = meta_s[(i & 3) * 2];
+      auto issue_sdp = [&](int kb) {        // S = Q K^T ; dP = dO V^T   (A = Q / dO in TMEM)
+        const int g = g0 + kb, s = g % NSK, b2 = g & 1;
+        mbar_wait(kfull(s), (uint32_t)((g / NSK) & 1));
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t kk_d = make_desc(kst + s * C::kStage, 16, 1024, 2), vk_d = make_desc(kst + s * C::kStage + C::kBlk, 16, 1024, 2);
+#pragma unroll
+          for (int kk = 0; kk < D / 8; ++kk) {
+            const uint64_t bo = (uint64_t)(((kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4);
+            umma_tf32_ts(t_s + b2 * 64, t_q + kk * 8, kk_d + bo, idesc_t, kk > 0 ? 1u : 0u);
+            umma_tf32_ts(t_dp + b2 * 64, t_do + kk * 8, vk_d + bo, idesc_t, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(sdp_full(b2));
+          umma_commit(kfree(s));
+        }
+        __syncwarp();
+      };
+      issue_sdp(0);
+      if (n_kv > 1) issue_sdp(1);
+      for (int kb = 0; kb < n_kv; ++kb) {
+        const int g = g0 + kb, s = g % NSM, b2 = g & 1;
+        mbar_wait(mfull(s), (uint32_t)((g / NSM) & 1));
+        mbar_wait(ds_full(b2), (uint32_t)((g >> 1) & 1));
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t kmn = make_desc(mst + s * C::kBlk, 64 * 128, 512, 1);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)        // dQ += dS K   (K = 64 keys, A = dS in TMEM)
+            umma_tf32_ts(t_dq, t_dp + b2 * 64 + kk * 8, kmn + (uint64_t)(kk * 64), idesc_a, (kb > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(mfree(s));
+          if (kb == n_kv - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
+        if (kb + 2 < n_kv) issue_sdp(kb + 2);
+      }
+      g0 += n_kv;
+    }
+  } else if (warp >= 10) {
+    // ---------------- re-swizzle warps: MN-major image of the landed K tile ----------------
+    const int w4 = warp - 10;
+    int g = 0, i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      mbar_wait(res_full, (uint32_t)(i & 1));                  // (acquire) this tile's ring entry is visible
+      const int n_kv = meta_s[(i & 3) * 2];
+      for (int kb = 0; kb < n_kv; ++kb, ++g) {
+        const int sk = g % NSK, sm = g % NSM;
+        mbar_wait(mfree(sm), (uint32_t)((g / NSM) & 1) ^ 1u);
+        mbar_wait(kfull(sk), (uint32_t)((g / NSK) & 1));
+        reswizzle_rows(base_ptr + sk * C::kStage, mst_ptr + sm * C::kBlk, C::kAtoms * 64, w4, lane);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(mfull(sm)); mbar_arrive(kfree(sk)); }
+      }
+    }
+  } else {
+    // ---------------- softmax threads: (query row r, key half) ----------------
+    const int cw = warp - 2;
+    const int q = warp & 3;
+    const int half = cw >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint64_t scale2 = pack2f(p.scale_log2, p.scale_log2);
+    const float scale = p.scale_log2 * (1.f / kLog2e);
+    const bool storer = cw == 0 && lane == 0;
+    const bool pads_staged = n_words <= kMaxPadWords;
+
+    auto stage_res = [&](int idx) {                            // resident Q and dO: buffer -> TMEM (32 columns per thread)
+      mbar_wait(res_full, (uint32_t)(idx & 1));
+      uint32_t v[32];
+      if (D == 64) {
+        load_swizzled_row(res_ptr + half * (128 * 128), r, v);
+        tmem_st32(t_q + lane_addr + half * 32, v);
+        load_swizzled_row(res_ptr + C::kStage + half * (128 * 128), r, v);
+        tmem_st32(t_do + lane_addr + half * 32, v);
+      } else {
+        load_swizzled_row(res_ptr + half * C::kStage, r, v);
+        tmem_st32((half ? t_do : t_q) + lane_addr, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(res_done);
+    };
+    // PAD words of a sequence: warp cw owns words cw, cw+8, ... ; up to 4 of them ride in registers a whole tile ahead
+    int32_t pad_id[4];
+    auto fetch_pads = [&](int b) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int key = (cw + 8 * u) * 32 + lane;
+        pad_id[u] = key < p.S ? __ldg(x + (int64_t)b * p.S + key) : 0;
+      }
+    };
+    auto store_pads = [&](int b, int idx) {
+      uint32_t* dst = pad32 + (idx & 1) * kMaxPadWords;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, pad_id[u] == 0);
+        if (lane == 0 && cw + 8 * u < n_words) dst[cw + 8 * u] = bits;
+      }
+      for (int w = cw + 32; w < n_words; w += 8) {            // sequences longer than 1024: the rest, synchronously
+        const int key = w * 32 + lane;
+        const uint32_t bits = __ballot_sync(0xffffffffu, key < p.S ? (__ldg(x + (int64_t)b * p.S + key) == 0) : true);
+        if (lane == 0) dst[w] = bits;
+      }
+    };
+
+    Tile tl = tile_of(blockIdx.x);
+    float lse_r = 0.f, dl_r = 0.f;
+    {
+      const int row = tl.q0 + r;
+      const int64_t so = ((int64_t)tl.b * p.h + tl.head) * p.S;
+      if (row < p.S) { lse_r = __ldg(lse + so + row); dl_r = __ldg(delta + so + row); }
+    }
+    if (pads_staged) { fetch_pads(tl.b); store_pads(tl.b, 0); }
+    stage_res(0);
+    asm volatile("bar.sync 1, 256;" ::: "memory");            // PAD words visible
+    int g0 = 0, i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const int n_kv = meta_s[(i & 3) * 2], first_real = meta_s[(i & 3) * 2 + 1];
+      const int row = tl.q0 + r;
+      const bool row_ok = row < p.S;
+      const bool deg = row < first_real;
+      const float nls = -lse_r * kLog2e, ndl = -dl_r;
+      const uint64_t nl2 = pack2f(nls, nls), ndl2 = pack2f(ndl, ndl);
+      const uint32_t* pads = pad32 + (i & 1) * kMaxPadWords;
+      const int t_next = t + gridDim.x;
+      Tile tn = tl;
+      float lse_n = 0.f, dl_n = 0.f;
+      if (t_next < n_tiles) {                                  // requested now, consumed a whole tile later
+        tn = tile_of(t_next);
+        const int rown = tn.q0 + r;
+        const int64_t so = ((int64_t)tn.b * p.h + tn.head) * p.S;
+        if (rown < p.S) { lse_n = __ldg(lse + so + rown); dl_n = __ldg(delta + so + rown); }
+        if (pads_staged) fetch_pads(tn.b);
+      }
+      for (int kb = 0; kb < n_kv; ++kb) {
+        const int g = g0 + kb, b2 = g & 1;
+        const uint32_t ph = (uint32_t)((g >> 1) & 1);
+        const int kbase = kb * 64 + half * 32;                // first key of this thread's 32 columns
+        uint32_t padbits;
+        if (pads_staged) {
+          padbits = pads[2 * kb + half];
+        } else {
+          const int ka = kbase + lane;
+          padbits = __ballot_sync(0xffffffffu, ka < p.S ? (x[(int64_t)tl.b * p.S + ka] == 0) : true);
+        }
+        const uint32_t range_bits = low_bits32(p.S - kbase);
+        uint32_t vis;
+        if (!row_ok) vis = 0u;
+        else if (deg) vis = range_bits;
+        else vis = low_bits32(row - kbase + 1) & ~padbits & range_bits;
+        mbar_wait(sdp_full(b2), ph);
+        tc_fence_after();
+        uint32_t sv[32], dv[32];
+        const uint32_t a_s = t_s + b2 * 64 + half * 32 + lane_addr, a_d = t_dp + b2 * 64 + half * 32 + lane_addr;
+        tmem_ld32_nowait(a_s, sv);
+        tmem_ld32_nowait(a_d, dv);
+        tmem_ld_wait();
+        if (__all_sync(0xffffffffu, vis == ~0u)) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) p_ds_pair<false, false>(sv[c], sv[c + 1], dv[c], dv[c + 1], scale2, nl2, ndl2, vis, c);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) p_ds_pair<true, false>(sv[c], sv[c + 1], dv[c], dv[c + 1], scale2, nl2, ndl2, vis, c);
+        }
+        tmem_st32(a_d, dv);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(ds_full(b2));
+        if (kb == 0 && i > 0 && storer) {                      // the previous tile's bulk store has had a whole block to read its staging
+          bulk_wait_read0();
+          mbar_arrive(st_done);
+        }
+      }
+      g0 += n_kv;
+      // every S / dP product of this tile has retired: the next tile's Q / dO go to TMEM before the drain
+      if (t_next < n_tiles) {
+        if (pads_staged) store_pads(tn.b, i + 1);
+        stage_res(i + 1);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // everyone has left the Q/dO buffer (it becomes the store staging); PAD words visible
+      mbar_wait(acc_full, (uint32_t)(i & 1));
+      tc_fence_after();
+      if (D == 64 || half == 0) {
+        uint32_t a[32];
+        tmem_ld32_nowait(t_dq + lane_addr + (D == 64 ? half * 32 : 0), a);
+        tmem_ld_wait();
+        put_row_sw128(res_ptr + (D == 64 ? half : 0) * (128 * 128), r, a, scale);
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (storer) {
+#pragma unroll
+        for (int at = 0; at < C::kAtoms; ++at)
+          tma_store_3d(&map_out, resb + at * (128 * 128), tl.head * D + at * 32, tl.q0, tl.b);
+        bulk_commit();
+      }
+      tc_fence_before();                                       // the drain is ordered before the next tile's ds_full arrivals
+      tl = tn;
+      lse_r = lse_n;
+      dl_r = dl_n;
+    }
+    if (storer) bulk_wait_read0();                             // the last tile's staging must outlive its store
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, C::kTmemCols);
+  }
+}
+
 template <int D>
 int launch_bwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int32_t* x, const int32_t* fnp,
                const float* dctx, const float* lse, const float* delta, float* dqkv) {
@@ -1221,7 +1571,19 @@ int launch_bwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int
     attn_bwd_dkdv_ts<D, NS><<<grid, kThreads, C::kSmemDkdv, st>>>(res, qk, qmn, dok, domn, p, x, fnp, lse, delta, dqkv);
   }
   NLPS_LAUNCH_CHECK();
-  attn_bwd_dq_ts<D, NS><<<grid, kThreads, C::kSmemDq, st>>>(res, dores, qk, qmn, p, x, fnp, lse, delta, dqkv);
+  if (persistent && (reinterpret_cast<uintptr_t>(dqkv) & 31u) == 0 && n_tiles < (1ll << 30)) {
+    static bool once_dq = false;
+    if (!once_dq) {
+      NLPS_CUDA(cudaFuncSetAttribute(attn_bwd_dq_ps<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, PsDqCfg<D>::kSmem));
+      once_dq = true;
+    }
+    CUtensorMap out3;
+    NLPS_TRY(make_map3(&out3, dqkv, 3 * (uint64_t)E, (uint64_t)S, (uint64_t)B, 3 * (int64_t)E, (int64_t)S * 3 * E, 32, 128));
+    attn_bwd_dq_ps<D><<<(unsigned)std::min<int64_t>(n_tiles, kNumSMs), kThreads, PsDqCfg<D>::kSmem, st>>>(
+        res, dores, qk, out3, p, (int)n_tiles, x, fnp, lse, delta);
+  } else {
+    attn_bwd_dq_ts<D, NS><<<grid, kThreads, C::kSmemDq, st>>>(res, dores, qk, qmn, p, x, fnp, lse, delta, dqkv);
+  }
   NLPS_LAUNCH_CHECK();
   if (trace_on) {
     static int printed = 0;
