@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 
 namespace nlps {
 namespace {
@@ -792,6 +794,23 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ts(const __grid_const
 //     block counter, the per-tile block count travels through a small ring in shared memory;
 //   * dV / dK leave as 256-bit row stores straight from registers (full 32-B sectors, no staging tile).
 // ============================================================================================
+// Draw order of the persistent kernels.  Tiles of one (batch, head) pair share their streamed blocks, so they should
+// run at the same time (one HBM read, L2 hits for the rest); heavy tiles should be drawn first so that the tail of the
+// kernel is made of light ones.  Compromise: bands of `band` consecutive tile ranks (rank 0 = heaviest); band-major,
+// then pair-major, then rank inside the band.
+__device__ __forceinline__ void banded_tile(int t, int n_rank, int n_bh, int band, int& bh, int& rank) {
+  const int full = (n_rank / band) * band;                    // ranks covered by complete bands
+  if (t < full * n_bh) {
+    const int per = band * n_bh, bi = t / per, rem = t - bi * per;
+    bh = rem / band;
+    rank = bi * band + (rem - bh * band);
+  } else {
+    const int tail = n_rank - full, rem = t - full * n_bh;
+    bh = rem / tail;
+    rank = full + (rem - bh * tail);
+  }
+}
+
 template <int D>
 struct PsCfg {
   static constexpr int NSK = 3;                              // K-major [Q | dO] stages (filled by TMA, latency-critical)
@@ -820,7 +839,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
                                                               const __grid_constant__ CUtensorMap map_qk,    // qkv, box {32,64}, K-major
                                                               const __grid_constant__ CUtensorMap map_dok,   // dctx, box {32,64}, K-major
                                                               const __grid_constant__ CUtensorMap map_out,   // dqkv as (3E, S, B), box {32,128,1}
-                                                              const Dims p, const int n_tiles, const int32_t* __restrict__ x,
+                                                              const Dims p, const int n_tiles, int* __restrict__ sched, const int32_t* __restrict__ x,
                                                               const int32_t* __restrict__ fnp,
                                                               const float* __restrict__ lse,
                                                               const float* __restrict__ delta,
@@ -849,15 +868,21 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ctl_ptr + 8 * 26);
   float* lse_s = reinterpret_cast<float*>(ctl_ptr + 256);     // [2][64]  -lse*log2e
   float* delta_s = lse_s + 128;                               // [2][64]  -delta
-  volatile int* meta_s = reinterpret_cast<volatile int*>(ctl_ptr + 1280);   // ring of 4 x {block count, first_real}
+  volatile int* meta_s = reinterpret_cast<volatile int*>(ctl_ptr + 1280);   // ring of 4 x {tile or -1, block count, first_real, -}
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_bh = p.B * p.h;
   const int n_q = (p.S + 63) / 64;
   struct Tile { int b, head, k0; };
+  const int n_kt = (p.S + 127) / 128;
+  // Tiles are drawn from a global counter (sched[0]) in (batch*head)-major order, heaviest key tile of each pair first:
+  // the CTAs running at any moment work on neighbouring (batch, head) pairs, so the Q / dO blocks that the key tiles of
+  // one pair share are read from HBM once and found in L2 afterwards, and the dynamic draw balances the SMs.
+  const int band = n_kt <= 8 ? 2 : 4;                         // see banded_tile
   auto tile_of = [&](int t) {
     Tile tl;
-    const int kt = t / n_bh, bh = t - kt * n_bh;              // key tile 0 has the most query blocks: first
+    int bh, kt;
+    banded_tile(t, n_kt, n_bh, band, bh, kt);                 // key tile 0 has the most query blocks: first
     tl.k0 = kt * 128;
     tl.b = bh / p.h;
     tl.head = bh - tl.b * p.h;
@@ -890,9 +915,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
 
   if (warp == 0) {
     // ---------------- producer: TMA + lse/delta staging + tile metadata ----------------
-    auto issue_kv = [&](const Tile& tl, int idx, int first_real) {      // lane 0 only
-      meta_s[(idx & 3) * 2] = n_blocks(tl, first_real);
-      meta_s[(idx & 3) * 2 + 1] = first_real;
+    auto issue_kv = [&](const Tile& tl, int idx, int first_real, int t) {   // lane 0 only
+      meta_s[(idx & 3) * 4] = t;
+      meta_s[(idx & 3) * 4 + 1] = n_blocks(tl, first_real);
+      meta_s[(idx & 3) * 4 + 2] = first_real;
       mbar_expect_tx(kv_full, C::kKv);                                   // (release: the ring entry is visible to every waiter)
 #pragma unroll
       for (int a = 0; a < C::kAtoms; ++a) {
@@ -911,17 +937,28 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
         nd_r[j] = __ldg(delta + so + qi);
       }
     };
-    Tile tl = tile_of(blockIdx.x);
-    int first_real = __ldg(fnp + tl.b);
-    if (lane == 0) issue_kv(tl, 0, first_real);
-    fetch_ld(tl, 0);
-    int g = 0, i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    auto draw = [&]() {                                      // next tile index for this CTA (warp-uniform), -1 = none left
+      int t = 0;
+      if (lane == 0) t = atomicAdd(sched, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      return t < n_tiles ? t : -1;
+    };
+    auto publish_stop = [&](int idx) {                       // lane 0: ring entry "no more tiles", completes the phase
+      meta_s[(idx & 3) * 4] = -1;
+      mbar_arrive(kv_full);
+    };
+    int t = draw();
+    Tile tl = tile_of(max(t, 0));
+    int first_real = t >= 0 ? __ldg(fnp + tl.b) : 0;
+    if (lane == 0) { if (t >= 0) issue_kv(tl, 0, first_real, t); else publish_stop(0); }
+    if (t >= 0) fetch_ld(tl, 0);
+    int g = 0;
+    for (int i = 0; t >= 0; ++i) {
       const int n_it = n_blocks(tl, first_real);
-      const int t_next = t + gridDim.x;
+      const int t_next = draw();
       Tile tn = tl;
       int fr_next = 0;
-      if (t_next < n_tiles) { tn = tile_of(t_next); fr_next = __ldg(fnp + tn.b); }
+      if (t_next >= 0) { tn = tile_of(t_next); fr_next = __ldg(fnp + tn.b); }
       for (int it = 0; it < n_it; ++it, ++g) {
         const int s = g % NSK;
         if (lane == 0) {
@@ -933,10 +970,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
             tma_load_2d(kst + s * C::kStage + a * (64 * 128), &map_qk, kfull(s), tl.head * D + a * 32, qrow);
             tma_load_2d(kst + s * C::kStage + C::kBlk + a * (64 * 128), &map_dok, kfull(s), tl.head * D + a * 32, qrow);
           }
-          if (it == min(1, n_it - 1) && t_next < n_tiles) {
+          if (it == min(1, n_it - 1)) {
             mbar_wait(kv_done, (uint32_t)(i & 1));             // this tile's K / V have left the buffer ...
             if (i > 0) mbar_wait(st_done, (uint32_t)((i - 1) & 1));   // ... and so has the previous tile's dV / dK (it doubles as their store staging)
-            issue_kv(tn, i + 1, fr_next);
+            if (t_next >= 0) issue_kv(tn, i + 1, fr_next, t_next); else publish_stop(i + 1);
           }
         }
         __syncwarp();
@@ -949,20 +986,25 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
         }
         mbar_arrive(ld_full(b2));
         if (it + 1 < n_it) fetch_ld(tl, it + 1);
-        else if (t_next < n_tiles) fetch_ld(tn, 0);
+        else if (t_next >= 0) fetch_ld(tn, 0);
       }
       tl = tn;
       first_real = fr_next;
+      t = t_next;
     }
+    // the CTA that draws the last "none left" puts the counters back for the next launch
+    if (lane == 0 && atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc_t = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int g0 = 0, i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    int g0 = 0;
+    for (int i = 0;; ++i) {
+      mbar_wait(kv_full, (uint32_t)(i & 1));                   // (acquire) ring entry of tile i
+      if (meta_s[(i & 3) * 4] < 0) break;
       mbar_wait(kv_done, (uint32_t)(i & 1));                   // K and V of this tile are in TMEM
       tc_fence_after();
-      const int n_it = meta_s[(i & 3) * 2];
+      const int n_it = meta_s[(i & 3) * 4 + 1];
       auto issue_sdp = [&](int it) {        // S^T = K Q^T ; dP^T = V dO^T   (A = K / V in TMEM)
         const int g = g0 + it, s = g % NSK, b2 = g & 1;
         mbar_wait(kfull(s), (uint32_t)((g / NSK) & 1));
@@ -1006,10 +1048,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
   } else if (warp >= 10) {
     // ---------------- re-swizzle warps ----------------
     const int w4 = warp - 10;
-    int g = 0, i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    int g = 0;
+    for (int i = 0;; ++i) {
       mbar_wait(kv_full, (uint32_t)(i & 1));                   // (acquire) this tile's ring entry is visible
-      const int n_it = meta_s[(i & 3) * 2];
+      if (meta_s[(i & 3) * 4] < 0) break;
+      const int n_it = meta_s[(i & 3) * 4 + 1];
       for (int it = 0; it < n_it; ++it, ++g) {
         const int sk = g % NSK, sm = g % NSM;
         mbar_wait(mfree(sm), (uint32_t)((g / NSM) & 1) ^ 1u);
@@ -1031,8 +1074,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
     const float scale = p.scale_log2 * (1.f / kLog2e);
     const bool storer = cw == 0 && lane == 0;
 
-    auto stage_kv = [&](int idx) {                             // resident K and V: buffer -> TMEM (32 columns per thread)
+    auto stage_kv = [&](int idx) {                             // resident K and V: buffer -> TMEM (32 columns per thread); false = no tile
       mbar_wait(kv_full, (uint32_t)(idx & 1));
+      if (meta_s[(idx & 3) * 4] < 0) return false;
       uint32_t v[32];
       if (D == 64) {
         load_swizzled_row(kvb_ptr + half * (128 * 128), r, v);
@@ -1046,26 +1090,21 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(kv_done);
+      return true;
     };
+    auto key_id_of = [&](const Tile& tl) { return (tl.k0 + r < p.S) ? __ldg(x + (int64_t)tl.b * p.S + tl.k0 + r) : 0; };
 
-    Tile tl = tile_of(blockIdx.x);
-    int key_id = (tl.k0 + r < p.S) ? __ldg(x + (int64_t)tl.b * p.S + tl.k0 + r) : 0;
     const bool trs = p.trace && blockIdx.x == 5 && cw == 0 && lane == 0;
     trace(trs, 0);
-    stage_kv(0);
-    int g0 = 0, i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-      const int n_it = meta_s[(i & 3) * 2], first_real = meta_s[(i & 3) * 2 + 1];
+    bool have = stage_kv(0);
+    Tile tl = tile_of(have ? meta_s[0] : 0);
+    int key_id = have ? key_id_of(tl) : 0;
+    int g0 = 0;
+    for (int i = 0; have; ++i) {
+      const int n_it = meta_s[(i & 3) * 4 + 1], first_real = meta_s[(i & 3) * 4 + 2];
       const int key = tl.k0 + r;
       const bool key_ok = key < p.S;
       const bool key_pad = key_id == 0;
-      const int t_next = t + gridDim.x;
-      Tile tn = tl;
-      int key_id_next = 0;
-      if (t_next < n_tiles) {                                  // requested now, consumed a whole tile later
-        tn = tile_of(t_next);
-        key_id_next = (tn.k0 + r < p.S) ? __ldg(x + (int64_t)tn.b * p.S + tn.k0 + r) : 0;
-      }
       trace(trs && i < 16, 700 + i * 8);
       if (trs && i < 16) g_ts_trace[707 + i * 8] = n_it;
       for (int it = 0; it < n_it; ++it) {
@@ -1116,7 +1155,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
       trace(trs && i < 16, 702 + i * 8);
       // every S^T / dP^T product of this tile has retired (its results were read above): K / V of the next tile
       // go to TMEM now, so the tensor pipe has work while this tile's accumulators drain
-      if (t_next < n_tiles) stage_kv(i + 1);
+      have = stage_kv(i + 1);
+      Tile tn = tl;
+      int key_id_next = 0;
+      if (have) {                                              // requested now, consumed after the drain
+        tn = tile_of(meta_s[((i + 1) & 3) * 4]);
+        key_id_next = key_id_of(tn);
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");          // every thread has left the K/V buffer: it becomes the store staging
       trace(trs && i < 16, 703 + i * 8);
       mbar_wait(acc_full, (uint32_t)(i & 1));
@@ -1190,7 +1235,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
                                                             const __grid_constant__ CUtensorMap map_dores,  // dctx, box {32,128}, K-major
                                                             const __grid_constant__ CUtensorMap map_kk,     // qkv, box {32,64}, K-major
                                                             const __grid_constant__ CUtensorMap map_out,    // dqkv as (3E, S, B), box {32,128,1}
-                                                            const Dims p, const int n_tiles, const int32_t* __restrict__ x,
+                                                            const Dims p, const int n_tiles, int* __restrict__ sched, const int32_t* __restrict__ x,
                                                             const int32_t* __restrict__ fnp,
                                                             const float* __restrict__ lse,
                                                             const float* __restrict__ delta) {
@@ -1225,9 +1270,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
   const int n_all = (p.S + 63) / 64;
   const int n_words = 2 * n_all;
   struct Tile { int b, head, q0; };
+  const int band = n_qt <= 8 ? 2 : 4;
   auto tile_of = [&](int t) {
     Tile tl;
-    const int k = t / n_bh, bh = t - k * n_bh;
+    int bh, k;
+    banded_tile(t, n_qt, n_bh, band, bh, k);                  // drawn from sched[0]: see attn_bwd_dkdv_ps
     tl.q0 = (n_qt - 1 - k) * 128;                             // latest query tiles have the most key blocks: first
     tl.b = bh / p.h;
     tl.head = bh - tl.b * p.h;
@@ -1255,9 +1302,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
   if (warp == 0) {
     // ---------------- producer ----------------
     if (lane == 0) {
-      auto issue_res = [&](const Tile& tl, int idx, int first_real) {
-        meta_s[(idx & 3) * 2] = n_blocks(tl, first_real);
-        meta_s[(idx & 3) * 2 + 1] = first_real;
+      auto issue_res = [&](const Tile& tl, int idx, int first_real, int t) {
+        meta_s[(idx & 3) * 4] = t;
+        meta_s[(idx & 3) * 4 + 1] = n_blocks(tl, first_real);
+        meta_s[(idx & 3) * 4 + 2] = first_real;
         mbar_expect_tx(res_full, C::kRes);                     // (release: the ring entry is visible to every waiter)
 #pragma unroll
         for (int a = 0; a < C::kAtoms; ++a) {
@@ -1265,16 +1313,22 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
           tma_load_2d(resb + C::kStage + a * (128 * 128), &map_dores, res_full, tl.head * D + a * 32, tl.b * p.S + tl.q0);
         }
       };
-      Tile tl = tile_of(blockIdx.x);
-      int first_real = __ldg(fnp + tl.b);
-      issue_res(tl, 0, first_real);
-      int g = 0, i = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      auto publish_stop = [&](int idx) {
+        meta_s[(idx & 3) * 4] = -1;
+        mbar_arrive(res_full);
+      };
+      auto draw = [&]() { const int t = atomicAdd(sched, 1); return t < n_tiles ? t : -1; };
+      int t = draw();
+      Tile tl = tile_of(max(t, 0));
+      int first_real = t >= 0 ? __ldg(fnp + tl.b) : 0;
+      if (t >= 0) issue_res(tl, 0, first_real, t); else publish_stop(0);
+      int g = 0;
+      for (int i = 0; t >= 0; ++i) {
         const int n_kv = n_blocks(tl, first_real);
-        const int t_next = t + gridDim.x;
+        const int t_next = draw();
         Tile tn = tl;
         int fr_next = 0;
-        if (t_next < n_tiles) { tn = tile_of(t_next); fr_next = __ldg(fnp + tn.b); }
+        if (t_next >= 0) { tn = tile_of(t_next); fr_next = __ldg(fnp + tn.b); }
         for (int kb = 0; kb < n_kv; ++kb, ++g) {
           const int s = g % NSK;
           const int krow = tl.b * p.S + kb * 64;
@@ -1285,26 +1339,30 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
             tma_load_2d(kst + s * C::kStage + a * (64 * 128), &map_kk, kfull(s), p.E + tl.head * D + a * 32, krow);
             tma_load_2d(kst + s * C::kStage + C::kBlk + a * (64 * 128), &map_kk, kfull(s), 2 * p.E + tl.head * D + a * 32, krow);
           }
-          if (kb == min(1, n_kv - 1) && t_next < n_tiles) {
+          if (kb == min(1, n_kv - 1)) {
             mbar_wait(res_done, (uint32_t)(i & 1));            // this tile's Q / dO have left the buffer ...
             if (i > 0) mbar_wait(st_done, (uint32_t)((i - 1) & 1));   // ... and so has the previous tile's dQ staging
-            issue_res(tn, i + 1, fr_next);
+            if (t_next >= 0) issue_res(tn, i + 1, fr_next, t_next); else publish_stop(i + 1);
           }
         }
         tl = tn;
         first_real = fr_next;
+        t = t_next;
       }
+      if (atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }   // counters ready for the next launch
     }
     __syncwarp();
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc_t = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int g0 = 0, i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    int g0 = 0;
+    for (int i = 0;; ++i) {
+      mbar_wait(res_full, (uint32_t)(i & 1));                  // (acquire) ring entry of tile i
+      if (meta_s[(i & 3) * 4] < 0) break;
       mbar_wait(res_done, (uint32_t)(i & 1));                  // Q and dO of this tile are in TMEM
       tc_fence_after();
-      const int n_kv = meta_s[(i & 3) * 2];
+      const int n_kv = meta_s[(i & 3) * 4 + 1];
       auto issue_sdp = [&](int kb) {        // S = Q K^T ; dP = dO V^T   (A = Q / dO in TMEM)
         const int g = g0 + kb, s = g % NSK, b2 = g & 1;
         mbar_wait(kfull(s), (uint32_t)((g / NSK) & 1));
@@ -1345,10 +1403,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
   } else if (warp >= 10) {
     // ---------------- re-swizzle warps: MN-major image of the landed K tile ----------------
     const int w4 = warp - 10;
-    int g = 0, i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    int g = 0;
+    for (int i = 0;; ++i) {
       mbar_wait(res_full, (uint32_t)(i & 1));                  // (acquire) this tile's ring entry is visible
-      const int n_kv = meta_s[(i & 3) * 2];
+      if (meta_s[(i & 3) * 4] < 0) break;
+      const int n_kv = meta_s[(i & 3) * 4 + 1];
       for (int kb = 0; kb < n_kv; ++kb, ++g) {
         const int sk = g % NSK, sm = g % NSM;
         mbar_wait(mfree(sm), (uint32_t)((g / NSM) & 1) ^ 1u);
@@ -1371,8 +1430,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
     const bool storer = cw == 0 && lane == 0;
     const bool pads_staged = n_words <= kMaxPadWords;
 
-    auto stage_res = [&](int idx) {                            // resident Q and dO: buffer -> TMEM (32 columns per thread)
+    auto stage_res = [&](int idx) {                            // resident Q and dO: buffer -> TMEM (32 columns per thread); false = no tile
       mbar_wait(res_full, (uint32_t)(idx & 1));
+      if (meta_s[(idx & 3) * 4] < 0) return false;
       uint32_t v[32];
       if (D == 64) {
         load_swizzled_row(res_ptr + half * (128 * 128), r, v);
@@ -1386,6 +1446,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(res_done);
+      return true;
     };
     // PAD words of a sequence: warp cw owns words cw, cw+8, ... ; up to 4 of them ride in registers a whole tile ahead
     int32_t pad_id[4];
@@ -1410,35 +1471,29 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
       }
     };
 
-    Tile tl = tile_of(blockIdx.x);
     float lse_r = 0.f, dl_r = 0.f;
-    {
+    auto fetch_row = [&](const Tile& tl) {                     // this thread's lse / delta of a tile
       const int row = tl.q0 + r;
       const int64_t so = ((int64_t)tl.b * p.h + tl.head) * p.S;
-      if (row < p.S) { lse_r = __ldg(lse + so + row); dl_r = __ldg(delta + so + row); }
+      lse_r = row < p.S ? __ldg(lse + so + row) : 0.f;
+      dl_r = row < p.S ? __ldg(delta + so + row) : 0.f;
+    };
+    bool have = stage_res(0);
+    Tile tl = tile_of(have ? meta_s[0] : 0);
+    if (have) {
+      fetch_row(tl);
+      if (pads_staged) { fetch_pads(tl.b); store_pads(tl.b, 0); }
     }
-    if (pads_staged) { fetch_pads(tl.b); store_pads(tl.b, 0); }
-    stage_res(0);
     asm volatile("bar.sync 1, 256;" ::: "memory");            // PAD words visible
-    int g0 = 0, i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-      const int n_kv = meta_s[(i & 3) * 2], first_real = meta_s[(i & 3) * 2 + 1];
+    int g0 = 0;
+    for (int i = 0; have; ++i) {
+      const int n_kv = meta_s[(i & 3) * 4 + 1], first_real = meta_s[(i & 3) * 4 + 2];
       const int row = tl.q0 + r;
       const bool row_ok = row < p.S;
       const bool deg = row < first_real;
       const float nls = -lse_r * kLog2e, ndl = -dl_r;
       const uint64_t nl2 = pack2f(nls, nls), ndl2 = pack2f(ndl, ndl);
       const uint32_t* pads = pad32 + (i & 1) * kMaxPadWords;
-      const int t_next = t + gridDim.x;
-      Tile tn = tl;
-      float lse_n = 0.f, dl_n = 0.f;
-      if (t_next < n_tiles) {                                  // requested now, consumed a whole tile later
-        tn = tile_of(t_next);
-        const int rown = tn.q0 + r;
-        const int64_t so = ((int64_t)tn.b * p.h + tn.head) * p.S;
-        if (rown < p.S) { lse_n = __ldg(lse + so + rown); dl_n = __ldg(delta + so + rown); }
-        if (pads_staged) fetch_pads(tn.b);
-      }
       for (int kb = 0; kb < n_kv; ++kb) {
         const int g = g0 + kb, b2 = g & 1;
         const uint32_t ph = (uint32_t)((g >> 1) & 1);
@@ -1480,11 +1535,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
       }
       g0 += n_kv;
       // every S / dP product of this tile has retired: the next tile's Q / dO go to TMEM before the drain
-      if (t_next < n_tiles) {
-        if (pads_staged) store_pads(tn.b, i + 1);
-        stage_res(i + 1);
+      have = stage_res(i + 1);
+      Tile tn = tl;
+      if (have) {                                              // the next tile's per-row values and PAD words: requested now, used after the drain
+        tn = tile_of(meta_s[((i + 1) & 3) * 4]);
+        fetch_row(tn);
+        if (pads_staged) fetch_pads(tn.b);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");          // everyone has left the Q/dO buffer (it becomes the store staging); PAD words visible
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // everyone has left the Q/dO buffer: it becomes the store staging
       mbar_wait(acc_full, (uint32_t)(i & 1));
       tc_fence_after();
       if (D == 64 || half == 0) {
@@ -1502,9 +1560,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
         bulk_commit();
       }
       tc_fence_before();                                       // the drain is ordered before the next tile's ds_full arrivals
+      if (have && pads_staged) store_pads(tn.b, i + 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // PAD words of the next tile visible
       tl = tn;
-      lse_r = lse_n;
-      dl_r = dl_n;
     }
     if (storer) bulk_wait_read0();                             // the last tile's staging must outlive its store
   }
@@ -1514,6 +1572,22 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
     tc_fence_after();
     tmem_dealloc(tmem, C::kTmemCols);
   }
+}
+
+// two ints per (device, stream) and kernel: next tile, CTAs finished -- zero between launches (the kernels restore them)
+int sched_counters(cudaStream_t st, int which, int** out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, int*> table;
+  int dev = 0;
+  NLPS_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  int*& ptr = table[{dev, st}];
+  if (ptr == nullptr) {
+    NLPS_CUDA(cudaMalloc(reinterpret_cast<void**>(&ptr), 64));
+    NLPS_CUDA(cudaMemset(ptr, 0, 64));
+  }
+  *out = ptr + 2 * which;
+  return 0;
 }
 
 template <int D>
@@ -1551,8 +1625,10 @@ int launch_bwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int
     }
     CUtensorMap out3;
     NLPS_TRY(make_map3(&out3, dqkv, 3 * (uint64_t)E, (uint64_t)S, (uint64_t)B, 3 * (int64_t)E, (int64_t)S * 3 * E, 32, 128));
+    int* sched = nullptr;
+    NLPS_TRY(sched_counters(st, 0, &sched));
     attn_bwd_dkdv_ps<D><<<(unsigned)std::min<int64_t>(n_tiles, kNumSMs), kThreads, PsCfg<D>::kSmemDkdv, st>>>(
-        res, qk, dok, out3, p, (int)n_tiles, x, fnp, lse, delta, dqkv);
+        res, qk, dok, out3, p, (int)n_tiles, sched, x, fnp, lse, delta, dqkv);
     if (trace_on) {
       static int printed_ps = 0;
       if (printed_ps++ == 3) {
@@ -1579,8 +1655,10 @@ int launch_bwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int
     }
     CUtensorMap out3;
     NLPS_TRY(make_map3(&out3, dqkv, 3 * (uint64_t)E, (uint64_t)S, (uint64_t)B, 3 * (int64_t)E, (int64_t)S * 3 * E, 32, 128));
+    int* sched = nullptr;
+    NLPS_TRY(sched_counters(st, 1, &sched));
     attn_bwd_dq_ps<D><<<(unsigned)std::min<int64_t>(n_tiles, kNumSMs), kThreads, PsDqCfg<D>::kSmem, st>>>(
-        res, dores, qk, out3, p, (int)n_tiles, x, fnp, lse, delta);
+        res, dores, qk, out3, p, (int)n_tiles, sched, x, fnp, lse, delta);
   } else {
     attn_bwd_dq_ts<D, NS><<<grid, kThreads, C::kSmemDq, st>>>(res, dores, qk, qmn, p, x, fnp, lse, delta, dqkv);
   }
