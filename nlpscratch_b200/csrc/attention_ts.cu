@@ -970,11 +970,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
             tma_load_2d(kst + s * C::kStage + a * (64 * 128), &map_qk, kfull(s), tl.head * D + a * 32, qrow);
             tma_load_2d(kst + s * C::kStage + C::kBlk + a * (64 * 128), &map_dok, kfull(s), tl.head * D + a * 32, qrow);
           }
-          if (it == min(1, n_it - 1)) {
-            mbar_wait(kv_done, (uint32_t)(i & 1));             // this tile's K / V have left the buffer ...
-            if (i > 0) mbar_wait(st_done, (uint32_t)((i - 1) & 1));   // ... and so has the previous tile's dV / dK (it doubles as their store staging)
-            if (t_next >= 0) issue_kv(tn, i + 1, fr_next, t_next); else publish_stop(i + 1);
-          }
         }
         __syncwarp();
         const int b2 = g & 1;
@@ -987,6 +982,16 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
         mbar_arrive(ld_full(b2));
         if (it + 1 < n_it) fetch_ld(tl, it + 1);
         else if (t_next >= 0) fetch_ld(tn, 0);
+        // The next tile is published only AFTER this block's lse/delta stage: st_done(i-1) is signalled by a thread that
+        // has finished block 0 of this tile, which needs that stage (a one-block tile would deadlock the other way round).
+        if (it == min(1, n_it - 1)) {
+          if (lane == 0) {
+            mbar_wait(kv_done, (uint32_t)(i & 1));             // this tile's K / V have left the buffer ...
+            if (i > 0) mbar_wait(st_done, (uint32_t)((i - 1) & 1));   // ... and so has the previous tile's dV / dK (it doubles as their store staging)
+            if (t_next >= 0) issue_kv(tn, i + 1, fr_next, t_next); else publish_stop(i + 1);
+          }
+          __syncwarp();
+        }
       }
       tl = tn;
       first_real = fr_next;

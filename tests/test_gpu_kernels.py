@@ -74,7 +74,11 @@ def _attention_case(B, S, h, d, pad_mode, seed):
                                          (1, 64, 1, 128, "none"), (2, 33, 3, 20, "tail"),
                                          # multi-block shapes for the tcgen05 kernels (head_dim 32 / 64)
                                          (2, 320, 2, 32, "tail"), (3, 300, 2, 64, "lead"), (2, 512, 2, 64, "none"),
-                                         (1, 1100, 1, 64, "tail"), (3, 257, 3, 32, "lead")])
+                                         (1, 1100, 1, 64, "tail"), (3, 257, 3, 32, "lead"),
+                                         # more tiles than SMs: every persistent backward CTA walks several tiles
+                                         # (one-block tiles and ragged last tiles included: S = 130, 65, 320)
+                                         (8, 512, 6, 64, "tail"), (40, 130, 4, 32, "lead"), (33, 65, 5, 64, "tail"),
+                                         (16, 320, 8, 32, "tail")])
 @pytest.mark.parametrize("prec", ["fp32", "tf32"])
 def test_attention_forward_backward(B, S, h, d, pad, prec):
     # fp32: CUDA-core kernels (attention.cu); tf32: mma.sync tensor-core kernels (attention_mma.cu,
