@@ -2036,6 +2036,390 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_ts(const __grid_const
   }
 }
 
+
+// ============================================================================================
+// Persistent forward: attn_fwd_ts's block pipeline, two CTAs per SM, each walking tiles drawn from the global
+// counter in the banded order of the backward kernels.  The Q image of the next tile is prefetched into the Q
+// buffer while the current tile runs (Q itself lives in TMEM), copied to TMEM before the current output is
+// drained, and the buffer then stages the normalised O tile for an asynchronous TMA store.
+// ============================================================================================
+template <int D, int NS>
+__global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_ps(const __grid_constant__ CUtensorMap map_q,    // qkv, box {32,128}, K-major
+                                                            const __grid_constant__ CUtensorMap map_k,    // qkv, box {32,64}, K-major
+                                                            const __grid_constant__ CUtensorMap map_v,    // qkv, box {32,64}, MN-major
+                                                            const __grid_constant__ CUtensorMap map_out,  // ctx as (E, S, B), box {32,128,1}
+                                                            const Dims p, const int n_tiles, int* __restrict__ sched,
+                                                            const int32_t* __restrict__ x,
+                                                            const int32_t* __restrict__ fnp, float* __restrict__ lse) {
+  using C = FwdCfg<D, NS>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t kv_s = base;                                 // NS stages of [K block | V block]
+  const uint32_t q_s = base + NS * C::kStage;                 // Q image of the upcoming tile, later the O staging
+  uint8_t* q_ptr = base_ptr + NS * C::kStage;
+  uint8_t* ctl_ptr = q_ptr + C::kTile;
+  const uint32_t bar = q_s + C::kTile;
+  auto kfull = [&](int s) { return bar + 8u * s; };
+  auto kfree = [&](int s) { return bar + 8u * (2 + s); };
+  auto vfull = [&](int s) { return bar + 8u * (4 + s); };
+  auto vfree = [&](int s) { return bar + 8u * (6 + s); };
+  auto s_full = [&](int b2) { return bar + 8u * (8 + b2); };
+  auto p_full = [&](int b2) { return bar + 8u * (10 + b2); };
+  const uint32_t o_full = bar + 8u * 12, o_read = bar + 8u * 13, q_full = bar + 8u * 14, q_done = bar + 8u * 15, st_done = bar + 8u * 16,
+                 tmem_slot = bar + 8u * 17;
+  static_assert(NS <= 2, "barrier table holds two K/V stages");
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ctl_ptr + 8 * 17);
+  uint32_t* pad32 = reinterpret_cast<uint32_t*>(ctl_ptr + 192);               // [2][64] words: 32 keys each (S <= 2048 staged)
+  volatile int* meta_s = reinterpret_cast<volatile int*>(ctl_ptr + 192 + 512); // ring of 4 x {tile or -1, block count, first_real, -}
+  constexpr int kMaxPadWords = 64;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_bh = p.B * p.h;
+  const int n_qt = (p.S + 127) / 128;
+  const int n_all = (p.S + 63) / 64;
+  const int n_words = 2 * n_all;
+  const int band = n_qt <= 8 ? 2 : 4;
+  struct Tile { int b, head, q0; };
+  auto tile_of = [&](int t) {
+    Tile tl;
+    int bh, k;
+    banded_tile(t, n_qt, n_bh, band, bh, k);
+    tl.q0 = (n_qt - 1 - k) * 128;                             // latest query tiles have the most key blocks: first
+    tl.b = bh / p.h;
+    tl.head = bh - tl.b * p.h;
+    return tl;
+  };
+  auto n_blocks = [&](const Tile& tl, int first_real) {
+    return tl.q0 < first_real ? n_all : min(n_all, (tl.q0 + 127) / 64 + 1);
+  };
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(kfull(s), 1); mbar_init(kfree(s), 1); mbar_init(vfull(s), 1); mbar_init(vfree(s), 1); }
+    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(s_full(b2), 1); mbar_init(p_full(b2), 128); }
+    mbar_init(o_full, 1); mbar_init(o_read, 128); mbar_init(q_full, 1); mbar_init(q_done, 128); mbar_init(st_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t t_q = tmem, t_o = tmem + D + 128;
+  auto t_s = [&](int b2) { return tmem + D + 64 * b2; };
+
+  if (warp == 0) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      auto issue_q = [&](const Tile& tl, int idx, int first_real, int t) {
+        meta_s[(idx & 3) * 4] = t;
+        meta_s[(idx & 3) * 4 + 1] = n_blocks(tl, first_real);
+        meta_s[(idx & 3) * 4 + 2] = first_real;
+        mbar_expect_tx(q_full, C::kTile);                      // (release: the ring entry is visible to every waiter)
+#pragma unroll
+        for (int a = 0; a < C::kAtoms; ++a)
+          tma_load_2d(q_s + a * (128 * 128), &map_q, q_full, tl.head * D + a * 32, tl.b * p.S + tl.q0);
+      };
+      auto publish_stop = [&](int idx) {
+        meta_s[(idx & 3) * 4] = -1;
+        mbar_arrive(q_full);
+      };
+      auto draw = [&]() { const int t = atomicAdd(sched, 1); return t < n_tiles ? t : -1; };
+      int t = draw();
+      Tile tl = tile_of(max(t, 0));
+      int first_real = t >= 0 ? __ldg(fnp + tl.b) : 0;
+      if (t >= 0) issue_q(tl, 0, first_real, t); else publish_stop(0);
+      int g = 0;
+      for (int i = 0; t >= 0; ++i) {
+        const int n_kv = n_blocks(tl, first_real);
+        const int t_next = draw();
+        Tile tn = tl;
+        int fr_next = 0;
+        if (t_next >= 0) { tn = tile_of(t_next); fr_next = __ldg(fnp + tn.b); }
+        for (int kb = 0; kb < n_kv; ++kb, ++g) {
+          const int s = g % NS;
+          const uint32_t free_par = (uint32_t)((g / NS) & 1) ^ 1u;
+          const int krow = tl.b * p.S + kb * 64;
+          mbar_wait(kfree(s), free_par);
+          mbar_expect_tx(kfull(s), C::kBlk);
+#pragma unroll
+          for (int a = 0; a < C::kAtoms; ++a)
+            tma_load_2d(kv_s + s * C::kStage + a * (64 * 128), &map_k, kfull(s), p.E + tl.head * D + a * 32, krow);
+          mbar_wait(vfree(s), free_par);
+          mbar_expect_tx(vfull(s), C::kBlk);
+#pragma unroll
+          for (int a = 0; a < C::kAtoms; ++a)
+            tma_load_2d(kv_s + s * C::kStage + C::kBlk + a * (64 * 128), &map_v, vfull(s), 2 * p.E + tl.head * D + a * 32, krow);
+          if (kb == min(1, n_kv - 1)) {
+            mbar_wait(q_done, (uint32_t)(i & 1));              // this tile's Q image has left the buffer ...
+            if (i > 0) mbar_wait(st_done, (uint32_t)((i - 1) & 1));   // ... and so has the previous tile's O staging
+            if (t_next >= 0) issue_q(tn, i + 1, fr_next, t_next); else publish_stop(i + 1);
+          }
+        }
+        tl = tn;
+        first_real = fr_next;
+        t = t_next;
+      }
+      if (atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }   // counters ready for the next launch
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (converged warp, elected lane) ----------------
+    constexpr uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int g0 = 0;
+    for (int i = 0;; ++i) {
+      mbar_wait(q_full, (uint32_t)(i & 1));                    // (acquire) ring entry of tile i
+      if (meta_s[(i & 3) * 4] < 0) break;
+      mbar_wait(q_done, (uint32_t)(i & 1));                    // Q of this tile is in TMEM
+      tc_fence_after();
+      const int n_kv = meta_s[(i & 3) * 4 + 1];
+      auto issue_s = [&](int j) {            // S = Q K^T (A = Q in TMEM)
+        const int g = g0 + j, s = g % NS, b2 = g & 1;
+        mbar_wait(kfull(s), (uint32_t)((g / NS) & 1));
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t kd = make_desc(kv_s + s * C::kStage, 16, 1024, 2);
+#pragma unroll
+          for (int kk = 0; kk < D / 8; ++kk)
+            umma_tf32_ts(t_s(b2), t_q + kk * 8, kd + (uint64_t)(((kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4), idesc_s, kk > 0 ? 1u : 0u);
+          umma_commit(s_full(b2));
+          umma_commit(kfree(s));
+        }
+        __syncwarp();
+      };
+      issue_s(0);
+      if (n_kv > 1) issue_s(1);
+      for (int j = 0; j < n_kv; ++j) {
+        const int g = g0 + j, s = g % NS, b2 = g & 1;
+        mbar_wait(vfull(s), (uint32_t)((g / NS) & 1));
+        mbar_wait(p_full(b2), (uint32_t)((g >> 1) & 1));
+        if (g > 0) mbar_wait(o_read, (uint32_t)((g - 1) & 1));      // the previous O block has been folded into registers
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t vd = make_desc(kv_s + s * C::kStage + C::kBlk, 64 * 128, 512, 1);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)          // O_blk = P V (A = P in TMEM, K = 64 keys)
+            umma_tf32_ts(t_o, t_s(b2) + kk * 8, vd + (uint64_t)(kk * 64), idesc_o, kk > 0 ? 1u : 0u);
+          umma_commit(o_full);
+          umma_commit(vfree(s));
+        }
+        __syncwarp();
+        if (j + 2 < n_kv) issue_s(j + 2);
+      }
+      g0 += n_kv;
+    }
+  } else {
+    // ---------------- softmax warps: thread == query row ----------------
+    const int cw = warp - 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint64_t scale2 = pack2f(p.scale_log2, p.scale_log2);
+    const bool pads_staged = n_words <= kMaxPadWords;
+    const bool storer = cw == 0 && lane == 0;
+
+    auto stage_q = [&](int idx) {                              // Q image -> TMEM (this thread's row); false = no tile
+      mbar_wait(q_full, (uint32_t)(idx & 1));
+      if (meta_s[(idx & 3) * 4] < 0) return false;
+#pragma unroll
+      for (int a = 0; a < C::kAtoms; ++a) {
+        uint32_t v[32];
+        load_swizzled_row(q_ptr + a * (128 * 128), r, v);
+        tmem_st32(t_q + lane_addr + a * 32, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(q_done);
+      return true;
+    };
+    // PAD words of a sequence: warp cw owns words cw, cw+4, ...; up to 4 of them ride in registers across a drain
+    int32_t pad_id[4];
+    auto fetch_pads = [&](int b) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int key = (cw + 4 * u) * 32 + lane;
+        pad_id[u] = key < p.S ? __ldg(x + (int64_t)b * p.S + key) : 0;
+      }
+    };
+    auto store_pads = [&](int b, int idx) {
+      uint32_t* dst = pad32 + (idx & 1) * kMaxPadWords;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, pad_id[u] == 0);
+        if (lane == 0 && cw + 4 * u < n_words) dst[cw + 4 * u] = bits;
+      }
+      for (int w = cw + 16; w < n_words; w += 4) {            // sequences longer than 512: the rest, synchronously
+        const int key = w * 32 + lane;
+        const uint32_t bits = __ballot_sync(0xffffffffu, key < p.S ? (__ldg(x + (int64_t)b * p.S + key) == 0) : true);
+        if (lane == 0) dst[w] = bits;
+      }
+    };
+
+    bool have = stage_q(0);
+    Tile tl = tile_of(have ? meta_s[0] : 0);
+    if (have && pads_staged) { fetch_pads(tl.b); store_pads(tl.b, 0); }
+    asm volatile("bar.sync 1, 128;" ::: "memory");            // PAD words visible
+    int g0 = 0;
+    for (int i = 0; have; ++i) {
+      const int n_kv = meta_s[(i & 3) * 4 + 1], first_real = meta_s[(i & 3) * 4 + 2];
+      const int row = tl.q0 + r;
+      const bool deg = row < first_real;
+      const uint32_t* pads = pad32 + (i & 1) * kMaxPadWords;
+      float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
+      uint32_t o[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) o[c] = 0u;
+      auto fold = [&](int g, float alpha) {                    // o = o * alpha + O_blk(g)
+        const uint64_t alpha2 = pack2f(alpha, alpha);
+        mbar_wait(o_full, (uint32_t)(g & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < D / 32; ++cc) {
+          uint32_t ov[32];
+          tmem_ld32_nowait(t_o + lane_addr + cc * 32, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; c += 2)
+            unpack2(ffma2(pack2(o[cc * 32 + c], o[cc * 32 + c + 1]), alpha2, pack2(ov[c], ov[c + 1])), o[cc * 32 + c], o[cc * 32 + c + 1]);
+        }
+        tc_fence_before();
+        mbar_arrive(o_read);
+      };
+      for (int j = 0; j < n_kv; ++j) {
+        const int g = g0 + j, b2 = g & 1;
+        const int k0 = j * 64;
+        unsigned long long padbits;
+        if (pads_staged) {
+          padbits = (unsigned long long)pads[2 * j] | ((unsigned long long)pads[2 * j + 1] << 32);
+        } else {
+          const int ka = k0 + lane, kb2 = k0 + 32 + lane;
+          const bool pa = ka < p.S ? (x[(int64_t)tl.b * p.S + ka] == 0) : true;
+          const bool pb = kb2 < p.S ? (x[(int64_t)tl.b * p.S + kb2] == 0) : true;
+          padbits = (unsigned long long)__ballot_sync(0xffffffffu, pa) | ((unsigned long long)__ballot_sync(0xffffffffu, pb) << 32);
+        }
+        const int in_range = min(64, p.S - k0);
+        const unsigned long long range_bits = in_range >= 64 ? ~0ull : ((1ull << in_range) - 1ull);
+        unsigned long long vis;
+        if (row >= p.S) vis = 0ull;
+        else if (deg) vis = range_bits;
+        else {
+          const int upto = row - k0;
+          const unsigned long long causal = upto < 0 ? 0ull : (upto >= 63 ? ~0ull : ((1ull << (upto + 1)) - 1ull));
+          vis = causal & ~padbits & range_bits;
+        }
+        mbar_wait(s_full(b2), (uint32_t)((g >> 1) & 1));
+        tc_fence_after();
+        uint32_t s0[32], s1[32];
+        tmem_ld32_nowait(t_s(b2) + lane_addr, s0);
+        tmem_ld32_nowait(t_s(b2) + lane_addr + 32, s1);
+        tmem_ld_wait();
+        const bool all_vis = __all_sync(0xffffffffu, vis == ~0ull);
+        float mx = -INFINITY;
+        if (all_vis) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (vis & (1ull << c)) mx = fmaxf(mx, __uint_as_float(s0[c]));
+            if (vis & (1ull << (c + 32))) mx = fmaxf(mx, __uint_as_float(s1[c]));
+          }
+        }
+        const float m_new = fmaxf(m, mx * p.scale_log2);
+        const float m_use = m_new == -INFINITY ? 0.f : m_new;      // row with no visible key yet
+        const float alpha = fast_exp2(m - m_use);                   // exp2(-inf) = 0 when m was -inf
+        const uint64_t negm2 = pack2f(-m_use, -m_use);
+        uint64_t rsum2 = 0ull;
+        const uint32_t vlo = (uint32_t)vis, vhi = (uint32_t)(vis >> 32);
+        if (all_vis) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            uint32_t xa, xb, ya, yb;
+            unpack2(ffma2(pack2(s0[c], s0[c + 1]), scale2, negm2), xa, xb);
+            unpack2(ffma2(pack2(s1[c], s1[c + 1]), scale2, negm2), ya, yb);
+            const float e0 = fast_exp2(__uint_as_float(xa)), e1 = fast_exp2(__uint_as_float(xb));
+            const float f0 = fast_exp2(__uint_as_float(ya)), f1 = fast_exp2(__uint_as_float(yb));
+            rsum2 = fadd2(rsum2, fadd2(pack2f(e0, e1), pack2f(f0, f1)));
+            s0[c] = rna_tf32_bits(__float_as_uint(e0)); s0[c + 1] = rna_tf32_bits(__float_as_uint(e1));
+            s1[c] = rna_tf32_bits(__float_as_uint(f0)); s1[c + 1] = rna_tf32_bits(__float_as_uint(f1));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            uint32_t xa, xb, ya, yb;
+            unpack2(ffma2(pack2(s0[c], s0[c + 1]), scale2, negm2), xa, xb);
+            unpack2(ffma2(pack2(s1[c], s1[c + 1]), scale2, negm2), ya, yb);
+            const float e0 = (vlo & (1u << c)) ? fast_exp2(__uint_as_float(xa)) : 0.f, e1 = (vlo & (2u << c)) ? fast_exp2(__uint_as_float(xb)) : 0.f;
+            const float f0 = (vhi & (1u << c)) ? fast_exp2(__uint_as_float(ya)) : 0.f, f1 = (vhi & (2u << c)) ? fast_exp2(__uint_as_float(yb)) : 0.f;
+            rsum2 = fadd2(rsum2, fadd2(pack2f(e0, e1), pack2f(f0, f1)));
+            s0[c] = rna_tf32_bits(__float_as_uint(e0)); s0[c + 1] = rna_tf32_bits(__float_as_uint(e1));
+            s1[c] = rna_tf32_bits(__float_as_uint(f0)); s1[c + 1] = rna_tf32_bits(__float_as_uint(f1));
+          }
+        }
+        tmem_st32(t_s(b2) + lane_addr, s0);
+        tmem_st32(t_s(b2) + lane_addr + 32, s1);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full(b2));
+        if (j == 0 && i > 0 && storer) {                       // the previous tile's bulk store has had a whole block to read its staging
+          bulk_wait_read0();
+          mbar_arrive(st_done);
+        }
+        uint32_t ra, rb;
+        unpack2(rsum2, ra, rb);
+        l = l * alpha + (__uint_as_float(ra) + __uint_as_float(rb));
+        m = m_new;
+        if (j > 0) fold(g - 1, alpha_prev);        // the product this thread enabled one block ago has long retired
+        alpha_prev = alpha;
+      }
+      fold(g0 + n_kv - 1, alpha_prev);
+      g0 += n_kv;
+      // natural-log LSE of the scaled scores (m, l are in the exp2 domain)
+      if (row < p.S) lse[((int64_t)tl.b * p.h + tl.head) * p.S + row] = (m + log2f(l)) * (1.f / kLog2e);
+
+      // every S product of this tile has retired: the next tile's Q goes to TMEM before this tile's output is drained
+      have = stage_q(i + 1);
+      Tile tn = tl;
+      if (have) {
+        tn = tile_of(meta_s[((i + 1) & 3) * 4]);
+        if (pads_staged) fetch_pads(tn.b);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // every row of the Q image has been read: the buffer becomes the O staging
+      {
+        const float inv = 1.f / l;
+#pragma unroll
+        for (int cc = 0; cc < D / 32; ++cc) {
+          uint32_t part[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) part[c] = o[cc * 32 + c];
+          put_row_sw128(q_ptr + cc * (128 * 128), r, part, inv);
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (storer) {
+#pragma unroll
+          for (int at = 0; at < C::kAtoms; ++at)
+            tma_store_3d(&map_out, q_s + at * (128 * 128), tl.head * D + at * 32, tl.q0, tl.b);
+          bulk_commit();
+        }
+      }
+      if (have && pads_staged) store_pads(tn.b, i + 1);
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // PAD words of the next tile visible
+      tl = tn;
+    }
+    if (storer) bulk_wait_read0();                             // the last tile's staging must outlive its store
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, C::kTmemCols);
+  }
+}
+
 template <int D>
 int launch_fwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int32_t* x, const int32_t* fnp, float* ctx,
                float* lse) {
@@ -2056,7 +2440,24 @@ int launch_fwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int
   if (trace_on < 0) { const char* e = getenv("NLPS_ATTN_TRACE"); trace_on = (e && e[0] == '1') ? 1 : 0; }
   Dims p{B, S, h, E, (float)(1.0 / std::sqrt((double)D)) * kLog2e, trace_on};
   dim3 grid((unsigned)ceil_div(S, 128), (unsigned)h, (unsigned)B);
-  attn_fwd_ts<D, NS><<<grid, kFwdThreads, C::kSmem, st>>>(mq, mk, mv, p, x, fnp, ctx, lse);
+  static int persistent = -1;
+  if (persistent < 0) { const char* e = getenv("NLPS_ATTN_PS"); persistent = (e && e[0] == '0') ? 0 : 1; }
+  const int64_t n_tiles = ceil_div(S, 128) * (int64_t)B * h;
+  if (persistent && !trace_on && (reinterpret_cast<uintptr_t>(ctx) & 15u) == 0 && n_tiles < (1ll << 30)) {
+    static bool once_ps = false;
+    if (!once_ps) {
+      NLPS_CUDA(cudaFuncSetAttribute(attn_fwd_ps<D, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+      once_ps = true;
+    }
+    CUtensorMap out3;
+    NLPS_TRY(make_map3(&out3, ctx, (uint64_t)E, (uint64_t)S, (uint64_t)B, (int64_t)E, (int64_t)S * E, 32, 128));
+    int* sched = nullptr;
+    NLPS_TRY(sched_counters(st, 2, &sched));
+    attn_fwd_ps<D, NS><<<(unsigned)std::min<int64_t>(n_tiles, 2 * kNumSMs), kFwdThreads, C::kSmem, st>>>(
+        mq, mk, mv, out3, p, (int)n_tiles, sched, x, fnp, lse);
+  } else {
+    attn_fwd_ts<D, NS><<<grid, kFwdThreads, C::kSmem, st>>>(mq, mk, mv, p, x, fnp, ctx, lse);
+  }
   NLPS_LAUNCH_CHECK();
   if (trace_on) {
     static int printed = 0;
