@@ -34,6 +34,7 @@ def t(fn):
         for _ in range(reps): fn()
         e1.record(); torch.cuda.synchronize()
         out.append(e0.elapsed_time(e1) / reps)
+    if os.environ.get('NLPS_BENCH_VERBOSE'): print('   trials (ms):', ' '.join('%.3f' % v for v in out))
     return sorted(out)[2]
 flops_fwd = 2.0 * 2 * B * h * S * S * d / 2      # causal half
 tf, tb = t(fwd), t(bwd)
