@@ -102,8 +102,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  Deliberately NOT .release.cluster: that form compiles to
+// MEMBAR.ALL.GPU + ERRBAR and makes the arriving epilogue lane wait until all of its outstanding global stores are
+// visible GPU-wide (18 % of the GEMM's stall samples).  The hand-over here is a TMEM buffer, ordered by
+// tcgen05.fence::before_thread_sync; the default (.release at CTA scope) is what CUTLASS's ClusterBarrier uses.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's smem, completing the transaction on the (leader's) mbarrier `bar_cluster`
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
