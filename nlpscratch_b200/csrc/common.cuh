@@ -148,6 +148,9 @@ struct GemmArgs {
   DropoutParams drop = {0.f, 1.f, 65536u, 0, 0, 0, 0};        // then inverted dropout
   const float* residual = nullptr; int64_t ldr = 0;   // then += residual
   bool accumulate = false;          // finally C += result instead of C = result
+  // optional by-product (tensor-core CTA-pair kernel only, see gemm_tf32_colsum_fusable): per 32-row block column sums of
+  // the stored result, [ceil(M/32)][N] floats -- the bias gradient of the layer below without another pass over C
+  float* colsum32_out = nullptr;
 };
 
 // bias -> relu -> gate -> dropout -> residual, identical in every GEMM implementation
@@ -164,6 +167,7 @@ int gemm_fp32(cudaStream_t st, const GemmArgs& g);       // gemm_simt.cu
 int gemm_tf32(cudaStream_t st, const GemmArgs& g);       // gemm_tcgen05.cu  (1xTF32)
 int gemm_tf32x3(cudaStream_t st, const GemmArgs& g);     // 3-pass split, FP32-level error
 bool gemm_tf32_supported(const GemmArgs& g);
+bool gemm_tf32_colsum_fusable(const GemmArgs& g);   // colsum32_out may be set for this product
 int gemm_dispatch(cudaStream_t st, int precision, const GemmArgs& g);
 
 // dataset.cu

@@ -191,6 +191,25 @@ __device__ __forceinline__ void epilogue_row(const GemmArgs& g, uint32_t (&v)[32
   }
 }
 
+// Column sums of a warp's 32x32 block (thread = row, v = its 32 columns): recursive halving over the lanes, 31 shuffles;
+// lane j ends up with the total of column j.  Fixed order => deterministic.
+__device__ __forceinline__ float block_colsum32(const uint32_t (&v)[32], bool row_live, int lane) {
+  float t[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) t[i] = row_live ? __uint_as_float(v[i]) : 0.f;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? t[i] : t[i + off];
+      const float keep = upper ? t[i + off] : t[i];
+      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return t[0];
+}
+
 // Phase 2 without the shared-memory transpose: the thread owns 32 consecutive output floats of one row
 // (128 B) and moves them with four 256-bit accesses (LDG/STG.E.ENL2.256).  Every access is a full 32-B
 // sector, and the 2 x 128 KB per tile of staging traffic -- which competes with TMA fills and UMMA
@@ -563,6 +582,11 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         uint32_t v[32];
         tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
         if (ka.ws == nullptr) epilogue_row(g, v, m0 + q * 32 + lane, n0 + c * 32);
+        if (g.colsum32_out != nullptr) {     // the epilogue warps have slack: the bias-gradient partials ride along
+          const float tot = block_colsum32(v, m0 + q * 32 + lane < g.M, lane);
+          const int col = n0 + c * 32 + lane;
+          if (col < g.N) g.colsum32_out[(int64_t)((m0 + q * 32) >> 5) * g.N + col] = tot;
+        }
         if (c == c_end - 1) {
           tc_fence_before();
           if (lane == 0) mbar_arrive_cluster(lead_tempty);
@@ -765,6 +789,8 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
                (!g.gate || (aligned16(g.gate) && g.ldg % 4 == 0))) ? 1 : 0;
   NLPS_REQUIRE(!(g.relu_bits_out || g.gate_bits) || (g.N % 32 == 0 && splits == 1),
                "gemm_tf32: bit-packed ReLU masks need N %% 32 == 0 and no split-K");
+  NLPS_REQUIRE(g.colsum32_out == nullptr || (pair && splits == 1 && !g.gate && !g.residual && !g.accumulate),
+               "gemm_tf32: colsum32_out needs the CTA-pair kernel without split-K, float gate, residual or accumulate");
   ka.ws = nullptr;
   ka.ws_ld = round_up(g.N, 8);
   {
@@ -817,6 +843,15 @@ bool gemm_tf32_supported(const GemmArgs& g) {
 }
 
 int gemm_tf32(cudaStream_t st, const GemmArgs& g) { return gemm_tf32_impl(st, g, /*round_tf32=*/true); }
+
+// mirrors the tile / split choice of gemm_tf32_impl
+bool gemm_tf32_colsum_fusable(const GemmArgs& g) {
+  if (!gemm_tf32_supported(g) || !(pair_mode() && g.M > 128 && g.N > 128)) return false;
+  if (g.gate || g.residual || g.accumulate) return false;
+  const int64_t tiles = ceil_div(g.M, 256) * ceil_div(g.N, 256);
+  const int64_t kblocks = ceil_div(g.K, BK);
+  return !(tiles < 2 * (kNumSMs / 2) && kblocks >= 64);      // no split-K
+}
 
 // 3xTF32: A = Ah + Al, B = Bh + Bl with Ah,Bh exactly representable in TF32;
 // T = Al*Bh + Ah*Bl + Ah*Bh (small terms first), dropping only Al*Bl (~2^-22 relative);

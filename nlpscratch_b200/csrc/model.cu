@@ -13,6 +13,7 @@
 //   per layer: qkv (N,3E), ctx (N,E), lse (B,h,S), r1 (N,E), mean1/rstd1 (N), y1 (N,E),
 //              hid (N,F), r2 (N,E), mean2/rstd2 (N), y2 (N,E);  plus h0 (N,E), x_flat, first_nonpad,
 //              logits (N,ldV).  The (B,h,S,S) attention tensors and dropout masks are never stored.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/nlps_b200.h"
 #include <algorithm>
@@ -72,6 +73,7 @@ struct nlps_model {
   // backward workspace (grows with N)
   int64_t ws_N = 0;
   float *g0 = nullptr, *g1 = nullptr, *gdrop = nullptr, *dctx = nullptr, *dqkv = nullptr, *dhid = nullptr;
+  float* colsum32 = nullptr;                  // [ceil(N/32)][F] column-sum partials written by the dz GEMM epilogue
   float *delta = nullptr, *row_loss = nullptr, *small = nullptr, *rows_tmp = nullptr;
   int32_t* iscratch = nullptr;
   int64_t rows_tmp_cap = 0;
@@ -128,7 +130,7 @@ int ensure_workspace(nlps_model* m, int B, int S) {
   const int64_t N = (int64_t)B * S;
   if (N <= m->ws_N) return 0;
   NLPS_CUDA(cudaStreamSynchronize(m->stream));
-  float** bufs[] = {&m->g0, &m->g1, &m->gdrop, &m->dctx, &m->dqkv, &m->dhid, &m->delta, &m->row_loss};
+  float** bufs[] = {&m->g0, &m->g1, &m->gdrop, &m->dctx, &m->dqkv, &m->dhid, &m->delta, &m->row_loss, &m->colsum32};
   for (float** b : bufs) { if (*b) cudaFree(*b); *b = nullptr; }
   if (m->iscratch) { cudaFree(m->iscratch); m->iscratch = nullptr; }
   const int64_t E = m->E, F = m->F;
@@ -138,6 +140,7 @@ int ensure_workspace(nlps_model* m, int B, int S) {
   NLPS_CUDA(cudaMalloc(&m->dctx, sizeof(float) * N * E));
   NLPS_CUDA(cudaMalloc(&m->dqkv, sizeof(float) * N * 3 * E));
   NLPS_CUDA(cudaMalloc(&m->dhid, sizeof(float) * N * F));
+  NLPS_CUDA(cudaMalloc(&m->colsum32, sizeof(float) * ceil_div(N, 32) * F));
   NLPS_CUDA(cudaMalloc(&m->delta, sizeof(float) * N * m->h));
   NLPS_CUDA(cudaMalloc(&m->row_loss, sizeof(float) * N));
   NLPS_CUDA(cudaMalloc(&m->iscratch, sizeof(int32_t) * embed_backward_scratch_ints(N, m->V)));
@@ -195,18 +198,24 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
       NLPS_TRY(gemm_dispatch(st, prec, g));
       NLPS_TRY(colsum(st, N, E, d_f, E, m->G + o.b2, m->colsum_scratch, colsum_tickets_for(m, E)));
     }
+    bool db1_fused = false;
     {  // dz = (d_f W2^T) * (hid > 0)
       GemmArgs g = gemm_nn(N, F, E, d_f, E, m->P + o.w2, E, m->dhid, F);
       g.trans_b = true;
       if (c->relu_bits_valid && prec == NLPS_PREC_TF32) { g.gate_bits = a.relu_bits; g.ld_bits = F / 32; }
       else { g.gate = a.hid; g.ldg = F; }
+      // db1 = column sums of dz: 32-row partials come out of this product's epilogue (tensor-core path)
+      static int fuse_db1 = -1;             // NLPS_FUSE_DB1=0: separate column-sum pass (A/B measurements)
+      if (fuse_db1 < 0) { const char* e = getenv("NLPS_FUSE_DB1"); fuse_db1 = (e && e[0] == '0') ? 0 : 1; }
+      if (fuse_db1 && prec == NLPS_PREC_TF32 && m->colsum32 != nullptr && gemm_tf32_colsum_fusable(g)) { g.colsum32_out = m->colsum32; db1_fused = true; }
       NLPS_TRY(gemm_dispatch(st, prec, g));
     }
     {  // dW1 = y1^T dz ; db1
       GemmArgs g = gemm_nn(E, F, N, a.y1, E, m->dhid, F, m->G + o.w1, F);
       g.trans_a = true;
       NLPS_TRY(gemm_dispatch(st, prec, g));
-      NLPS_TRY(colsum(st, N, F, m->dhid, F, m->G + o.b1, m->colsum_scratch, colsum_tickets_for(m, F)));
+      if (db1_fused) NLPS_TRY(colsum(st, ceil_div(N, 32), F, m->colsum32, F, m->G + o.b1, m->colsum_scratch, colsum_tickets_for(m, F)));
+      else NLPS_TRY(colsum(st, N, F, m->dhid, F, m->G + o.b1, m->colsum_scratch, colsum_tickets_for(m, F)));
     }
     {  // d(y1) = dz W1^T + d_r2
       GemmArgs g = gemm_nn(N, E, F, m->dhid, F, m->P + o.w1, F, m->g0, E);
@@ -386,7 +395,7 @@ int nlps_destroy(nlps_model* m) {
   cudaDeviceSynchronize();
   for (nlps_cache* c : m->pool) { if (c->base) cudaFree(c->base); delete c; }
   float* bufs[] = {m->P, m->G, m->M, m->Vv, m->pe, m->g0, m->g1, m->gdrop, m->dctx, m->dqkv, m->dhid, m->delta,
-                   m->row_loss, m->rows_tmp, m->ln_partial, m->colsum_scratch, m->sumsq_scratch, m->scalars};
+                   m->row_loss, m->rows_tmp, m->ln_partial, m->colsum_scratch, m->sumsq_scratch, m->scalars, m->colsum32};
   for (float* b : bufs) if (b) cudaFree(b);
   if (m->iscratch) cudaFree(m->iscratch);
   if (m->err_flag) cudaFree(m->err_flag);
