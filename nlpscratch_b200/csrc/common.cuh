@@ -151,6 +151,10 @@ struct GemmArgs {
   // optional by-product (tensor-core CTA-pair kernel only, see gemm_tf32_colsum_fusable): per 32-row block column sums of
   // the stored result, [ceil(M/32)][N] floats -- the bias gradient of the layer below without another pass over C
   float* colsum32_out = nullptr;
+  // second by-product (same kernel, same conditions): softmax statistics of every 32-column block of a row,
+  // rowstat_out[row * ceil(N/32) + block] = {max, sum exp(v - max)} -- the cross-entropy then skips its first pass
+  // over the logits (the part of the vocab-head + CE fusion that pays at V = 8192)
+  float2* rowstat_out = nullptr;
 };
 
 // bias -> relu -> gate -> dropout -> residual, identical in every GEMM implementation
@@ -211,8 +215,12 @@ int layernorm_forward(cudaStream_t st, int64_t rows, int E, const float* x, cons
 int layernorm_backward(cudaStream_t st, int64_t rows, int E, const float* dy, const float* x,
                        const float* mean, const float* rstd, const float* gamma, float* dx,
                        float* dx_dropped, const DropoutParams* drop,
-                       float* dgamma, float* dbeta, float* partial_scratch);
+                       float* dgamma, float* dbeta, float* partial_scratch,
+                       float* dbias = nullptr);   // optional: column sums of the branch gradient leaving the kernel (dx_dropped, else dx)
 size_t layernorm_backward_scratch_floats(int E);
+// rowstat != nullptr: per-32-column {max, sum exp} blocks from the vocab-head GEMM epilogue (see GemmArgs::rowstat_out)
+int softmax_xent_stats(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
+                       float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss, const float2* rowstat);
 int softmax_xent(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
                  float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss_scratch);
 // tickets: ceil(cols/128) zero-initialised counters (self-resetting) -> the reduction finishes inside the one kernel;

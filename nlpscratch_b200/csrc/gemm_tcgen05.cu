@@ -582,6 +582,16 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         uint32_t v[32];
         tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
         if (ka.ws == nullptr) epilogue_row(g, v, m0 + q * 32 + lane, n0 + c * 32);
+        if (g.rowstat_out != nullptr && m0 + q * 32 + lane < g.M) {   // softmax statistics of this row's 32 columns
+          const int col0 = n0 + c * 32;
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (col0 + j < g.N) mx = fmaxf(mx, __uint_as_float(v[j]));
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (col0 + j < g.N) sum += exp2f((__uint_as_float(v[j]) - mx) * 1.4426950408889634f);
+          g.rowstat_out[(int64_t)(m0 + q * 32 + lane) * ((g.N + 31) >> 5) + (col0 >> 5)] = make_float2(mx, sum);
+        }
         if (g.colsum32_out != nullptr) {     // the epilogue warps have slack: the bias-gradient partials ride along
           const float tot = block_colsum32(v, m0 + q * 32 + lane < g.M, lane);
           const int col = n0 + c * 32 + lane;
@@ -789,8 +799,8 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
                (!g.gate || (aligned16(g.gate) && g.ldg % 4 == 0))) ? 1 : 0;
   NLPS_REQUIRE(!(g.relu_bits_out || g.gate_bits) || (g.N % 32 == 0 && splits == 1),
                "gemm_tf32: bit-packed ReLU masks need N %% 32 == 0 and no split-K");
-  NLPS_REQUIRE(g.colsum32_out == nullptr || (pair && splits == 1 && !g.gate && !g.residual && !g.accumulate),
-               "gemm_tf32: colsum32_out needs the CTA-pair kernel without split-K, float gate, residual or accumulate");
+  NLPS_REQUIRE((g.colsum32_out == nullptr && g.rowstat_out == nullptr) || (pair && splits == 1 && !g.gate && !g.residual && !g.accumulate),
+               "gemm_tf32: colsum32_out / rowstat_out need the CTA-pair kernel without split-K, float gate, residual or accumulate");
   ka.ws = nullptr;
   ka.ws_ld = round_up(g.N, 8);
   {

@@ -42,6 +42,8 @@ struct nlps_cache {
   struct L { float *qkv, *ctx, *lse, *r1, *mean1, *rstd1, *y1, *hid, *r2, *mean2, *rstd2, *y2; uint32_t* relu_bits; };
   std::vector<L> layers;
   float* logits = nullptr;
+  float2* rowstat = nullptr;          // [N][ceil(V/32)] softmax statistics left by the vocab-head GEMM epilogue
+  bool rowstat_valid = false;
   float drop_p = 0.f;       // dropout probability in effect during this forward
   uint32_t drop_step = 0;
   bool has_logits = false;
@@ -190,13 +192,12 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
     DropoutParams dpf = drop_for(m, c, l, 1);
     NLPS_TRY(layernorm_backward(st, N, E, m->g0, a.r2, a.mean2, a.rstd2, m->P + o.ln2g, m->g1,
                                 dropping ? m->gdrop : nullptr, dropping ? &dpf : nullptr, m->G + o.ln2g,
-                                m->G + o.ln2b, m->ln_partial));
+                                m->G + o.ln2b, m->ln_partial, m->G + o.b2));     // db2 = column sums of d_f ride along
     const float* d_f = dropping ? m->gdrop : m->g1;
     {  // dW2 = hid^T d_f ; db2
       GemmArgs g = gemm_nn(F, E, N, a.hid, F, d_f, E, m->G + o.w2, E);
       g.trans_a = true;
       NLPS_TRY(gemm_dispatch(st, prec, g));
-      NLPS_TRY(colsum(st, N, E, d_f, E, m->G + o.b2, m->colsum_scratch, colsum_tickets_for(m, E)));
     }
     bool db1_fused = false;
     {  // dz = (d_f W2^T) * (hid > 0)
@@ -520,6 +521,7 @@ int nlps_cache_create(nlps_model* m, int B, int S, nlps_cache** out) {
     q.bits = carve(N * ((F + 31) / 32));
   }
   const int64_t o_logits = carve(N * m->ldV);
+  const int64_t o_rowstat = carve(2 * N * ((m->V + 31) / 32));
   c->bytes = (size_t)cur * sizeof(float);
   cudaError_t e = cudaMalloc(&c->base, c->bytes);
   if (e != cudaSuccess) {
@@ -546,6 +548,7 @@ int nlps_cache_create(nlps_model* m, int B, int S, nlps_cache** out) {
                     reinterpret_cast<uint32_t*>(f + q.bits)};
   }
   c->logits = f + o_logits;
+  c->rowstat = reinterpret_cast<float2*>(f + o_rowstat);
   *out = c;
   return 0;
 }
@@ -628,6 +631,13 @@ int nlps_forward(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, i
   if (!hidden_only) {  // logits = H W_vocab + b_vocab                 (:191)
     GemmArgs g = gemm_nn(N, m->V, E, x_in, E, m->P + m->off_Wvocab, m->ldV, c->logits, m->ldV);
     g.bias = m->P + m->off_bvocab;
+    // NLPS_FUSE_CE=1: softmax statistics come out of this product's epilogue and the loss skips its first pass over
+    // the logits.  Off by default: at c4 the 64 extra MUFU/FMNMX per 32-column block cost the K=512 vocab product more
+    // (+0.17 ms/step measured, same box) than the saved 1.07 GB read that mostly hits L2 anyway.
+    static int fuse_ce = -1;
+    if (fuse_ce < 0) { const char* e = getenv("NLPS_FUSE_CE"); fuse_ce = (e && e[0] == '1') ? 1 : 0; }
+    c->rowstat_valid = fuse_ce && prec == NLPS_PREC_TF32 && c->rowstat != nullptr && gemm_tf32_colsum_fusable(g);
+    if (c->rowstat_valid) g.rowstat_out = c->rowstat;
     NLPS_TRY(gemm_dispatch(st, prec, g));
     c->has_logits = true;
   }
@@ -741,8 +751,12 @@ int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs
   NLPS_REQUIRE(m && c && d_x && d_y, "nlps_train_step: null argument");
   NLPS_TRY(nlps_forward(m, c, d_x, xs, 0, nullptr, 0));
   // dlogits overwrite the logits in place: 8V bytes of HBM traffic per token for the loss
-  NLPS_TRY(nlps_loss_dlogits(m, c->logits, m->ldV, d_y, c->N, grad_scale, d_loss, c->logits, m->ldV));
+  NLPS_CUDA(cudaSetDevice(m->device));
+  NLPS_TRY(ensure_rows_tmp(m, c->N));
+  NLPS_TRY(softmax_xent_stats(m->stream, c->logits, m->ldV, d_y, c->N, m->V, grad_scale, d_loss ? d_loss : m->scalars + 3, c->logits,
+                              m->ldV, m->rows_tmp, c->rowstat_valid ? c->rowstat : nullptr));
   c->has_logits = false;
+  c->rowstat_valid = false;
   NLPS_TRY(nlps_backward(m, c, c->logits, m->ldV));
   if (defer_update) return 0;
   if (max_norm > 0.f) NLPS_TRY(nlps_clip_compute(m, max_norm));

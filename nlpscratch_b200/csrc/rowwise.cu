@@ -86,20 +86,23 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(int64_t rows, int
                                                                const float* __restrict__ gamma,
                                                                float* __restrict__ dx, float* __restrict__ dx_dropped,
                                                                const DropoutParams drop, int use_drop,
-                                                               float* __restrict__ partial) {
-  extern __shared__ float red[];     // [kLnWarps][2][E]
+                                                               float* __restrict__ partial, int nsum) {
+  // nsum == 3: a third column sum rides along -- of the branch gradient that leaves this kernel (dx_dropped, or dx when
+  // there is no dropout): the bias gradient of the sub-layer's last projection (db2) without another pass
+  extern __shared__ float red[];     // [kLnWarps][nsum][E]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float invE = 1.f / (float)E;
   const int64_t rows_per_cta = (rows + gridDim.x - 1) / gridDim.x;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t r1 = min(rows, r0 + rows_per_cta);
   if constexpr (VEC > 0) {
-    float4 g[VEC], ag[VEC], ab[VEC];
+    float4 g[VEC], ag[VEC], ab[VEC], ad[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       g[i] = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
       ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int64_t row = r0 + warp; row < r1; row += kLnWarps) {
       const float mu = mean[row], rs = rstd[row];
@@ -132,68 +135,76 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(int64_t rows, int
           dropout_four(drop, (uint64_t)row * (uint64_t)E + (uint64_t)c, o);
           *reinterpret_cast<float4*>(dx_dropped + row * E + c) = o;
         }
+        ad[i].x += o.x; ad[i].y += o.y; ad[i].z += o.z; ad[i].w += o.w;
       }
     }
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const int c = (i * 32 + lane) * 4;
-      *reinterpret_cast<float4*>(red + (warp * 2 + 0) * E + c) = ag[i];
-      *reinterpret_cast<float4*>(red + (warp * 2 + 1) * E + c) = ab[i];
+      *reinterpret_cast<float4*>(red + (warp * nsum + 0) * E + c) = ag[i];
+      *reinterpret_cast<float4*>(red + (warp * nsum + 1) * E + c) = ab[i];
+      if (nsum == 3) *reinterpret_cast<float4*>(red + (warp * nsum + 2) * E + c) = ad[i];
     }
   } else {
-    for (int c = lane; c < E; c += 32) { red[(warp * 2 + 0) * E + c] = 0.f; red[(warp * 2 + 1) * E + c] = 0.f; }
+    for (int c = lane; c < E; c += 32)
+      for (int k = 0; k < nsum; ++k) red[(warp * nsum + k) * E + c] = 0.f;
     for (int64_t row = r0 + warp; row < r1; row += kLnWarps) {
       const float mu = mean[row], rs = rstd[row];
       float s1 = 0.f, s2 = 0.f;
       for (int c = lane; c < E; c += 32) {
         const float xh = (x[row * E + c] - mu) * rs, dv = dy[row * E + c], dh = dv * gamma[c];
         s1 += dh; s2 += dh * xh;
-        red[(warp * 2 + 0) * E + c] += dv * xh;
-        red[(warp * 2 + 1) * E + c] += dv;
+        red[(warp * nsum + 0) * E + c] += dv * xh;
+        red[(warp * nsum + 1) * E + c] += dv;
       }
       s1 = warp_sum(s1) * invE;
       s2 = warp_sum(s2) * invE;
       for (int c = lane; c < E; c += 32) {
         const float xh = (x[row * E + c] - mu) * rs, dh = dy[row * E + c] * gamma[c];
-        const float o = (dh - s1 - xh * s2) * rs;
+        float o = (dh - s1 - xh * s2) * rs;
         dx[row * E + c] = o;
-        if (use_drop) dx_dropped[row * E + c] = dropout_one(drop, (uint64_t)row * (uint64_t)E + (uint64_t)c, o);
+        if (use_drop) { o = dropout_one(drop, (uint64_t)row * (uint64_t)E + (uint64_t)c, o); dx_dropped[row * E + c] = o; }
+        if (nsum == 3) red[(warp * nsum + 2) * E + c] += o;
       }
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * E; c += blockDim.x) {
+  for (int c = threadIdx.x; c < nsum * E; c += blockDim.x) {
     const int which = c / E, col = c - which * E;
     float acc = 0.f;
 #pragma unroll
-    for (int w = 0; w < kLnWarps; ++w) acc += red[(w * 2 + which) * E + col];
-    partial[((int64_t)blockIdx.x * 2 + which) * E + col] = acc;
+    for (int w = 0; w < kLnWarps; ++w) acc += red[(w * nsum + which) * E + col];
+    partial[((int64_t)blockIdx.x * nsum + which) * E + col] = acc;
   }
 }
 
 // block = 32 columns x 8 partial-slices; fixed summation order (slice-major) => deterministic
-__global__ void __launch_bounds__(256) ln_bwd_finish_kernel(int nparts, int E, const float* __restrict__ partial,
-                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+__global__ void __launch_bounds__(256) ln_bwd_finish_kernel(int nparts, int E, int nsum, const float* __restrict__ partial,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            float* __restrict__ dbias) {
   __shared__ float sm[8][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;               // column in the concatenated [dgamma | dbeta] row
+  const int c = blockIdx.x * 32 + lane;               // column in the concatenated [dgamma | dbeta | dbias] row
+  const int W = nsum * E;
   float acc = 0.f;
-  if (c < 2 * E) {
+  if (c < W) {
     int p = warp;
     for (; p + 24 < nparts; p += 32) {                  // four loads in flight, added in slice order
-      const float a = partial[(int64_t)p * 2 * E + c], b = partial[(int64_t)(p + 8) * 2 * E + c];
-      const float d = partial[(int64_t)(p + 16) * 2 * E + c], e = partial[(int64_t)(p + 24) * 2 * E + c];
+      const float a = partial[(int64_t)p * W + c], b = partial[(int64_t)(p + 8) * W + c];
+      const float d = partial[(int64_t)(p + 16) * W + c], e = partial[(int64_t)(p + 24) * W + c];
       acc += a; acc += b; acc += d; acc += e;
     }
-    for (; p < nparts; p += 8) acc += partial[(int64_t)p * 2 * E + c];
+    for (; p < nparts; p += 8) acc += partial[(int64_t)p * W + c];
   }
   sm[warp][lane] = acc;
   __syncthreads();
-  if (warp == 0 && c < 2 * E) {
+  if (warp == 0 && c < W) {
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += sm[w][lane];
-    (c < E ? dgamma : dbeta)[c < E ? c : c - E] = t;
+    if (c < E) dgamma[c] = t;
+    else if (c < 2 * E) dbeta[c - E] = t;
+    else dbias[c - 2 * E] = t;
   }
 }
 
@@ -202,6 +213,52 @@ __device__ __forceinline__ void online_merge(float& m, float& s, float m2, float
   const float mn = fmaxf(m, m2);
   s = s * expf(m - mn) + s2 * expf(m2 - mn);
   m = mn;
+}
+
+// Cross-entropy whose (max, sum exp) come from the vocab-head GEMM's epilogue as one pair per 32 columns: one read of
+// the logits instead of two.  Same merge and the same second phase as xent_kernel.
+__global__ void __launch_bounds__(256) xent_stats_kernel(const float* logits, int64_t ld, const int32_t* __restrict__ y, int V,
+                                                         float inv_rows_scaled, float* dlogits, int64_t ldd,
+                                                         float* __restrict__ row_loss, const float2* __restrict__ rowstat) {
+  __shared__ float sm_m[8], sm_s[8];
+  __shared__ float bc[2];
+  const int64_t row = blockIdx.x;
+  const float* z = logits + row * ld;
+  float* dz = dlogits + row * ldd;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nblk = (V + 31) >> 5;
+  float m = -INFINITY, s = 0.f;
+  for (int k = tid; k < nblk; k += 256) {
+    const float2 st = rowstat[row * nblk + k];
+    if (m > -INFINITY) online_merge(m, s, st.x, st.y); else { m = st.x; s = st.y; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    if (m2 > -INFINITY) { if (m > -INFINITY) online_merge(m, s, m2, s2); else { m = m2; s = s2; } }
+  }
+  if (lane == 0) { sm_m[warp] = m; sm_s[warp] = s; }
+  __syncthreads();
+  if (tid == 0) {
+    float M = sm_m[0], S = sm_s[0];
+    for (int w = 1; w < 8; ++w)
+      if (sm_m[w] > -INFINITY) { if (M > -INFINITY) online_merge(M, S, sm_m[w], sm_s[w]); else { M = sm_m[w]; S = sm_s[w]; } }
+    bc[0] = M; bc[1] = S;
+    const int t = y[row];
+    row_loss[row] = -(z[t] - M - logf(S));
+  }
+  __syncthreads();
+  const float M = bc[0], invS = 1.f / bc[1];
+  const int target = y[row];
+  for (int c = tid * 4; c < V; c += 1024) {                // V % 4 == 0 and 16-B aligned rows (checked by the launcher)
+    const float4 v = *reinterpret_cast<const float4*>(z + c);
+    float4 o;
+    o.x = (expf(v.x - M) * invS - (c + 0 == target ? 1.f : 0.f)) * inv_rows_scaled;
+    o.y = (expf(v.y - M) * invS - (c + 1 == target ? 1.f : 0.f)) * inv_rows_scaled;
+    o.z = (expf(v.z - M) * invS - (c + 2 == target ? 1.f : 0.f)) * inv_rows_scaled;
+    o.w = (expf(v.w - M) * invS - (c + 3 == target ? 1.f : 0.f)) * inv_rows_scaled;
+    *reinterpret_cast<float4*>(dz + c) = o;
+  }
 }
 
 __global__ void __launch_bounds__(256) xent_kernel(const float* logits, int64_t ld,
@@ -454,18 +511,19 @@ int layernorm_forward(cudaStream_t st, int64_t rows, int E, const float* x, cons
   return 0;
 }
 
-size_t layernorm_backward_scratch_floats(int E) { return (size_t)kLnPartials * 2 * E; }
+size_t layernorm_backward_scratch_floats(int E) { return (size_t)kLnPartials * 3 * E; }
 
 int layernorm_backward(cudaStream_t st, int64_t rows, int E, const float* dy, const float* x, const float* mean,
                        const float* rstd, const float* gamma, float* dx, float* dx_dropped,
-                       const DropoutParams* drop, float* dgamma, float* dbeta, float* partial) {
+                       const DropoutParams* drop, float* dgamma, float* dbeta, float* partial, float* dbias) {
   if (rows <= 0) return 0;
   const int grid = (int)std::min<int64_t>(kLnPartials, ceil_div(rows, kLnWarps));
   const int use_drop = (drop != nullptr && drop->p > 0.f && dx_dropped != nullptr) ? 1 : 0;
   DropoutParams dp = drop ? *drop : make_dropout(0.f, 0, 0, 0);
   const bool vec = (E % 128 == 0) && E <= 1024 && aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(gamma) &&
                    (!use_drop || aligned16(dx_dropped));
-  const size_t smem = (size_t)kLnWarps * 2 * E * sizeof(float);
+  const int nsum = dbias != nullptr ? 3 : 2;
+  const size_t smem = (size_t)kLnWarps * nsum * E * sizeof(float);
 #define NLPS_LN_BWD(V)                                                                                         \
   {                                                                                                            \
     static size_t smem_set = 0;                                                                                \
@@ -474,7 +532,7 @@ int layernorm_backward(cudaStream_t st, int64_t rows, int E, const float* dy, co
       smem_set = smem;                                                                                         \
     }                                                                                                          \
     ln_bwd_kernel<V><<<grid, kLnWarps * 32, smem, st>>>(rows, E, dy, x, mean, rstd, gamma, dx, dx_dropped, dp, \
-                                                        use_drop, partial);                                    \
+                                                        use_drop, partial, nsum);                              \
   }
   NLPS_REQUIRE(smem <= 200 * 1024, "layernorm_backward: embed_dim %d too large", E);
   if (!vec) NLPS_LN_BWD(0)
@@ -490,7 +548,7 @@ int layernorm_backward(cudaStream_t st, int64_t rows, int E, const float* dy, co
   }
 #undef NLPS_LN_BWD
   NLPS_LAUNCH_CHECK();
-  ln_bwd_finish_kernel<<<(unsigned)ceil_div(2 * E, 32), 256, 0, st>>>(grid, E, partial, dgamma, dbeta);
+  ln_bwd_finish_kernel<<<(unsigned)ceil_div(nsum * E, 32), 256, 0, st>>>(grid, E, nsum, partial, dgamma, dbeta, dbias);
   NLPS_LAUNCH_CHECK();
   return 0;
 }
@@ -501,6 +559,19 @@ int softmax_xent(cudaStream_t st, const float* logits, int64_t ld, const int32_t
   const int vec_ok = (V % 4 == 0 && ld % 4 == 0 && ldd % 4 == 0 && aligned16(logits) && aligned16(dlogits)) ? 1 : 0;
   const float inv = (float)((double)grad_scale / (double)rows);
   xent_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, ld, y, V, inv, dlogits, ldd, row_loss, vec_ok);
+  NLPS_LAUNCH_CHECK();
+  sum_to_scalar_kernel<<<1, 1024, 0, st>>>(row_loss, rows, (float)(1.0 / (double)rows), loss);
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+
+int softmax_xent_stats(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
+                       float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss, const float2* rowstat) {
+  const bool vec_ok = V % 4 == 0 && ld % 4 == 0 && ldd % 4 == 0 && aligned16(logits) && aligned16(dlogits);
+  if (rowstat == nullptr || !vec_ok) return softmax_xent(st, logits, ld, y, rows, V, grad_scale, loss, dlogits, ldd, row_loss);
+  NLPS_REQUIRE(rows > 0 && V > 0, "softmax_xent: empty input");
+  const float inv = (float)((double)grad_scale / (double)rows);
+  xent_stats_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, ld, y, V, inv, dlogits, ldd, row_loss, rowstat);
   NLPS_LAUNCH_CHECK();
   sum_to_scalar_kernel<<<1, 1024, 0, st>>>(row_loss, rows, (float)(1.0 / (double)rows), loss);
   NLPS_LAUNCH_CHECK();

@@ -381,3 +381,29 @@ def test_device_resident_train_loop_learns_and_matches_oracle_loop():
             last_token_step(oracle, xs[i:i + 16], ys[i:i + 16], lr=3e-3, clip=1.0)
     assert np.allclose(evals, want, rtol=2e-3, atol=2e-3), (evals, want)
     m.close()
+
+
+@pytest.mark.gpu
+def test_fused_ce_statistics_variant_matches_default():
+    """NLPS_FUSE_CE=1 (softmax statistics from the vocab-head GEMM epilogue) gives the same training
+    trajectory as the default two-pass loss; run in a subprocess because the switch is read once per process."""
+    import subprocess, sys, os, json
+    code = r"""
+import json, sys, numpy as np
+sys.path.insert(0, %r)
+from nlpscratch_b200 import Transformer
+np.random.seed(3)
+m = Transformer(512, 256, 4, 512, 2, 160, dropout_p=0.0, precision="tf32")
+rng = np.random.default_rng(0)
+x = rng.integers(1, 512, (4, 160)).astype(np.int32); x[1, 100:] = 0
+y = rng.integers(0, 512, (4, 160)).astype(np.int32)
+print(json.dumps([float(m.train_step(x, y, learning_rate=1e-3, clip_grad_norm=1.0)) for _ in range(3)]))
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, NLPS_FUSE_CE=flag)
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        out[flag] = json.loads(res.stdout.strip().splitlines()[-1])
+    for a, b in zip(out["0"], out["1"]):
+        assert abs(a - b) < 2e-5 * max(1.0, abs(a)), (out["0"], out["1"])
