@@ -51,7 +51,8 @@ struct KernelArgs {
   int64_t ws_ld;
   int vec_ok;           // float4 epilogue allowed (alignment of C / residual / gate / N)
   int direct_ok;        // 32-B aligned output/fused operands: epilogue stores rows straight from registers
-  int debug;            // NLPS_GEMM_DEBUG bits: 1 = skip global stores, 2 = skip the whole epilogue body
+  int debug;            // NLPS_GEMM_DEBUG bits: 1 = skip global stores, 2 = skip the whole epilogue body, 4 = .release.cluster
+                        // TMEM-buffer hand-over, 8 = releasing cluster barrier at the end (the two pre-fix forms, for A/B)
 };
 
 // ---- epilogue store of one 32x32 fp32 block, coalesced ---------------------------------
@@ -599,7 +600,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
         if (c == c_end - 1) {
           tc_fence_before();
-          if (lane == 0) mbar_arrive_cluster(lead_tempty);
+          if (lane == 0) { if (ka.debug & 4) mbar_arrive_cluster_release(lead_tempty); else mbar_arrive_cluster(lead_tempty); }
         }
         if (ka.direct_ok && (m0 + q * 32 + 32 <= g.M) && (n0 + c * 32 + 32 <= g.N)) {      // warp-uniform
           if (!(ka.debug & 1)) store_row_direct(ka, v, m0 + q * 32 + lane, n0 + c * 32, split);
@@ -616,12 +617,12 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
       if (c_end <= c_begin) {
         tc_fence_before();
-        if (lane == 0) mbar_arrive_cluster(lead_tempty);
+        if (lane == 0) { if (ka.debug & 4) mbar_arrive_cluster_release(lead_tempty); else mbar_arrive_cluster(lead_tempty); }
       }
     }
   }
   tc_fence_before();
-  cluster_sync_all();                      // nobody leaves while the peer may still touch its smem / TMEM
+  if (ka.debug & 8) cluster_sync_all(); else cluster_sync_relaxed();   // nobody leaves while the peer may still touch its smem / TMEM
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);

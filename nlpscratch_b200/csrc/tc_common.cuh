@@ -96,6 +96,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// execution-only rendezvous (no memory ordering): the .release form would add MEMBAR.ALL.GPU and wait for every
+// outstanding global store of the CTA before it may leave
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 // address of the same smem offset in CTA `rank` of the cluster (shared::cluster window)
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
   uint32_t r;
@@ -108,6 +114,10 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
 // tcgen05.fence::before_thread_sync; the default (.release at CTA scope) is what CUTLASS's ClusterBarrier uses.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// the .release.cluster form, kept only for A/B measurements (NLPS_GEMM_DEBUG bit 4)
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's smem, completing the transaction on the (leader's) mbarrier `bar_cluster`
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
