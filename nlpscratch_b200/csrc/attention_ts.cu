@@ -29,6 +29,7 @@ using namespace tc;
 
 constexpr int kThreads = 448;   // warp0 TMA + lse/delta staging, warp1 MMA + TMEM owner, warps 2-9 softmax, warps 10-13 re-swizzle
 constexpr int kSwzWarps = 4;
+constexpr int kPsThreads = 480;  // persistent backward kernels: + warp 14, a second MMA issuer (see attn_bwd_dkdv_ps)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kTraceSlots = 4096;
 
@@ -835,7 +836,7 @@ __device__ __forceinline__ void put_row_sw128(uint8_t* atom, int r, const uint32
 }
 
 template <int D>
-__global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_constant__ CUtensorMap map_res,   // qkv, box {32,128}, K-major
+__global__ void __launch_bounds__(kPsThreads, 1) attn_bwd_dkdv_ps(const __grid_constant__ CUtensorMap map_res,   // qkv, box {32,128}, K-major
                                                               const __grid_constant__ CUtensorMap map_qk,    // qkv, box {32,64}, K-major
                                                               const __grid_constant__ CUtensorMap map_dok,   // dctx, box {32,64}, K-major
                                                               const __grid_constant__ CUtensorMap map_out,   // dqkv as (3E, S, B), box {32,128,1}
@@ -865,6 +866,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
   auto pds_full = [&](int b2) { return bar + 8u * (18 + b2); };
   auto ld_full = [&](int b2) { return bar + 8u * (20 + b2); };
   const uint32_t kv_full = bar + 8u * 22, kv_done = bar + 8u * 23, acc_full = bar + 8u * 24, st_done = bar + 8u * 25, tmem_slot = bar + 8u * 26;
+  auto sfree = [&](int b2) { return bar + 8u * (27 + b2); };
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ctl_ptr + 8 * 26);
   float* lse_s = reinterpret_cast<float*>(ctl_ptr + 256);     // [2][64]  -lse*log2e
   float* delta_s = lse_s + 128;                               // [2][64]  -delta
@@ -903,6 +905,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
     for (int s = 0; s < NSM; ++s) { mbar_init(mfull(s), kSwzWarps); mbar_init(mfree(s), 1); }
     for (int b2 = 0; b2 < 2; ++b2) { mbar_init(sdp_full(b2), 1); mbar_init(pds_full(b2), 256); mbar_init(ld_full(b2), 32); }
     mbar_init(kv_full, 1); mbar_init(kv_done, 256); mbar_init(acc_full, 1); mbar_init(st_done, 1);
+    mbar_init(sfree(0), 1); mbar_init(sfree(1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
@@ -1000,18 +1003,21 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
     // the CTA that draws the last "none left" puts the counters back for the next launch
     if (lane == 0 && atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
+    // ---------------- MMA issuer A: S^T = K Q^T ; dP^T = V dO^T (A = K / V in TMEM) ----------------
+    // Two issuing warps: with one, the products of block it+2 queued behind the wait for the threads of block it and
+    // ~800 clk of every block were lost to that serialisation.  Issue order across the two warps is not program order,
+    // so the reuse of an S^T/dP^T buffer is guarded by completion: warp B commits sfree(b2) behind its products.
     constexpr uint32_t idesc_t = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    constexpr uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int g0 = 0;
+    int g = 0;
     for (int i = 0;; ++i) {
       mbar_wait(kv_full, (uint32_t)(i & 1));                   // (acquire) ring entry of tile i
       if (meta_s[(i & 3) * 4] < 0) break;
       mbar_wait(kv_done, (uint32_t)(i & 1));                   // K and V of this tile are in TMEM
       tc_fence_after();
       const int n_it = meta_s[(i & 3) * 4 + 1];
-      auto issue_sdp = [&](int it) {        // S^T = K Q^T ; dP^T = V dO^T   (A = K / V in TMEM)
-        const int g = g0 + it, s = g % NSK, b2 = g & 1;
+      for (int it = 0; it < n_it; ++it, ++g) {
+        const int s = g % NSK, b2 = g & 1;
+        if (g >= 2) mbar_wait(sfree(b2), (uint32_t)(((g >> 1) - 1) & 1));   // dV / dK products of block g-2 have retired
         mbar_wait(kfull(s), (uint32_t)((g / NSK) & 1));
         tc_fence_after();
         if (elect_one_sync()) {
@@ -1026,29 +1032,35 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkdv_ps(const __grid_con
           umma_commit(kfree(s));
         }
         __syncwarp();
-      };
-      issue_sdp(0);
-      if (n_it > 1) issue_sdp(1);
-      for (int it = 0; it < n_it; ++it) {
-        const int g = g0 + it, s = g % NSM, b2 = g & 1;
+      }
+    }
+  } else if (warp == 14) {
+    // ---------------- MMA issuer B: dV += P^T dO ; dK += dS^T Q (A = P^T / dS^T in TMEM, K = 64 queries) ----------------
+    constexpr uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int g = 0;
+    for (int i = 0;; ++i) {
+      mbar_wait(kv_full, (uint32_t)(i & 1));
+      if (meta_s[(i & 3) * 4] < 0) break;
+      const int n_it = meta_s[(i & 3) * 4 + 1];
+      for (int it = 0; it < n_it; ++it, ++g) {
+        const int s = g % NSM, b2 = g & 1;
         mbar_wait(mfull(s), (uint32_t)((g / NSM) & 1));
         mbar_wait(pds_full(b2), (uint32_t)((g >> 1) & 1));
         tc_fence_after();
         if (elect_one_sync()) {
           const uint64_t qmn = make_desc(mst + s * C::kStage, 64 * 128, 512, 1), domn = make_desc(mst + s * C::kStage + C::kBlk, 64 * 128, 512, 1);
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {      // dV += P^T dO ; dK += dS^T Q   (K = 64 queries, A = P^T / dS^T in TMEM)
+          for (int kk = 0; kk < 8; ++kk) {
             const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
             umma_tf32_ts(t_dv, t_st + b2 * 64 + kk * 8, domn + (uint64_t)(kk * 64), idesc_a, acc);
             umma_tf32_ts(t_dk, t_dpt + b2 * 64 + kk * 8, qmn + (uint64_t)(kk * 64), idesc_a, acc);
           }
           umma_commit(mfree(s));
+          umma_commit(sfree(b2));
           if (it == n_it - 1) umma_commit(acc_full);
         }
         __syncwarp();
-        if (it + 2 < n_it) issue_sdp(it + 2);
       }
-      g0 += n_it;
     }
   } else if (warp >= 10) {
     // ---------------- re-swizzle warps ----------------
@@ -1236,7 +1248,7 @@ struct PsDqCfg {
 };
 
 template <int D>
-__global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_constant__ CUtensorMap map_qres,   // qkv, box {32,128}, K-major
+__global__ void __launch_bounds__(kPsThreads, 1) attn_bwd_dq_ps(const __grid_constant__ CUtensorMap map_qres,   // qkv, box {32,128}, K-major
                                                             const __grid_constant__ CUtensorMap map_dores,  // dctx, box {32,128}, K-major
                                                             const __grid_constant__ CUtensorMap map_kk,     // qkv, box {32,64}, K-major
                                                             const __grid_constant__ CUtensorMap map_out,    // dqkv as (3E, S, B), box {32,128,1}
@@ -1264,6 +1276,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
   auto sdp_full = [&](int b2) { return bar + 8u * (16 + b2); };
   auto ds_full = [&](int b2) { return bar + 8u * (18 + b2); };
   const uint32_t res_full = bar + 8u * 22, res_done = bar + 8u * 23, acc_full = bar + 8u * 24, st_done = bar + 8u * 25, tmem_slot = bar + 8u * 26;
+  auto sfree = [&](int b2) { return bar + 8u * (27 + b2); };
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ctl_ptr + 8 * 26);
   uint32_t* pad32 = reinterpret_cast<uint32_t*>(ctl_ptr + 256);             // [2][128] words: 32 keys each
   volatile int* meta_s = reinterpret_cast<volatile int*>(ctl_ptr + 256 + 1024);   // ring of 4 x {block count, first_real}
@@ -1294,6 +1307,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
     for (int s = 0; s < NSM; ++s) { mbar_init(mfull(s), kSwzWarps); mbar_init(mfree(s), 1); }
     for (int b2 = 0; b2 < 2; ++b2) { mbar_init(sdp_full(b2), 1); mbar_init(ds_full(b2), 256); }
     mbar_init(res_full, 1); mbar_init(res_done, 256); mbar_init(acc_full, 1); mbar_init(st_done, 1);
+    mbar_init(sfree(0), 1); mbar_init(sfree(1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
@@ -1358,18 +1372,18 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
+    // ---------------- MMA issuer A: S = Q K^T ; dP = dO V^T (A = Q / dO in TMEM); see attn_bwd_dkdv_ps ----------------
     constexpr uint32_t idesc_t = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    constexpr uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int g0 = 0;
+    int g = 0;
     for (int i = 0;; ++i) {
       mbar_wait(res_full, (uint32_t)(i & 1));                  // (acquire) ring entry of tile i
       if (meta_s[(i & 3) * 4] < 0) break;
       mbar_wait(res_done, (uint32_t)(i & 1));                  // Q and dO of this tile are in TMEM
       tc_fence_after();
       const int n_kv = meta_s[(i & 3) * 4 + 1];
-      auto issue_sdp = [&](int kb) {        // S = Q K^T ; dP = dO V^T   (A = Q / dO in TMEM)
-        const int g = g0 + kb, s = g % NSK, b2 = g & 1;
+      for (int kb = 0; kb < n_kv; ++kb, ++g) {
+        const int s = g % NSK, b2 = g & 1;
+        if (g >= 2) mbar_wait(sfree(b2), (uint32_t)(((g >> 1) - 1) & 1));   // the dQ product of block g-2 has retired
         mbar_wait(kfull(s), (uint32_t)((g / NSK) & 1));
         tc_fence_after();
         if (elect_one_sync()) {
@@ -1384,26 +1398,32 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_ps(const __grid_const
           umma_commit(kfree(s));
         }
         __syncwarp();
-      };
-      issue_sdp(0);
-      if (n_kv > 1) issue_sdp(1);
-      for (int kb = 0; kb < n_kv; ++kb) {
-        const int g = g0 + kb, s = g % NSM, b2 = g & 1;
+      }
+    }
+  } else if (warp == 14) {
+    // ---------------- MMA issuer B: dQ += dS K (A = dS in TMEM, K = 64 keys) ----------------
+    constexpr uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int g = 0;
+    for (int i = 0;; ++i) {
+      mbar_wait(res_full, (uint32_t)(i & 1));
+      if (meta_s[(i & 3) * 4] < 0) break;
+      const int n_kv = meta_s[(i & 3) * 4 + 1];
+      for (int kb = 0; kb < n_kv; ++kb, ++g) {
+        const int s = g % NSM, b2 = g & 1;
         mbar_wait(mfull(s), (uint32_t)((g / NSM) & 1));
         mbar_wait(ds_full(b2), (uint32_t)((g >> 1) & 1));
         tc_fence_after();
         if (elect_one_sync()) {
           const uint64_t kmn = make_desc(mst + s * C::kBlk, 64 * 128, 512, 1);
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)        // dQ += dS K   (K = 64 keys, A = dS in TMEM)
+          for (int kk = 0; kk < 8; ++kk)
             umma_tf32_ts(t_dq, t_dp + b2 * 64 + kk * 8, kmn + (uint64_t)(kk * 64), idesc_a, (kb > 0 || kk > 0) ? 1u : 0u);
           umma_commit(mfree(s));
+          umma_commit(sfree(b2));
           if (kb == n_kv - 1) umma_commit(acc_full);
         }
         __syncwarp();
-        if (kb + 2 < n_kv) issue_sdp(kb + 2);
       }
-      g0 += n_kv;
     }
   } else if (warp >= 10) {
     // ---------------- re-swizzle warps: MN-major image of the landed K tile ----------------
@@ -1632,7 +1652,7 @@ int launch_bwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int
     NLPS_TRY(make_map3(&out3, dqkv, 3 * (uint64_t)E, (uint64_t)S, (uint64_t)B, 3 * (int64_t)E, (int64_t)S * 3 * E, 32, 128));
     int* sched = nullptr;
     NLPS_TRY(sched_counters(st, 0, &sched));
-    attn_bwd_dkdv_ps<D><<<(unsigned)std::min<int64_t>(n_tiles, kNumSMs), kThreads, PsCfg<D>::kSmemDkdv, st>>>(
+    attn_bwd_dkdv_ps<D><<<(unsigned)std::min<int64_t>(n_tiles, kNumSMs), kPsThreads, PsCfg<D>::kSmemDkdv, st>>>(
         res, qk, dok, out3, p, (int)n_tiles, sched, x, fnp, lse, delta, dqkv);
     if (trace_on) {
       static int printed_ps = 0;
@@ -1662,7 +1682,7 @@ int launch_bwd(cudaStream_t st, int B, int S, int h, const float* qkv, const int
     NLPS_TRY(make_map3(&out3, dqkv, 3 * (uint64_t)E, (uint64_t)S, (uint64_t)B, 3 * (int64_t)E, (int64_t)S * 3 * E, 32, 128));
     int* sched = nullptr;
     NLPS_TRY(sched_counters(st, 1, &sched));
-    attn_bwd_dq_ps<D><<<(unsigned)std::min<int64_t>(n_tiles, kNumSMs), kThreads, PsDqCfg<D>::kSmem, st>>>(
+    attn_bwd_dq_ps<D><<<(unsigned)std::min<int64_t>(n_tiles, kNumSMs), kPsThreads, PsDqCfg<D>::kSmem, st>>>(
         res, dores, qk, out3, p, (int)n_tiles, sched, x, fnp, lse, delta);
   } else {
     attn_bwd_dq_ts<D, NS><<<grid, kThreads, C::kSmemDq, st>>>(res, dores, qk, qmn, p, x, fnp, lse, delta, dqkv);

@@ -279,7 +279,9 @@ def test_baseline_model_size_tf32_agrees_with_fp32():
 @pytest.mark.parametrize("cfg,B,S", [((13, 6, 2, 10, 1, 5), 1, 1),        # head_dim 3, nothing 4-aligned, S = B = 1
                                      ((31, 12, 3, 18, 2, 9), 2, 9),       # head_dim 4, ff not a multiple of 4
                                      ((64, 40, 5, 100, 1, 70), 3, 70),    # head_dim 8, S > one attention tile
-                                     ((257, 96, 3, 200, 2, 33), 2, 33)])  # head_dim 32 (tcgen05 attention), odd vocab
+                                     ((257, 96, 3, 200, 2, 33), 2, 33),   # head_dim 32 (tcgen05 attention), odd vocab
+                                     # CTA-pair GEMMs with ragged row blocks (210 rows): db1 from the dz epilogue's partials
+                                     ((300, 160, 5, 288, 1, 70), 3, 70)])
 def test_odd_shapes_against_oracle(cfg, B, S, precision):
     """Ragged / unaligned dimensions: whatever mix of tensor-core and CUDA-core kernels the shapes
     allow must still match the oracle (the reference accepts any embed_dim % num_heads == 0)."""
