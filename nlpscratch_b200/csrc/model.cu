@@ -816,6 +816,7 @@ int nlps_attention_forward(void* stream, int precision, int B, int S, int h, int
                            float* ctx, float* lse) {
   int32_t* fnp = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
+  ensure_mempool_config();            // keep the scratch cached: a trip to the driver per call stalls the stream
   NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&fnp), sizeof(int32_t) * B, st));
   NLPS_TRY(first_nonpad(st, B, S, x, fnp));
   const int rc = attention_forward(st, precision, B, S, h, d, qkv, x, fnp, ctx, lse);
@@ -828,6 +829,7 @@ int nlps_attention_backward(void* stream, int precision, int B, int S, int h, in
   cudaStream_t st = (cudaStream_t)stream;
   char* buf = nullptr;
   const size_t nd = sizeof(float) * (size_t)B * h * S;
+  ensure_mempool_config();
   NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&buf), nd + sizeof(int32_t) * B, st));
   float* delta = reinterpret_cast<float*>(buf);
   int32_t* fnp = reinterpret_cast<int32_t*>(buf + nd);
@@ -846,6 +848,7 @@ int nlps_layernorm_backward(void* stream, int64_t rows, int E, const float* dy, 
                             const float* rstd, const float* gamma, float* dx, float* dgamma, float* dbeta) {
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = nullptr;
+  ensure_mempool_config();
   NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partial), sizeof(float) * layernorm_backward_scratch_floats(E), st));
   const int rc = layernorm_backward(st, rows, E, dy, x, mean, rstd, gamma, dx, nullptr, nullptr, dgamma, dbeta, partial);
   NLPS_CUDA(cudaFreeAsync(partial, st));
@@ -860,6 +863,7 @@ int nlps_embed_forward(void* stream, int B, int S, int E, int V, const int32_t* 
 int nlps_embed_backward(void* stream, int64_t N, int E, int V, const int32_t* x_flat, const float* dh, float* dWe) {
   cudaStream_t st = (cudaStream_t)stream;
   int32_t* scratch = nullptr;
+  ensure_mempool_config();
   NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), sizeof(int32_t) * embed_backward_scratch_ints(N, V), st));
   const int rc = embed_backward(st, N, E, V, x_flat, dh, dWe, scratch);
   NLPS_CUDA(cudaFreeAsync(scratch, st));
@@ -869,6 +873,7 @@ int nlps_embed_backward(void* stream, int64_t N, int E, int V, const int32_t* x_
 int nlps_colsum(void* stream, int64_t rows, int cols, const float* x, int64_t ld, float* out) {
   cudaStream_t st = (cudaStream_t)stream;
   float* scratch = nullptr;
+  ensure_mempool_config();
   NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), sizeof(float) * colsum_scratch_floats(cols), st));
   const int rc = colsum(st, rows, cols, x, ld, out, scratch);
   NLPS_CUDA(cudaFreeAsync(scratch, st));
@@ -878,6 +883,7 @@ int nlps_colsum(void* stream, int64_t rows, int cols, const float* x, int64_t ld
 int nlps_sumsq(void* stream, int64_t n, const float* x, float* out) {
   cudaStream_t st = (cudaStream_t)stream;
   float* scratch = nullptr;
+  ensure_mempool_config();
   NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), sizeof(float) * sumsq_scratch_floats(), st));
   const int rc = sumsq(st, n, x, out, scratch);
   NLPS_CUDA(cudaFreeAsync(scratch, st));
