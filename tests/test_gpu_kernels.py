@@ -113,6 +113,33 @@ def test_attention_forward_backward(B, S, h, d, pad, prec):
     assert rel_err(dqkv.get(), want) < tol_b
 
 
+def test_attention_tensor_core_path_is_bitwise_deterministic_across_launches_and_shapes():
+    """The persistent attention kernels draw their tiles from a global counter, so which CTA computes which tile
+    differs from launch to launch -- the results must not (one owner per output, fixed summation order), and the
+    self-resetting counters must survive launches of other shapes on the same stream."""
+    PREC = C.c_int(_lib.PREC["tf32"])
+
+    def run(B, S, h, d, seed):
+        qkv, x = _attention_case(B, S, h, d, "tail", seed)
+        E = h * d
+        QKV, X = dev(qkv), dev(x)
+        ctx, lse = DeviceArray.empty((B, S, E)), DeviceArray.empty((B, h, S))
+        _lib.call("nlps_attention_forward", S0, PREC, C.c_int(B), C.c_int(S), C.c_int(h), C.c_int(d),
+                  _lib.vp(QKV.ptr), _lib.vp(X.ptr), _lib.vp(ctx.ptr), _lib.vp(lse.ptr))
+        DC = dev(np.random.default_rng(seed + 1).standard_normal((B, S, E)).astype(np.float32))
+        dqkv = DeviceArray.empty((B, S, 3 * E))
+        _lib.call("nlps_attention_backward", S0, PREC, C.c_int(B), C.c_int(S), C.c_int(h), C.c_int(d),
+                  _lib.vp(QKV.ptr), _lib.vp(X.ptr), _lib.vp(ctx.ptr), _lib.vp(lse.ptr), _lib.vp(DC.ptr), _lib.vp(dqkv.ptr))
+        return ctx.get().copy(), lse.get().copy(), dqkv.get().copy()
+
+    first = run(24, 300, 4, 64, 5)          # 288 tiles: several per persistent CTA
+    run(3, 77, 2, 32, 6)                    # other shapes in between
+    run(40, 130, 4, 32, 7)
+    again = run(24, 300, 4, 64, 5)
+    for a, b in zip(first, again):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("rows,E", [(1, 8), (7, 32), (33, 64), (19, 128), (50, 256), (9, 512), (5, 100)])
 def test_layernorm_forward_backward(rows, E):
     rng = np.random.default_rng(rows + E)
