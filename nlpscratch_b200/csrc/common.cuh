@@ -15,6 +15,8 @@ const char* get_error();
 void count_launch(int n = 1);         // every kernel launch of ours goes through this counter
 long long launch_count(bool reset);
 void ensure_mempool_config();
+unsigned long long alloc_epoch();      // see util.cu: invalidates captured CUDA graphs after a re-allocation
+void bump_alloc_epoch();
 
 #define NLPS_CUDA(expr)                                                                   \
   do {                                                                                    \
@@ -89,12 +91,16 @@ struct DropoutParams {
   uint32_t seed_lo, seed_hi;
   uint32_t stream;     // (layer*2 + which)
   uint32_t step;       // forward-call counter so that every step draws fresh masks
+  // when set, the counter is read from device memory instead: the value is then not baked into the launch parameters
+  // and a captured CUDA graph of the step can be replayed with a new counter
+  const uint32_t* step_ptr;
 };
 
 // One Philox4x32-10 call yields the keep decisions of 8 consecutive elements (16 random bits each):
 // element idx uses call idx>>3, 16-bit field idx&7.  Inverted dropout, transformer.py:102-108.
 __device__ __forceinline__ uint4 dropout_rand8(const DropoutParams& d, uint64_t idx8) {
-  return philox4x32((uint32_t)idx8, (uint32_t)(idx8 >> 32), d.stream, d.step, d.seed_lo, d.seed_hi);
+  const uint32_t step = d.step_ptr != nullptr ? __ldg(d.step_ptr) : d.step;
+  return philox4x32((uint32_t)idx8, (uint32_t)(idx8 >> 32), d.stream, step, d.seed_lo, d.seed_hi);
 }
 __device__ __forceinline__ bool dropout_keep(const DropoutParams& d, const uint4& r, int field) {
   const uint32_t w = (field >> 1) == 0 ? r.x : (field >> 1) == 1 ? r.y : (field >> 1) == 2 ? r.z : r.w;
@@ -114,7 +120,7 @@ __device__ __forceinline__ void dropout_four(const DropoutParams& d, uint64_t id
   v.w = (w1 >> 16) < d.threshold ? v.w * d.inv_keep : 0.f;
 }
 
-inline DropoutParams make_dropout(float p, uint64_t seed, uint32_t stream, uint32_t step) {
+inline DropoutParams make_dropout(float p, uint64_t seed, uint32_t stream, uint32_t step, const uint32_t* step_ptr = nullptr) {
   DropoutParams d{};
   d.p = p;
   if (p > 0.f) {
@@ -130,6 +136,7 @@ inline DropoutParams make_dropout(float p, uint64_t seed, uint32_t stream, uint3
   d.seed_hi = (uint32_t)(seed >> 32);
   d.stream = stream;
   d.step = step;
+  d.step_ptr = step_ptr;
   return d;
 }
 
@@ -145,7 +152,7 @@ struct GemmArgs {
   // bit-packed ReLU mask, one uint32 per (row, 32 columns): written by the ReLU GEMM, read by its
   // backward instead of the float gate (tensor-core path only; needs N % 32 == 0)
   uint32_t* relu_bits_out = nullptr; const uint32_t* gate_bits = nullptr; int64_t ld_bits = 0;
-  DropoutParams drop = {0.f, 1.f, 65536u, 0, 0, 0, 0};        // then inverted dropout
+  DropoutParams drop = {0.f, 1.f, 65536u, 0, 0, 0, 0, nullptr};   // then inverted dropout
   const float* residual = nullptr; int64_t ldr = 0;   // then += residual
   bool accumulate = false;          // finally C += result instead of C = result
   // optional by-product (tensor-core CTA-pair kernel only, see gemm_tf32_colsum_fusable): per 32-row block column sums of
@@ -244,8 +251,10 @@ int clip_scale_from_sumsq(cudaStream_t st, const float* sumsq, float max_norm, f
 int scale_inplace(cudaStream_t st, int64_t n, float* x, const float* scale_dev);
 int adam_update(cudaStream_t st, int64_t n, float* p, const float* g, float* m, float* v, float lr,
                 float b1, float b2, float one_minus_b1, float one_minus_b2, float eps, float bc1, float bc2,
-                const float* clip_scale_dev);
-int sgd_update(cudaStream_t st, int64_t n, float* p, const float* g, float lr, const float* clip_scale_dev);
+                const float* clip_scale_dev,
+                const float* hyper_dev = nullptr);   // {lr, bc1, bc2} on the device override the by-value arguments
+int sgd_update(cudaStream_t st, int64_t n, float* p, const float* g, float lr, const float* clip_scale_dev,
+               const float* hyper_dev = nullptr);
 
 }  // namespace nlps
 

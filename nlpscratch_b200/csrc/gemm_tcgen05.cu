@@ -707,6 +707,7 @@ int splitk_workspace(cudaStream_t st, size_t bytes, float** out) {
   if (w.bytes < bytes) {
     NLPS_CUDA(cudaStreamSynchronize(st));
     if (w.ptr) NLPS_CUDA(cudaFree(w.ptr));
+    bump_alloc_epoch();
     w.ptr = nullptr; w.bytes = 0;
     const size_t want = std::max(bytes, (size_t)64 << 20);
     NLPS_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.ptr), want));

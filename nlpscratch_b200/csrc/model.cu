@@ -42,6 +42,7 @@ struct nlps_cache {
   struct L { float *qkv, *ctx, *lse, *r1, *mean1, *rstd1, *y1, *hid, *r2, *mean2, *rstd2, *y2; uint32_t* relu_bits; };
   std::vector<L> layers;
   float* logits = nullptr;
+  uint32_t* dev_step = nullptr;       // drop_step on the device: what the kernels of this cache read (graph-replayable)
   float2* rowstat = nullptr;          // [N][ceil(V/32)] softmax statistics left by the vocab-head GEMM epilogue
   bool rowstat_valid = false;
   float drop_p = 0.f;       // dropout probability in effect during this forward
@@ -86,9 +87,35 @@ struct nlps_model {
   int32_t* err_flag = nullptr;
 
   std::vector<nlps_cache*> pool;
+
+  // ---- CUDA graph of the fused full-sequence step (nlps_train_step) ----
+  // One graph per (cache, x, y, clip, scale, mode) signature; the only node whose parameters change from step to step is
+  // the setter that publishes the step's scalars (dropout counter, lr, Adam bias corrections) to device memory.
+  struct StepGraph {
+    const nlps_cache* cache; const int32_t* x; int64_t xs; const int32_t* y;
+    float max_norm, grad_scale, dropout_p; int precision; bool training;
+    unsigned long long epoch;
+    int state;                         // 1 = signature seen once (ran eagerly), 2 = captured, 3 = not capturable
+    cudaGraphExec_t exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphNode_t setter = nullptr;
+    long long launches = 0;
+    bool relu_bits_valid = false;
+  };
+  std::vector<StepGraph> graphs;
+  cudaStream_t own_stream = nullptr;   // created when the model would otherwise run on the legacy default stream
+  float* hyper = nullptr;              // device {lr, bc1, bc2}
+  bool in_graph_body = false;          // the per-call setters are replaced by the one setter node
+  int graph_mode = -1;
 };
 
 namespace {
+
+// the step's scalars on the device: every other kernel of the step reads them from there
+__global__ void set_step_scalars_kernel(uint32_t* step_slot, uint32_t step, float* hyper, float lr, float bc1, float bc2) {
+  if (step_slot != nullptr) *step_slot = step;
+  if (hyper != nullptr) { hyper[0] = lr; hyper[1] = bc1; hyper[2] = bc2; }
+}
 
 inline int64_t take(int64_t& cursor, int64_t n) {
   const int64_t at = cursor;
@@ -134,6 +161,7 @@ int ensure_workspace(nlps_model* m, int B, int S) {
   NLPS_CUDA(cudaStreamSynchronize(m->stream));
   float** bufs[] = {&m->g0, &m->g1, &m->gdrop, &m->dctx, &m->dqkv, &m->dhid, &m->delta, &m->row_loss, &m->colsum32};
   for (float** b : bufs) { if (*b) cudaFree(*b); *b = nullptr; }
+  bump_alloc_epoch();
   if (m->iscratch) { cudaFree(m->iscratch); m->iscratch = nullptr; }
   const int64_t E = m->E, F = m->F;
   NLPS_CUDA(cudaMalloc(&m->g0, sizeof(float) * N * E));
@@ -154,6 +182,7 @@ int ensure_rows_tmp(nlps_model* m, int64_t floats) {
   if (floats <= m->rows_tmp_cap) return 0;
   NLPS_CUDA(cudaStreamSynchronize(m->stream));
   if (m->rows_tmp) cudaFree(m->rows_tmp);
+  bump_alloc_epoch();
   m->rows_tmp = nullptr;
   NLPS_CUDA(cudaMalloc(&m->rows_tmp, sizeof(float) * floats));
   m->rows_tmp_cap = floats;
@@ -167,12 +196,26 @@ GemmArgs gemm_nn(int M, int N, int K, const float* A, int64_t lda, const float* 
 }
 
 DropoutParams drop_for(const nlps_model* m, const nlps_cache* c, int layer, int which) {
-  return make_dropout(c->drop_p, m->seed, (uint32_t)(layer * 2 + which), c->drop_step);
+  return make_dropout(c->drop_p, m->seed, (uint32_t)(layer * 2 + which), c->drop_step, c->dev_step);
 }
 
 inline unsigned int* colsum_tickets_for(nlps_model* m, int64_t cols) { return ceil_div(cols, 128) <= 4096 ? m->colsum_tickets : nullptr; }
 
+void drop_step_graphs(nlps_model* m) {
+  for (auto& g : m->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+  }
+  m->graphs.clear();
+}
+
+inline void adam_bias_corrections(int64_t t, float* bc1, float* bc2) {
+  *bc1 = (float)(1.0 - std::pow(0.9, (double)t));
+  *bc2 = (float)(1.0 - std::pow(0.999, (double)t));
+}
+
 int record_bucket(nlps_model* m, int bucket) {
+  if (m->in_graph_body) return 0;      // nobody waits on the bucket events of a single-GPU captured step
   NLPS_CUDA(cudaEventRecord(m->bucket_ev[bucket], m->stream));
   return 0;
 }
@@ -379,10 +422,22 @@ int nlps_create(const nlps_config* cfg, int device, nlps_model** out) {
   NLPS_CUDA(cudaMalloc(&m->colsum_tickets, sizeof(unsigned int) * 4096));
   NLPS_CUDA(cudaMemset(m->colsum_tickets, 0, sizeof(unsigned int) * 4096));
   NLPS_CUDA(cudaMalloc(&m->sumsq_scratch, sizeof(float) * sumsq_scratch_floats()));
+  NLPS_CUDA(cudaMalloc(&m->hyper, sizeof(float) * 4));
+  NLPS_CUDA(cudaMemset(m->hyper, 0, sizeof(float) * 4));
   NLPS_CUDA(cudaMalloc(&m->scalars, sizeof(float) * 16));
   NLPS_CUDA(cudaMemset(m->scalars, 0, sizeof(float) * 16));
   NLPS_CUDA(cudaMalloc(&m->err_flag, sizeof(int32_t)));
   NLPS_CUDA(cudaMemset(m->err_flag, 0, sizeof(int32_t)));
+  {
+    // NLPS_GRAPH=0 disables CUDA graphs.  Stream capture is impossible on the legacy default stream, so the model then
+    // gets a stream of its own -- a BLOCKING one: it stays ordered with everything the caller does on stream 0.
+    const char* e = getenv("NLPS_GRAPH");
+    m->graph_mode = (e && e[0] == '0') ? 0 : 1;
+    if (m->graph_mode) {
+      NLPS_CUDA(cudaStreamCreate(&m->own_stream));
+      m->stream = m->own_stream;
+    }
+  }
   m->bucket_ev.resize(m->buckets.size());
   for (auto& e : m->bucket_ev) NLPS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   NLPS_CUDA(cudaEventCreateWithFlags(&m->aux_ev, cudaEventDisableTiming));
@@ -401,13 +456,22 @@ int nlps_destroy(nlps_model* m) {
   if (m->iscratch) cudaFree(m->iscratch);
   if (m->err_flag) cudaFree(m->err_flag);
   if (m->colsum_tickets) cudaFree(m->colsum_tickets);
+  if (m->hyper) cudaFree(m->hyper);
+  drop_step_graphs(m);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
   for (auto& e : m->bucket_ev) cudaEventDestroy(e);
   if (m->aux_ev) cudaEventDestroy(m->aux_ev);
   delete m;
   return 0;
 }
 
-int nlps_set_stream(nlps_model* m, void* s) { NLPS_REQUIRE(m, "null model"); m->stream = (cudaStream_t)s; return 0; }
+int nlps_set_stream(nlps_model* m, void* s) {
+  NLPS_REQUIRE(m, "null model");
+  drop_step_graphs(m);
+  // a null handle means "the default": with graphs enabled that is the model's own blocking stream
+  m->stream = (s == nullptr && m->own_stream != nullptr) ? m->own_stream : (cudaStream_t)s;
+  return 0;
+}
 int nlps_set_precision(nlps_model* m, int p) {
   NLPS_REQUIRE(m, "null model");
   NLPS_REQUIRE(p >= 0 && p <= 2, "unknown precision %d", p);
@@ -511,7 +575,7 @@ int nlps_cache_create(nlps_model* m, int B, int S, nlps_cache** out) {
   const int64_t N = c->N, E = m->E, F = m->F;
   int64_t cur = 0;   // in floats
   auto carve = [&](int64_t n) { const int64_t at = cur; cur = round_up(cur + n, kAlign); return at; };
-  const int64_t o_x = carve(N), o_fnp = carve(B), o_h0 = carve(N * E);
+  const int64_t o_x = carve(N), o_fnp = carve(B), o_step = carve(1), o_h0 = carve(N * E);
   struct LO { int64_t qkv, ctx, lse, r1, mean1, rstd1, y1, hid, r2, mean2, rstd2, y2, bits; };
   std::vector<LO> lo(m->L);
   for (auto& q : lo) {
@@ -529,6 +593,7 @@ int nlps_cache_create(nlps_model* m, int B, int S, nlps_cache** out) {
     cudaGetLastError();
     for (nlps_cache* p : m->pool) { cudaFree(p->base); delete p; }
     m->pool.clear();
+    bump_alloc_epoch();
     e = cudaMalloc(&c->base, c->bytes);
   }
   if (e != cudaSuccess) {
@@ -539,6 +604,7 @@ int nlps_cache_create(nlps_model* m, int B, int S, nlps_cache** out) {
   float* f = reinterpret_cast<float*>(c->base);
   c->x_flat = reinterpret_cast<int32_t*>(f + o_x);
   c->fnp = reinterpret_cast<int32_t*>(f + o_fnp);
+  c->dev_step = reinterpret_cast<uint32_t*>(f + o_step);
   c->h0 = f + o_h0;
   c->layers.resize(m->L);
   for (int l = 0; l < m->L; ++l) {
@@ -562,6 +628,7 @@ int nlps_cache_release(nlps_model* m, nlps_cache* c) {
     m->pool.erase(m->pool.begin());
     cudaStreamSynchronize(m->stream);
     cudaFree(old->base);
+    bump_alloc_epoch();
     delete old;
   }
   m->pool.push_back(c);
@@ -591,6 +658,10 @@ int nlps_forward(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, i
   c->drop_p = (m->training && m->dropout_p > 0.f) ? m->dropout_p : 0.f;
   c->drop_step = m->fwd_counter++;
   c->has_logits = false;
+  if (!m->in_graph_body && c->drop_p > 0.f) {
+    set_step_scalars_kernel<<<1, 1, 0, st>>>(c->dev_step, c->drop_step, nullptr, 0.f, 0.f, 0.f);
+    NLPS_LAUNCH_CHECK();
+  }
   NLPS_TRY(embed_forward(st, c->B, c->S, E, m->V, d_x, xs, m->P + m->off_We, m->pe, c->h0, c->x_flat, m->err_flag));
   NLPS_TRY(first_nonpad(st, c->B, c->S, c->x_flat, c->fnp));
   const float* x_in = c->h0;
@@ -730,13 +801,14 @@ int nlps_step(nlps_model* m, float lr, int use_clip_scale) {
   NLPS_REQUIRE(m, "null model");
   NLPS_CUDA(cudaSetDevice(m->device));
   const float* cs = use_clip_scale ? m->scalars + 1 : nullptr;
-  if (!m->cfg.use_adam) return sgd_update(m->stream, m->flat, m->P, m->G, lr, cs);
+  const float* hyper = m->in_graph_body ? m->hyper : nullptr;    // inside a captured step the values come from the setter node
+  if (!m->cfg.use_adam) return sgd_update(m->stream, m->flat, m->P, m->G, lr, cs, hyper);
   m->adam_t += 1;
   const double b1 = 0.9, b2 = 0.999;                       // transformer.py:29-31
-  const float bc1 = (float)(1.0 - std::pow(b1, (double)m->adam_t));
-  const float bc2 = (float)(1.0 - std::pow(b2, (double)m->adam_t));
+  float bc1, bc2;
+  adam_bias_corrections(m->adam_t, &bc1, &bc2);
   return adam_update(m->stream, m->flat, m->P, m->G, m->M, m->Vv, lr, (float)b1, (float)b2, (float)(1.0 - b1),
-                     (float)(1.0 - b2), 1e-8f, bc1, bc2, cs);
+                     (float)(1.0 - b2), 1e-8f, bc1, bc2, cs, hyper);
 }
 
 int nlps_adam_t(nlps_model* m, int64_t* t, int set, int64_t value) {
@@ -746,9 +818,9 @@ int nlps_adam_t(nlps_model* m, int64_t* t, int set, int64_t value) {
   return 0;
 }
 
-int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_y, float lr,
-                    float max_norm, float grad_scale, int defer_update, float* d_loss) {
-  NLPS_REQUIRE(m && c && d_x && d_y, "nlps_train_step: null argument");
+// the fused step as it always ran: forward, loss (dlogits in place), backward, clip, update
+static int train_step_body(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_y, float lr,
+                           float max_norm, float grad_scale, int defer_update, float* d_loss) {
   NLPS_TRY(nlps_forward(m, c, d_x, xs, 0, nullptr, 0));
   // dlogits overwrite the logits in place: 8V bytes of HBM traffic per token for the loss
   NLPS_CUDA(cudaSetDevice(m->device));
@@ -761,6 +833,125 @@ int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs
   if (defer_update) return 0;
   if (max_norm > 0.f) NLPS_TRY(nlps_clip_compute(m, max_norm));
   return nlps_step(m, lr, max_norm > 0.f ? 1 : 0);
+}
+
+int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_y, float lr,
+                    float max_norm, float grad_scale, int defer_update, float* d_loss) {
+  NLPS_REQUIRE(m && c && d_x && d_y, "nlps_train_step: null argument");
+  // CUDA graph path: single-GPU update in the same call, on a capturable stream, 1xTF32 or FP32 arithmetic (the 3xTF32
+  // split allocates stream-ordered scratch per product).  First sighting of a signature runs eagerly (it sizes every
+  // workspace), the second one is captured, later ones are replayed with one patched node.
+  const bool graphable = m->graph_mode == 1 && !defer_update && m->stream != nullptr && m->precision != NLPS_PREC_TF32X3;
+  if (!graphable) return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
+  NLPS_CUDA(cudaSetDevice(m->device));
+  const float drop_p = (m->training && m->dropout_p > 0.f) ? m->dropout_p : 0.f;
+  nlps_model::StepGraph* e = nullptr;
+  for (size_t i = 0; i < m->graphs.size();) {
+    nlps_model::StepGraph& g = m->graphs[i];
+    if (g.epoch != alloc_epoch()) {            // something it points into was re-allocated
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+      if (g.graph) cudaGraphDestroy(g.graph);
+      m->graphs.erase(m->graphs.begin() + i);
+      continue;
+    }
+    if (g.cache == c && g.x == d_x && g.xs == xs && g.y == d_y && g.max_norm == max_norm && g.grad_scale == grad_scale &&
+        g.dropout_p == drop_p && g.precision == m->precision && g.training == m->training) e = &g;
+    ++i;
+  }
+  if (e == nullptr) {
+    const int rc = train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, 0, d_loss);
+    if (rc != 0) return rc;
+    if (m->graphs.size() >= 8) {               // bounded: forget the oldest signature
+      if (m->graphs.front().exec) cudaGraphExecDestroy(m->graphs.front().exec);
+      if (m->graphs.front().graph) cudaGraphDestroy(m->graphs.front().graph);
+      m->graphs.erase(m->graphs.begin());
+    }
+    nlps_model::StepGraph g{};
+    g.cache = c; g.x = d_x; g.xs = xs; g.y = d_y; g.max_norm = max_norm; g.grad_scale = grad_scale; g.dropout_p = drop_p;
+    g.precision = m->precision; g.training = m->training; g.epoch = alloc_epoch(); g.state = 1;
+    m->graphs.push_back(g);
+    return 0;
+  }
+  if (e->state == 3) return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, 0, d_loss);
+  // this step's scalars
+  const uint32_t step = m->fwd_counter;
+  float bc1 = 1.f, bc2 = 1.f;
+  if (m->cfg.use_adam) adam_bias_corrections(m->adam_t + 1, &bc1, &bc2);
+  uint32_t* a_slot = c->dev_step; uint32_t a_step = step; float* a_hyper = m->hyper; float a_lr = lr, a_bc1 = bc1, a_bc2 = bc2;
+  void* setter_args[6] = {&a_slot, &a_step, &a_hyper, &a_lr, &a_bc1, &a_bc2};
+  float* loss_slot = m->scalars + 3;
+  if (e->state == 1) {
+    // ---- capture ----
+    cudaStream_t st = m->stream;
+    const long long launches_before = launch_count(false);
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      e->state = 3;
+      return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, 0, d_loss);
+    }
+    m->in_graph_body = true;
+    set_step_scalars_kernel<<<1, 1, 0, st>>>(a_slot, a_step, a_hyper, a_lr, a_bc1, a_bc2);
+    count_launch();
+    const int rc = train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, 0, loss_slot);
+    m->in_graph_body = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    const unsigned long long epoch_after = alloc_epoch();
+    bool ok = rc == 0 && ce == cudaSuccess && graph != nullptr && epoch_after == e->epoch;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t setter = nullptr;
+    if (ok) {
+      size_t n_nodes = 0;
+      ok = cudaGraphGetNodes(graph, nullptr, &n_nodes) == cudaSuccess && n_nodes > 0;
+      std::vector<cudaGraphNode_t> nodes(n_nodes);
+      if (ok) ok = cudaGraphGetNodes(graph, nodes.data(), &n_nodes) == cudaSuccess;
+      for (size_t i = 0; ok && i < n_nodes && setter == nullptr; ++i) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp{};
+        if (cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && kp.func == (void*)set_step_scalars_kernel) setter = nodes[i];
+      }
+      ok = ok && setter != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    }
+    if (!ok) {
+      // The host-side bookkeeping of the captured body has happened (counters advanced) but no kernel ran: wind it back
+      // and run this step eagerly; the signature stays eager from now on.
+      cudaGetLastError();
+      if (exec) cudaGraphExecDestroy(exec);
+      if (graph) cudaGraphDestroy(graph);
+      if (rc == 0) { m->fwd_counter -= 1; if (m->cfg.use_adam) m->adam_t -= 1; }
+      // e may dangle if the vector changed: look the entry up again
+      for (auto& g : m->graphs) if (g.cache == c && g.x == d_x && g.y == d_y && g.state == 1) g.state = 3;
+      return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, 0, d_loss);
+    }
+    e->graph = graph; e->exec = exec; e->setter = setter; e->state = 2;
+    e->launches = launch_count(false) - launches_before;
+    e->relu_bits_valid = c->relu_bits_valid;
+    // nothing has executed yet: this step's work is the first launch of the graph
+    NLPS_CUDA(cudaGraphLaunch(exec, st));
+    if (d_loss != nullptr) NLPS_CUDA(cudaMemcpyAsync(d_loss, loss_slot, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  // ---- replay ----
+  {
+    cudaKernelNodeParams kp{};
+    kp.func = (void*)set_step_scalars_kernel;
+    kp.gridDim = dim3(1, 1, 1); kp.blockDim = dim3(1, 1, 1); kp.sharedMemBytes = 0;
+    kp.kernelParams = setter_args; kp.extra = nullptr;
+    NLPS_CUDA(cudaGraphExecKernelNodeSetParams(e->exec, e->setter, &kp));
+    NLPS_CUDA(cudaGraphLaunch(e->exec, m->stream));
+    if (d_loss != nullptr) NLPS_CUDA(cudaMemcpyAsync(d_loss, loss_slot, sizeof(float), cudaMemcpyDeviceToDevice, m->stream));
+    // the host-side state the eager body leaves behind
+    c->drop_p = drop_p;
+    c->drop_step = m->fwd_counter++;
+    c->valid = true;
+    c->has_logits = false;
+    c->rowstat_valid = false;
+    c->relu_bits_valid = e->relu_bits_valid;
+    if (m->cfg.use_adam) m->adam_t += 1;
+    count_launch((int)e->launches);
+  }
+  return 0;
 }
 
 int nlps_train_step_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_t,

@@ -38,7 +38,8 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
 __global__ void __launch_bounds__(256) adam_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, float lr, float b1,
                                                    float b2, float omb1, float omb2, float eps, float bc1, float bc2,
-                                                   const float* __restrict__ clip_scale) {
+                                                   const float* __restrict__ clip_scale, const float* __restrict__ hyper) {
+  if (hyper != nullptr) { lr = hyper[0]; bc1 = hyper[1]; bc2 = hyper[2]; }   // graph replay: the step's values live on the device
   const float cs = clip_scale ? clip_scale[0] : 1.f;
   const int64_t n4 = n >> 2;
   float4* p4 = reinterpret_cast<float4*>(p);
@@ -63,7 +64,8 @@ __global__ void __launch_bounds__(256) adam_kernel(int64_t n, float* __restrict_
 }
 
 __global__ void __launch_bounds__(256) sgd_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g,
-                                                  float lr, const float* __restrict__ clip_scale) {
+                                                  float lr, const float* __restrict__ clip_scale, const float* __restrict__ hyper) {
+  if (hyper != nullptr) lr = hyper[0];
   const float cs = clip_scale ? clip_scale[0] : 1.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gg = g[i];
@@ -89,17 +91,17 @@ int scale_inplace(cudaStream_t st, int64_t n, float* x, const float* scale_dev) 
 
 int adam_update(cudaStream_t st, int64_t n, float* p, const float* g, float* m, float* v, float lr, float b1,
                 float b2, float one_minus_b1, float one_minus_b2, float eps, float bc1, float bc2,
-                const float* clip_scale_dev) {
+                const float* clip_scale_dev, const float* hyper_dev) {
   if (n <= 0) return 0;
   adam_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 1024), kNumSMs * 8), 256, 0, st>>>(
-      n, p, g, m, v, lr, b1, b2, one_minus_b1, one_minus_b2, eps, bc1, bc2, clip_scale_dev);
+      n, p, g, m, v, lr, b1, b2, one_minus_b1, one_minus_b2, eps, bc1, bc2, clip_scale_dev, hyper_dev);
   NLPS_LAUNCH_CHECK();
   return 0;
 }
 
-int sgd_update(cudaStream_t st, int64_t n, float* p, const float* g, float lr, const float* clip_scale_dev) {
+int sgd_update(cudaStream_t st, int64_t n, float* p, const float* g, float lr, const float* clip_scale_dev, const float* hyper_dev) {
   if (n <= 0) return 0;
-  sgd_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), kNumSMs * 8), 256, 0, st>>>(n, p, g, lr, clip_scale_dev);
+  sgd_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), kNumSMs * 8), 256, 0, st>>>(n, p, g, lr, clip_scale_dev, hyper_dev);
   NLPS_LAUNCH_CHECK();
   return 0;
 }

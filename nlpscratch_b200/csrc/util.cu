@@ -15,6 +15,12 @@ long long launch_count(bool reset) {
   return reset ? g_launches.exchange(0, std::memory_order_relaxed) : g_launches.load(std::memory_order_relaxed);
 }
 
+// Bumped whenever a device buffer that a captured CUDA graph may point into is re-allocated (split-K workspace,
+// model workspaces, activation caches): graphs captured under an older epoch are dropped instead of replayed.
+static std::atomic<unsigned long long> g_alloc_epoch{1};
+unsigned long long alloc_epoch() { return g_alloc_epoch.load(std::memory_order_relaxed); }
+void bump_alloc_epoch() { g_alloc_epoch.fetch_add(1, std::memory_order_relaxed); }
+
 // cudaMallocAsync scratch (split-K workspaces, 3xTF32 splits) must not go back to the driver at every
 // synchronisation: keep the default pool's memory cached.
 void ensure_mempool_config() {

@@ -409,3 +409,37 @@ print(json.dumps([float(m.train_step(x, y, learning_rate=1e-3, clip_grad_norm=1.
         out[flag] = json.loads(res.stdout.strip().splitlines()[-1])
     for a, b in zip(out["0"], out["1"]):
         assert abs(a - b) < 2e-5 * max(1.0, abs(a)), (out["0"], out["1"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+def test_cuda_graph_replay_of_the_fused_step_is_bitwise_the_eager_step(precision):
+    """nlps_train_step captures the step into a CUDA graph the second time it sees a (cache, x, y) signature and replays it
+    afterwards with one patched node (dropout counter, lr, Adam bias corrections).  With device-resident batches the
+    trajectory must equal the eager one (NLPS_GRAPH=0) bit for bit -- dropout on, learning rate changing."""
+    import subprocess, sys, os, json
+    code = r"""
+import json, sys, hashlib, numpy as np
+sys.path.insert(0, %r)
+from nlpscratch_b200 import Transformer
+from nlpscratch_b200.array import DeviceArray
+np.random.seed(5)
+m = Transformer(300, 128, 4, 256, 2, 96, dropout_p=0.1, precision=%r)
+rng = np.random.default_rng(1)
+xs = [DeviceArray.from_host(rng.integers(1, 300, (6, 96)).astype(np.int32)) for _ in range(2)]
+ys = [DeviceArray.from_host(rng.integers(0, 300, (6, 96)).astype(np.int32)) for _ in range(2)]
+losses = []
+for i in range(9):                      # each batch is seen 4-5 times: eager, capture, replays
+    lr = 1e-3 if i < 5 else 5e-4
+    losses.append(float(m.train_step(xs[i %% 2], ys[i %% 2], learning_rate=lr, clip_grad_norm=1.0)).hex())
+p = m.get_params()
+print(json.dumps({"losses": losses, "params": hashlib.sha256(b"".join(np.ascontiguousarray(p[k]).tobytes() for k in sorted(p))).hexdigest()}))
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), precision)
+    out = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, NLPS_GRAPH=flag)
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        out[flag] = json.loads(res.stdout.strip().splitlines()[-1])
+    assert out["0"]["losses"] == out["1"]["losses"]
+    assert out["0"]["params"] == out["1"]["params"]
