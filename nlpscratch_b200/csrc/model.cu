@@ -93,7 +93,7 @@ struct nlps_model {
   // the setter that publishes the step's scalars (dropout counter, lr, Adam bias corrections) to device memory.
   struct StepGraph {
     const nlps_cache* cache; const int32_t* x; int64_t xs; const int32_t* y;
-    float max_norm, grad_scale, dropout_p; int precision; bool training;
+    float max_norm, grad_scale, dropout_p; int precision; bool training; bool deferred;
     unsigned long long epoch;
     int state;                         // 1 = signature seen once (ran eagerly), 2 = captured, 3 = not capturable
     cudaGraphExec_t exec = nullptr;
@@ -106,6 +106,7 @@ struct nlps_model {
   cudaStream_t own_stream = nullptr;   // created when the model would otherwise run on the legacy default stream
   float* hyper = nullptr;              // device {lr, bc1, bc2}
   bool in_graph_body = false;          // the per-call setters are replaced by the one setter node
+  bool graph_external_events = false;  // capturing a deferred-update step: bucket events become external record nodes
   int graph_mode = -1;
 };
 
@@ -215,7 +216,14 @@ inline void adam_bias_corrections(int64_t t, float* bc1, float* bc2) {
 }
 
 int record_bucket(nlps_model* m, int bucket) {
-  if (m->in_graph_body) return 0;      // nobody waits on the bucket events of a single-GPU captured step
+  if (m->in_graph_body) {
+    // single-GPU captured step: nobody waits on the bucket events.  Deferred (data-parallel) captured step: the record
+    // becomes an external event-record node, so the communication stream's cudaStreamWaitEvent after the graph launch
+    // waits for this point of the replay.
+    if (!m->graph_external_events) return 0;
+    NLPS_CUDA(cudaEventRecordWithFlags(m->bucket_ev[bucket], m->stream, cudaEventRecordExternal));
+    return 0;
+  }
   NLPS_CUDA(cudaEventRecord(m->bucket_ev[bucket], m->stream));
   return 0;
 }
@@ -841,7 +849,9 @@ int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs
   // CUDA graph path: single-GPU update in the same call, on a capturable stream, 1xTF32 or FP32 arithmetic (the 3xTF32
   // split allocates stream-ordered scratch per product).  First sighting of a signature runs eagerly (it sizes every
   // workspace), the second one is captured, later ones are replayed with one patched node.
-  const bool graphable = m->graph_mode == 1 && !defer_update && m->stream != nullptr && m->precision != NLPS_PREC_TF32X3;
+  static const bool dp_graph = [] { const char* e = getenv("NLPS_GRAPH_DP"); return !(e && e[0] == '0'); }();
+  const bool graphable = m->graph_mode == 1 && (!defer_update || dp_graph) && m->stream != nullptr && m->precision != NLPS_PREC_TF32X3;
+  const bool deferred = defer_update != 0;
   if (!graphable) return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
   NLPS_CUDA(cudaSetDevice(m->device));
   const float drop_p = (m->training && m->dropout_p > 0.f) ? m->dropout_p : 0.f;
@@ -855,11 +865,11 @@ int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs
       continue;
     }
     if (g.cache == c && g.x == d_x && g.xs == xs && g.y == d_y && g.max_norm == max_norm && g.grad_scale == grad_scale &&
-        g.dropout_p == drop_p && g.precision == m->precision && g.training == m->training) e = &g;
+        g.dropout_p == drop_p && g.precision == m->precision && g.training == m->training && g.deferred == deferred) e = &g;
     ++i;
   }
   if (e == nullptr) {
-    const int rc = train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, 0, d_loss);
+    const int rc = train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
     if (rc != 0) return rc;
     if (m->graphs.size() >= 8) {               // bounded: forget the oldest signature
       if (m->graphs.front().exec) cudaGraphExecDestroy(m->graphs.front().exec);
@@ -868,15 +878,15 @@ int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs
     }
     nlps_model::StepGraph g{};
     g.cache = c; g.x = d_x; g.xs = xs; g.y = d_y; g.max_norm = max_norm; g.grad_scale = grad_scale; g.dropout_p = drop_p;
-    g.precision = m->precision; g.training = m->training; g.epoch = alloc_epoch(); g.state = 1;
+    g.precision = m->precision; g.training = m->training; g.deferred = deferred; g.epoch = alloc_epoch(); g.state = 1;
     m->graphs.push_back(g);
     return 0;
   }
-  if (e->state == 3) return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, 0, d_loss);
+  if (e->state == 3) return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
   // this step's scalars
   const uint32_t step = m->fwd_counter;
   float bc1 = 1.f, bc2 = 1.f;
-  if (m->cfg.use_adam) adam_bias_corrections(m->adam_t + 1, &bc1, &bc2);
+  if (m->cfg.use_adam) adam_bias_corrections(m->adam_t + 1, &bc1, &bc2);   // unused by a deferred graph (no update inside)
   uint32_t* a_slot = c->dev_step; uint32_t a_step = step; float* a_hyper = m->hyper; float a_lr = lr, a_bc1 = bc1, a_bc2 = bc2;
   void* setter_args[6] = {&a_slot, &a_step, &a_hyper, &a_lr, &a_bc1, &a_bc2};
   float* loss_slot = m->scalars + 3;
@@ -887,13 +897,15 @@ int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
       cudaGetLastError();
       e->state = 3;
-      return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, 0, d_loss);
+      return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
     }
     m->in_graph_body = true;
+    m->graph_external_events = deferred;
     set_step_scalars_kernel<<<1, 1, 0, st>>>(a_slot, a_step, a_hyper, a_lr, a_bc1, a_bc2);
     count_launch();
-    const int rc = train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, 0, loss_slot);
+    const int rc = train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, loss_slot);
     m->in_graph_body = false;
+    m->graph_external_events = false;
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(st, &graph);
     const unsigned long long epoch_after = alloc_epoch();
@@ -919,10 +931,10 @@ int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs
       cudaGetLastError();
       if (exec) cudaGraphExecDestroy(exec);
       if (graph) cudaGraphDestroy(graph);
-      if (rc == 0) { m->fwd_counter -= 1; if (m->cfg.use_adam) m->adam_t -= 1; }
+      if (rc == 0) { m->fwd_counter -= 1; if (m->cfg.use_adam && !deferred) m->adam_t -= 1; }
       // e may dangle if the vector changed: look the entry up again
       for (auto& g : m->graphs) if (g.cache == c && g.x == d_x && g.y == d_y && g.state == 1) g.state = 3;
-      return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, 0, d_loss);
+      return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
     }
     e->graph = graph; e->exec = exec; e->setter = setter; e->state = 2;
     e->launches = launch_count(false) - launches_before;
@@ -948,7 +960,7 @@ int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs
     c->has_logits = false;
     c->rowstat_valid = false;
     c->relu_bits_valid = e->relu_bits_valid;
-    if (m->cfg.use_adam) m->adam_t += 1;
+    if (m->cfg.use_adam && !deferred) m->adam_t += 1;
     count_launch((int)e->launches);
   }
   return 0;

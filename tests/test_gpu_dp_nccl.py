@@ -29,14 +29,19 @@ model = Transformer(*cfg, dropout_p=0.0, precision="fp32", device=local)
 dp = DataParallel(model, min_bucket_floats=1)  # one all-reduce per bucket: exercises the bucket events
 dp.broadcast_parameters(0)
 b, e = shard_rows(8, rank, world)
-for step in range(3):
-    loss = dp.train_step(x[b:e], y[b:e], 1e-3, 0.5)
+from nlpscratch_b200.array import DeviceArray
+xd, yd = DeviceArray.from_host(x[b:e]), DeviceArray.from_host(y[b:e])
+STEPS = 5                                      # device-resident inputs: eager, captured, then replayed as a CUDA graph
+for step in range(STEPS):
+    loss = dp.train_step(xd, yd, 1e-3, 0.5)
 got = model.get_params()
+import hashlib
+print("rank%d params sha %s" % (rank, hashlib.sha256(b"".join(np.ascontiguousarray(got[k]).tobytes() for k in sorted(got))).hexdigest()))
 losses = torch.tensor([float(loss)], device="cuda"); dist.all_reduce(losses)
 if rank == 0:
     np.random.seed(11)
     ref = Transformer(*cfg, dropout_p=0.0, precision="fp32", device=local)
-    for step in range(3):
+    for step in range(STEPS):
         l = ref.train_step(x, y, 1e-3, 0.5)
     want = ref.get_params()
     worst = max(float(np.linalg.norm(got[k].astype(np.float64) - want[k]) / max(np.linalg.norm(want[k]), 1e-30)) for k in want)
@@ -57,6 +62,12 @@ def test_two_rank_nccl_step_matches_single_gpu(tmp_path):
     env = dict(os.environ, REPO=ROOT)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29541", script]
-    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=280)
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert "dp ok" in res.stdout
+    shas = {}
+    for graph_dp in ("1", "0"):                # the deferred step replayed as a CUDA graph (bucket events = external
+        env["NLPS_GRAPH_DP"] = graph_dp        # event-record nodes) must equal the eager data-parallel step bit for bit
+        res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=280)
+        assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+        assert "dp ok" in res.stdout
+        shas[graph_dp] = sorted(l for l in res.stdout.splitlines() if "params sha" in l)
+        assert len(shas[graph_dp]) == 2 and shas[graph_dp][0].split()[-1] == shas[graph_dp][1].split()[-1], shas
+    assert shas["1"] == shas["0"], shas

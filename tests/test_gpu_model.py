@@ -443,3 +443,47 @@ print(json.dumps({"losses": losses, "params": hashlib.sha256(b"".join(np.asconti
         out[flag] = json.loads(res.stdout.strip().splitlines()[-1])
     assert out["0"]["losses"] == out["1"]["losses"]
     assert out["0"]["params"] == out["1"]["params"]
+
+
+@pytest.mark.gpu
+def test_cuda_graph_of_the_deferred_step_with_external_bucket_events_is_bitwise_the_eager_one():
+    """The data-parallel half-step (defer_update: forward, loss, backward; the update follows the all-reduce) is captured
+    too; its per-bucket events become external event-record nodes that a communication stream waits on after the graph
+    launch.  One rank, NCCL group of size 1 so that DataParallel's bucket waits and all-reduces really run: the
+    trajectory must equal the eager one (NLPS_GRAPH_DP=0) bit for bit, dropout on."""
+    import subprocess, sys, os, json
+    code = r"""
+import json, sys, os, hashlib, numpy as np
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29547")
+torch.cuda.set_device(0)
+dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+from nlpscratch_b200 import Transformer
+from nlpscratch_b200.array import DeviceArray
+from nlpscratch_b200.dp import DataParallel
+np.random.seed(5)
+m = Transformer(300, 128, 4, 256, 2, 96, dropout_p=0.1, precision="tf32", device=0)
+dp = DataParallel(m, min_bucket_floats=1)
+rng = np.random.default_rng(1)
+xs = [DeviceArray.from_host(rng.integers(1, 300, (6, 96)).astype(np.int32)) for _ in range(2)]
+ys = [DeviceArray.from_host(rng.integers(0, 300, (6, 96)).astype(np.int32)) for _ in range(2)]
+losses = []
+for i in range(9):
+    lr = 1e-3 if i < 5 else 5e-4
+    l = m.train_step(xs[i %% 2], ys[i %% 2], learning_rate=lr, clip_grad_norm=1.0, grad_scale=0.5, defer_update=True)
+    dp.allreduce_gradients()
+    m.apply_update(lr, 1.0)
+    losses.append(float(l).hex())
+p = m.get_params()
+print(json.dumps({"losses": losses, "launches": m.launch_count(), "params": hashlib.sha256(b"".join(np.ascontiguousarray(p[k]).tobytes() for k in sorted(p))).hexdigest()}))
+dist.destroy_process_group()
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    out = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, NLPS_GRAPH_DP=flag)
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        out[flag] = json.loads([l for l in res.stdout.strip().splitlines() if l.startswith("{")][-1])
+    assert out["0"]["losses"] == out["1"]["losses"]
+    assert out["0"]["params"] == out["1"]["params"]
