@@ -556,12 +556,13 @@ int attention_forward(cudaStream_t st, int precision, int B, int S, int h, int d
 
 int attention_backward(cudaStream_t st, int precision, int B, int S, int h, int d, const float* qkv,
                        const int32_t* x, const int32_t* fnp, const float* ctx, const float* lse,
-                       const float* dctx, float* delta, float* dqkv) {
+                       const float* dctx, float* delta, float* dqkv, bool delta_ready) {
   NLPS_TRY(check_dims(B, S, h, d));
   AttnDims p{B, S, h, d, h * d, (float)(1.0 / sqrt((double)d))};
   const int64_t ntok = (int64_t)B * S;
   const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(ctx) | reinterpret_cast<uintptr_t>(dctx)) & 15u) == 0;
   const unsigned vgrid = (unsigned)ceil_div(ntok, 8);
+  if (delta_ready) goto delta_done;
   if (vec && d == 64) attn_delta_vec_kernel<16><<<vgrid, 256, 0, st>>>(p, ntok, ctx, dctx, delta);
   else if (vec && d == 32) attn_delta_vec_kernel<8><<<vgrid, 256, 0, st>>>(p, ntok, ctx, dctx, delta);
   else if (vec && d == 128) attn_delta_vec_kernel<32><<<vgrid, 256, 0, st>>>(p, ntok, ctx, dctx, delta);
@@ -569,6 +570,7 @@ int attention_backward(cudaStream_t st, int precision, int B, int S, int h, int 
   else if (vec && d == 8) attn_delta_vec_kernel<2><<<vgrid, 256, 0, st>>>(p, ntok, ctx, dctx, delta);
   else attn_delta_kernel<<<(unsigned)ntok, std::min(1024, 32 * h), 0, st>>>(p, ctx, dctx, delta);
   NLPS_LAUNCH_CHECK();
+delta_done:
   if (precision == 1 && attention_tc_supported(d, h * d, qkv) && attn_impl() != 1 &&
       (reinterpret_cast<uintptr_t>(dctx) & 15u) == 0) {
     if (attn_impl() == 2) return attention_backward_tc(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv);

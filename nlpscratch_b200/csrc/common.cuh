@@ -162,6 +162,12 @@ struct GemmArgs {
   // rowstat_out[row * ceil(N/32) + block] = {max, sum exp(v - max)} -- the cross-entropy then skips its first pass
   // over the logits (the part of the vocab-head + CE fusion that pays at V = 8192)
   float2* rowstat_out = nullptr;
+  // third by-product (same kernel, same conditions, see gemm_tf32_rowdot_fusable): blocked row dots of the stored result
+  // with a second matrix, rowdot_out[((row / rowdot_S) * (N / rowdot_w) + col / rowdot_w) * rowdot_S + row % rowdot_S] =
+  // sum over the rowdot_w (32 or 64) columns of the block of C[row, col] * rowdot_in[row, col].  With C = dctx and
+  // rowdot_in = ctx this is the row term of softmax_backward moved through P@V, delta[b,h,i] = dO_i . O_i
+  // (function.py:59-65), without the extra pass over dctx and ctx.
+  const float* rowdot_in = nullptr; int64_t ld_rowdot = 0; float* rowdot_out = nullptr; int rowdot_w = 0, rowdot_S = 0;
 };
 
 // bias -> relu -> gate -> dropout -> residual, identical in every GEMM implementation
@@ -179,6 +185,7 @@ int gemm_tf32(cudaStream_t st, const GemmArgs& g);       // gemm_tcgen05.cu  (1x
 int gemm_tf32x3(cudaStream_t st, const GemmArgs& g);     // 3-pass split, FP32-level error
 bool gemm_tf32_supported(const GemmArgs& g);
 bool gemm_tf32_colsum_fusable(const GemmArgs& g);   // colsum32_out may be set for this product
+bool gemm_tf32_rowdot_fusable(const GemmArgs& g);   // rowdot_out may be set for this product (rowdot_* fields filled in)
 int gemm_dispatch(cudaStream_t st, int precision, const GemmArgs& g);
 
 // dataset.cu
@@ -194,7 +201,8 @@ int attention_forward(cudaStream_t st, int precision, int B, int S, int h, int d
                       const int32_t* x, const int32_t* first_nonpad, float* ctx, float* lse);
 int attention_backward(cudaStream_t st, int precision, int B, int S, int h, int d, const float* qkv,
                        const int32_t* x, const int32_t* first_nonpad, const float* ctx, const float* lse,
-                       const float* dctx, float* delta_scratch, float* dqkv);
+                       const float* dctx, float* delta_scratch, float* dqkv, bool delta_ready = false);
+// delta_ready: delta_scratch already holds sum(dO*O) per (b,h,i) (by-product of the Wo dgrad GEMM, GemmArgs::rowdot_out)
 int first_nonpad(cudaStream_t st, int B, int S, const int32_t* x, int32_t* out);
 // attention_tc.cu (tcgen05 / TMEM versions, head_dim 32 or 64)
 bool attention_tc_supported(int d, int E, const float* qkv);

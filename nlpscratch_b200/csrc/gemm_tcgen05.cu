@@ -578,6 +578,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int c_begin = half * kChunksPerWarp;
       int c_end = min(c_begin + kChunksPerWarp, (g.N - n0 + 31) / 32);
       if (!rows_live || (ka.debug & 2)) c_end = c_begin;
+      float rowdot_carry = 0.f;
 #pragma unroll 1
       for (int c = c_begin; c < c_end; ++c) {
         uint32_t v[32];
@@ -592,6 +593,29 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (col0 + j < g.N) sum += exp2f((__uint_as_float(v[j]) - mx) * 1.4426950408889634f);
           g.rowstat_out[(int64_t)(m0 + q * 32 + lane) * ((g.N + 31) >> 5) + (col0 >> 5)] = make_float2(mx, sum);
+        }
+        if (g.rowdot_out != nullptr) {       // blocked row dots with a second matrix (delta = dO . O of the attention backward)
+          const int row = m0 + q * 32 + lane;
+          float part = 0.f;
+          if (row < g.M) {
+            const float* src = g.rowdot_in + (int64_t)row * g.ld_rowdot + n0 + c * 32;
+            float t[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ld_v8(src + 8 * i, t[i]);
+            float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) ps[i] = fmaf(__uint_as_float(v[8 * i + j]), t[i][j], ps[i]);
+            part = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+          }
+          // a 64-wide block is two consecutive chunks of the same thread (chunk ranges start even, hold an even count)
+          if (g.rowdot_w == 64 && (c & 1) == 0) rowdot_carry = part;
+          else if (row < g.M) {
+            const float tot = g.rowdot_w == 64 ? rowdot_carry + part : part;
+            const int bi = row / g.rowdot_S, si = row - bi * g.rowdot_S;
+            g.rowdot_out[((int64_t)bi * (g.N / g.rowdot_w) + (n0 + c * 32) / g.rowdot_w) * g.rowdot_S + si] = tot;
+          }
         }
         if (g.colsum32_out != nullptr) {     // the epilogue warps have slack: the bias-gradient partials ride along
           const float tot = block_colsum32(v, m0 + q * 32 + lane < g.M, lane);
@@ -801,8 +825,10 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
                (!g.gate || (aligned16(g.gate) && g.ldg % 4 == 0))) ? 1 : 0;
   NLPS_REQUIRE(!(g.relu_bits_out || g.gate_bits) || (g.N % 32 == 0 && splits == 1),
                "gemm_tf32: bit-packed ReLU masks need N %% 32 == 0 and no split-K");
-  NLPS_REQUIRE((g.colsum32_out == nullptr && g.rowstat_out == nullptr) || (pair && splits == 1 && !g.gate && !g.residual && !g.accumulate),
-               "gemm_tf32: colsum32_out / rowstat_out need the CTA-pair kernel without split-K, float gate, residual or accumulate");
+  NLPS_REQUIRE((g.colsum32_out == nullptr && g.rowstat_out == nullptr && g.rowdot_out == nullptr) ||
+                   (pair && splits == 1 && !g.gate && !g.residual && !g.accumulate),
+               "gemm_tf32: colsum32_out / rowstat_out / rowdot_out need the CTA-pair kernel without split-K, float gate, residual or accumulate");
+  NLPS_REQUIRE(g.rowdot_out == nullptr || gemm_tf32_rowdot_fusable(g), "gemm_tf32: rowdot_out is not fusable for this product");
   ka.ws = nullptr;
   ka.ws_ld = round_up(g.N, 8);
   {
@@ -863,6 +889,13 @@ bool gemm_tf32_colsum_fusable(const GemmArgs& g) {
   const int64_t tiles = ceil_div(g.M, 256) * ceil_div(g.N, 256);
   const int64_t kblocks = ceil_div(g.K, BK);
   return !(tiles < 2 * (kNumSMs / 2) && kblocks >= 64);      // no split-K
+}
+
+bool gemm_tf32_rowdot_fusable(const GemmArgs& g) {
+  if (!gemm_tf32_colsum_fusable(g)) return false;
+  if (g.rowdot_w != 32 && g.rowdot_w != 64) return false;
+  if (g.N % g.rowdot_w != 0 || g.rowdot_S <= 0 || g.M % g.rowdot_S != 0) return false;
+  return g.rowdot_in != nullptr && (reinterpret_cast<uintptr_t>(g.rowdot_in) & 31u) == 0 && g.ld_rowdot % 8 == 0;
 }
 
 // 3xTF32: A = Ah + Al, B = Bh + Bl with Ah,Bh exactly representable in TF32;

@@ -286,13 +286,21 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
       g.trans_a = true;
       NLPS_TRY(gemm_dispatch(st, prec, g));
     }
-    {  // dctx = d_a Wo^T
+    bool delta_ready = false;
+    {  // dctx = d_a Wo^T; the epilogue also forms delta = sum(dctx * ctx) per (token, head) when the product allows it
       GemmArgs g = gemm_nn(N, E, E, d_a, E, m->P + o.wo, E, m->dctx, E);
       g.trans_b = true;
+      static int fuse_delta = -1;
+      if (fuse_delta < 0) { const char* e = getenv("NLPS_FUSE_DELTA"); fuse_delta = (e && e[0] == '0') ? 0 : 1; }
+      if (fuse_delta && prec == NLPS_PREC_TF32) {
+        GemmArgs t = g;
+        t.rowdot_in = a.ctx; t.ld_rowdot = E; t.rowdot_out = m->delta; t.rowdot_w = m->d; t.rowdot_S = c->S;
+        if (gemm_tf32_rowdot_fusable(t)) { g = t; delta_ready = true; }
+      }
       NLPS_TRY(gemm_dispatch(st, prec, g));
     }
     NLPS_TRY(attention_backward(st, prec, c->B, c->S, m->h, m->d, a.qkv, c->x_flat, c->fnp, a.ctx, a.lse, m->dctx,
-                                m->delta, m->dqkv));
+                                m->delta, m->dqkv, delta_ready));
     {  // dWqkv = x_in^T dqkv
       GemmArgs g = gemm_nn(E, 3 * E, N, x_in, E, m->dqkv, 3 * E, m->G + o.wqkv, 3 * E);
       g.trans_a = true;

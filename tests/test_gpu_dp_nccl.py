@@ -2,6 +2,7 @@
 Needs two GPUs; skipped otherwise (the single-GPU identity test in test_gpu_model.py and the gloo
 test in test_cpu_abi_and_host.py cover the arithmetic and the host logic)."""
 import os
+import re
 import subprocess
 import sys
 
@@ -68,6 +69,6 @@ def test_two_rank_nccl_step_matches_single_gpu(tmp_path):
         res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=280)
         assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
         assert "dp ok" in res.stdout
-        shas[graph_dp] = sorted(l for l in res.stdout.splitlines() if "params sha" in l)
-        assert len(shas[graph_dp]) == 2 and shas[graph_dp][0].split()[-1] == shas[graph_dp][1].split()[-1], shas
+        shas[graph_dp] = re.findall(r"params sha ([0-9a-f]{64})", res.stdout)     # the ranks' lines may interleave
+        assert len(shas[graph_dp]) == 2 and shas[graph_dp][0] == shas[graph_dp][1], shas
     assert shas["1"] == shas["0"], shas

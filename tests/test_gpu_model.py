@@ -487,3 +487,39 @@ dist.destroy_process_group()
         out[flag] = json.loads([l for l in res.stdout.strip().splitlines() if l.startswith("{")][-1])
     assert out["0"]["losses"] == out["1"]["losses"]
     assert out["0"]["params"] == out["1"]["params"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("heads", [4, 8])
+def test_delta_from_the_wo_dgrad_epilogue_matches_the_separate_pass(heads, tmp_path):
+    """The row term of the softmax backward, delta = sum(dO * O) per (token, head) (function.py:59-65 moved through P@V),
+    is a by-product of the dctx = d_a Wo^T GEMM epilogue (GemmArgs::rowdot_out).  NLPS_FUSE_DELTA=0 runs the separate
+    pass instead; the attention-path gradients must agree to FP32 summation-order accuracy (head_dim 64 and 32, PAD tail,
+    a row count that is not a multiple of the 256-row tile)."""
+    import subprocess, sys, os
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+from nlpscratch_b200 import Transformer
+np.random.seed(3)
+m = Transformer(512, 256, %d, 512, 2, 160, dropout_p=0.0, precision="tf32")
+rng = np.random.default_rng(0)
+x = rng.integers(1, 512, (5, 160)).astype(np.int32); x[1, 100:] = 0
+y = rng.integers(0, 512, (5, 160)).astype(np.int32)
+logits, cache = m.forward(x)
+loss, dl = m.calculate_loss_dlogits(logits, y)
+g = m.backward(cache, dl)
+np.savez(sys.argv[1], **{k: np.asarray(g[k].get()) for k in ("Wq", "Wk", "Wv", "We")})
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), heads)
+    out = {}
+    for flag in ("0", "1"):
+        path = os.path.join(tmp_path, "g%s.npz" % flag)
+        env = dict(os.environ, NLPS_FUSE_DELTA=flag)
+        res = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, env=env, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        out[flag] = np.load(path)
+    for k in ("Wq", "Wk", "Wv", "We"):
+        a, b = out["0"][k].astype(np.float64), out["1"][k].astype(np.float64)
+        assert np.isfinite(b).all()
+        # delta itself moves by ~1e-7 relative; dS is then rounded onto the TF32 grid, where a flipped rounding is 2^-11
+        assert np.linalg.norm(a - b) <= 5e-4 * np.linalg.norm(a), (k, np.linalg.norm(a - b) / np.linalg.norm(a))
