@@ -281,7 +281,7 @@ def run_ours(args, wl):
     for i in range(min(3, args.warmup)):
         e2e_step(i)
     fence()
-    e_steps = max(3, args.steps // 2)
+    e_steps = max(10, args.steps)          # a sync per step exposes host hiccups: enough steps to dilute one
     t0 = time.perf_counter()
     ev0.record()
     for i in range(e_steps):
@@ -322,7 +322,7 @@ def run_ours(args, wl):
                                                            "dropout %.2f, Adam lr 1e-4, clip 1.0" % args.dropout),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": int(2 * nbytes),
-                    "d2h_bytes_per_step": 4, "steps": e_steps},
+                    "d2h_bytes_per_step": 4, "steps": e_steps, "ms_per_step": e_ms / e_steps},
             "roofline": roof, "cpu_baseline": cpu, "loss_first": first_loss, "loss_last": last_loss}
     print(json.dumps(line), flush=True)
 

@@ -563,6 +563,31 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     constexpr int kChunksPerWarp = BN / 32 / (kEpiWarps / 4);
     float* stg = epi_ptr + (warp - 2) * kEpiStageFloats;
     int local = 0;
+    // rowdot operand: this thread's 512 B of the second matrix for a tile are requested into L2 one tile ahead (the
+    // epilogue of a K = 512 product has no slack for a DRAM round trip per chunk)
+    auto rowdot_prefetch = [&](int it) {
+      const bool want_dot = g.rowdot_out != nullptr && !(ka.debug & 16);
+      // the same lead for the residual rows measured SLOWER (same-box A/B at c4: +0.15 ms/step); opt-in for A/B runs only
+      const bool want_res = g.residual != nullptr && ka.ws == nullptr && (ka.debug & 32);
+      if ((!want_dot && !want_res) || it >= items) return;
+      const int tt = it % tiles;
+      const int row = (tt / ka.num_n_tiles) * BMP + (int)rank * BM + q * 32 + lane;
+      const int col = (tt % ka.num_n_tiles) * BN + half * kChunksPerWarp * 32;
+      if (row >= g.M) return;
+      if (want_dot) {
+        const float* src = g.rowdot_in + (int64_t)row * g.ld_rowdot + col;
+#pragma unroll
+        for (int i = 0; i < kChunksPerWarp; ++i)
+          if (col + i * 32 < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + i * 32));
+      }
+      if (want_res) {
+        const float* src = g.residual + (int64_t)row * g.ldr + col;
+#pragma unroll
+        for (int i = 0; i < kChunksPerWarp; ++i)
+          if (col + i * 32 < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + i * 32));
+      }
+    };
+    rowdot_prefetch(pair);
     for (int item = pair; item < items; item += num_pairs, ++local) {
       const int split = item / tiles;
       const int t = item - split * tiles;
@@ -570,6 +595,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int n0 = (t % ka.num_n_tiles) * BN;
       const int buf = local & 1;
       const uint32_t aphase = (uint32_t)(local >> 1) & 1u;
+      rowdot_prefetch(item + num_pairs);
       mbar_wait(tfull_bar(buf), aphase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
