@@ -77,6 +77,14 @@ struct nlps_model {
   int64_t ws_N = 0;
   float *g0 = nullptr, *g1 = nullptr, *gdrop = nullptr, *dctx = nullptr, *dqkv = nullptr, *dhid = nullptr;
   float* colsum32 = nullptr;                  // [ceil(N/32)][F] column-sum partials written by the dz GEMM epilogue
+  float *g1b = nullptr, *gdropb = nullptr;    // LayerNorm-2 backward outputs (own buffers so that the weight-gradient stream may lag)
+  // weight-gradient stream: dW2, dW1, dWo, dWqkv and dW_vocab are off the critical path of backward; on a second stream
+  // they fill the tensor pipe while the main stream runs its bandwidth-bound kernels (LayerNorm backward, column sums,
+  // split-K reducers).  ev_fork: main -> wstream; ev_w[k]: "the k-th kind of weight gradient has been formed" (guards the
+  // buffers it read); w_pending[k]: recorded in this pass.
+  cudaStream_t wstream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_w[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool w_pending[6] = {false, false, false, false, false, false};
   float *delta = nullptr, *row_loss = nullptr, *small = nullptr, *rows_tmp = nullptr;
   int32_t* iscratch = nullptr;
   int64_t rows_tmp_cap = 0;
@@ -160,7 +168,8 @@ int ensure_workspace(nlps_model* m, int B, int S) {
   const int64_t N = (int64_t)B * S;
   if (N <= m->ws_N) return 0;
   NLPS_CUDA(cudaStreamSynchronize(m->stream));
-  float** bufs[] = {&m->g0, &m->g1, &m->gdrop, &m->dctx, &m->dqkv, &m->dhid, &m->delta, &m->row_loss, &m->colsum32};
+  if (m->wstream) NLPS_CUDA(cudaStreamSynchronize(m->wstream));
+  float** bufs[] = {&m->g0, &m->g1, &m->gdrop, &m->dctx, &m->dqkv, &m->dhid, &m->delta, &m->row_loss, &m->colsum32, &m->g1b, &m->gdropb};
   for (float** b : bufs) { if (*b) cudaFree(*b); *b = nullptr; }
   bump_alloc_epoch();
   if (m->iscratch) { cudaFree(m->iscratch); m->iscratch = nullptr; }
@@ -168,6 +177,8 @@ int ensure_workspace(nlps_model* m, int B, int S) {
   NLPS_CUDA(cudaMalloc(&m->g0, sizeof(float) * N * E));
   NLPS_CUDA(cudaMalloc(&m->g1, sizeof(float) * N * E));
   NLPS_CUDA(cudaMalloc(&m->gdrop, sizeof(float) * N * E));
+  NLPS_CUDA(cudaMalloc(&m->g1b, sizeof(float) * N * E));
+  NLPS_CUDA(cudaMalloc(&m->gdropb, sizeof(float) * N * E));
   NLPS_CUDA(cudaMalloc(&m->dctx, sizeof(float) * N * E));
   NLPS_CUDA(cudaMalloc(&m->dqkv, sizeof(float) * N * 3 * E));
   NLPS_CUDA(cudaMalloc(&m->dhid, sizeof(float) * N * F));
@@ -215,40 +226,85 @@ inline void adam_bias_corrections(int64_t t, float* bc1, float* bc2) {
   *bc2 = (float)(1.0 - std::pow(0.999, (double)t));
 }
 
-int record_bucket(nlps_model* m, int bucket) {
+// ---- weight-gradient stream plumbing (no-ops when the model has none) ----
+enum { W_DW2 = 0, W_DW1 = 1, W_DWO = 2, W_DWQKV = 3, W_VOCAB = 4, W_JOIN = 5 };
+// the stream the next weight-gradient product goes to, ordered after everything enqueued on the main stream so far
+int wgrad_fork(nlps_model* m, cudaStream_t* out) {
+  if (!m->wstream) { *out = m->stream; return 0; }
+  NLPS_CUDA(cudaEventRecord(m->ev_fork, m->stream));
+  NLPS_CUDA(cudaStreamWaitEvent(m->wstream, m->ev_fork, 0));
+  *out = m->wstream;
+  return 0;
+}
+int wgrad_done(nlps_model* m, int kind) {
+  if (!m->wstream) return 0;
+  NLPS_CUDA(cudaEventRecord(m->ev_w[kind], m->wstream));
+  m->w_pending[kind] = true;
+  return 0;
+}
+// the main stream is about to overwrite what weight gradient `kind` read (or needs its result)
+int wgrad_need(nlps_model* m, int kind) {
+  if (!m->wstream || !m->w_pending[kind]) return 0;
+  NLPS_CUDA(cudaStreamWaitEvent(m->stream, m->ev_w[kind], 0));
+  m->w_pending[kind] = false;
+  return 0;
+}
+// everything on the weight-gradient stream so far is ordered before what the main stream does next
+int wgrad_join(nlps_model* m) {
+  if (!m->wstream) return 0;
+  NLPS_CUDA(cudaEventRecord(m->ev_w[W_JOIN], m->wstream));
+  NLPS_CUDA(cudaStreamWaitEvent(m->stream, m->ev_w[W_JOIN], 0));
+  for (bool& b : m->w_pending) b = false;
+  return 0;
+}
+
+int record_bucket(nlps_model* m, int bucket, bool on_wstream = false) {
+  // a bucket that holds weight gradients is complete when the weight-gradient stream has passed this point too
+  cudaStream_t rs = m->stream;
+  if (on_wstream && m->wstream && !(m->in_graph_body && !m->graph_external_events)) NLPS_TRY(wgrad_fork(m, &rs));
   if (m->in_graph_body) {
     // single-GPU captured step: nobody waits on the bucket events.  Deferred (data-parallel) captured step: the record
     // becomes an external event-record node, so the communication stream's cudaStreamWaitEvent after the graph launch
     // waits for this point of the replay.
     if (!m->graph_external_events) return 0;
-    NLPS_CUDA(cudaEventRecordWithFlags(m->bucket_ev[bucket], m->stream, cudaEventRecordExternal));
+    NLPS_CUDA(cudaEventRecordWithFlags(m->bucket_ev[bucket], rs, cudaEventRecordExternal));
     return 0;
   }
-  NLPS_CUDA(cudaEventRecord(m->bucket_ev[bucket], m->stream));
+  NLPS_CUDA(cudaEventRecord(m->bucket_ev[bucket], rs));
   return 0;
 }
 
-// layers L-1..0 and the embedding scatter, starting from dH in m->g0 (transformer.py:360-457)
+// layers L-1..0 and the embedding scatter, starting from dH in m->g0 (transformer.py:360-457).
+// Critical path on the main stream: LN2 bwd -> dz -> d(y1) -> LN1 bwd -> dctx -> attention bwd -> d(x_in); the four weight
+// gradients of a layer go to the weight-gradient stream as soon as their inputs exist (wgrad_fork) and the main stream
+// only waits for one of them right before it overwrites what that product read (wgrad_need).
 int backward_stack(nlps_model* m, nlps_cache* c) {
   const int E = m->E, F = m->F;
   const int N = (int)c->N;
   cudaStream_t st = m->stream;
+  cudaStream_t ws = st;
   const int prec = m->precision;
   const bool dropping = c->drop_p > 0.f;
+  float* g1b = m->wstream ? m->g1b : m->g1;            // one buffer set is enough without the second stream
+  float* gdropb = m->wstream ? m->gdropb : m->gdrop;
+  for (int k = 0; k < W_VOCAB; ++k) m->w_pending[k] = false;   // nothing of an earlier (possibly failed) pass is waited for
   for (int l = m->L - 1; l >= 0; --l) {
     const LayerOff& o = m->lo[l];
     const nlps_cache::L& a = c->layers[l];
     const float* x_in = l == 0 ? c->h0 : c->layers[l - 1].y2;
     // LN2 backward (+ dropout backward of the FFN branch)
     DropoutParams dpf = drop_for(m, c, l, 1);
-    NLPS_TRY(layernorm_backward(st, N, E, m->g0, a.r2, a.mean2, a.rstd2, m->P + o.ln2g, m->g1,
-                                dropping ? m->gdrop : nullptr, dropping ? &dpf : nullptr, m->G + o.ln2g,
+    NLPS_TRY(wgrad_need(m, W_DW2));                    // the layer above read d_f from these buffers
+    NLPS_TRY(layernorm_backward(st, N, E, m->g0, a.r2, a.mean2, a.rstd2, m->P + o.ln2g, g1b,
+                                dropping ? gdropb : nullptr, dropping ? &dpf : nullptr, m->G + o.ln2g,
                                 m->G + o.ln2b, m->ln_partial, m->G + o.b2));     // db2 = column sums of d_f ride along
-    const float* d_f = dropping ? m->gdrop : m->g1;
+    const float* d_f = dropping ? gdropb : g1b;
     {  // dW2 = hid^T d_f ; db2
       GemmArgs g = gemm_nn(F, E, N, a.hid, F, d_f, E, m->G + o.w2, E);
       g.trans_a = true;
-      NLPS_TRY(gemm_dispatch(st, prec, g));
+      NLPS_TRY(wgrad_fork(m, &ws));
+      NLPS_TRY(gemm_dispatch(ws, prec, g));
+      NLPS_TRY(wgrad_done(m, W_DW2));
     }
     bool db1_fused = false;
     {  // dz = (d_f W2^T) * (hid > 0)
@@ -260,23 +316,27 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
       static int fuse_db1 = -1;             // NLPS_FUSE_DB1=0: separate column-sum pass (A/B measurements)
       if (fuse_db1 < 0) { const char* e = getenv("NLPS_FUSE_DB1"); fuse_db1 = (e && e[0] == '0') ? 0 : 1; }
       if (fuse_db1 && prec == NLPS_PREC_TF32 && m->colsum32 != nullptr && gemm_tf32_colsum_fusable(g)) { g.colsum32_out = m->colsum32; db1_fused = true; }
+      NLPS_TRY(wgrad_need(m, W_DW1));                  // the layer above read dz from m->dhid
       NLPS_TRY(gemm_dispatch(st, prec, g));
     }
     {  // dW1 = y1^T dz ; db1
       GemmArgs g = gemm_nn(E, F, N, a.y1, E, m->dhid, F, m->G + o.w1, F);
       g.trans_a = true;
-      NLPS_TRY(gemm_dispatch(st, prec, g));
+      NLPS_TRY(wgrad_fork(m, &ws));
+      NLPS_TRY(gemm_dispatch(ws, prec, g));
+      NLPS_TRY(wgrad_done(m, W_DW1));
       if (db1_fused) NLPS_TRY(colsum(st, ceil_div(N, 32), F, m->colsum32, F, m->G + o.b1, m->colsum_scratch, colsum_tickets_for(m, F)));
       else NLPS_TRY(colsum(st, N, F, m->dhid, F, m->G + o.b1, m->colsum_scratch, colsum_tickets_for(m, F)));
     }
     {  // d(y1) = dz W1^T + d_r2
       GemmArgs g = gemm_nn(N, E, F, m->dhid, F, m->P + o.w1, F, m->g0, E);
       g.trans_b = true;
-      g.residual = m->g1; g.ldr = E;
+      g.residual = g1b; g.ldr = E;
       NLPS_TRY(gemm_dispatch(st, prec, g));
     }
     // LN1 backward (+ dropout backward of the attention branch)
     DropoutParams dpa = drop_for(m, c, l, 0);
+    NLPS_TRY(wgrad_need(m, W_DWO));                    // the layer above read d_a from these buffers
     NLPS_TRY(layernorm_backward(st, N, E, m->g0, a.r1, a.mean1, a.rstd1, m->P + o.ln1g, m->g1,
                                 dropping ? m->gdrop : nullptr, dropping ? &dpa : nullptr, m->G + o.ln1g,
                                 m->G + o.ln1b, m->ln_partial));
@@ -284,7 +344,9 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
     {  // dWo = ctx^T d_a
       GemmArgs g = gemm_nn(E, E, N, a.ctx, E, d_a, E, m->G + o.wo, E);
       g.trans_a = true;
-      NLPS_TRY(gemm_dispatch(st, prec, g));
+      NLPS_TRY(wgrad_fork(m, &ws));
+      NLPS_TRY(gemm_dispatch(ws, prec, g));
+      NLPS_TRY(wgrad_done(m, W_DWO));
     }
     bool delta_ready = false;
     {  // dctx = d_a Wo^T; the epilogue also forms delta = sum(dctx * ctx) per (token, head) when the product allows it
@@ -299,12 +361,15 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
       }
       NLPS_TRY(gemm_dispatch(st, prec, g));
     }
+    NLPS_TRY(wgrad_need(m, W_DWQKV));                  // the layer above read m->dqkv
     NLPS_TRY(attention_backward(st, prec, c->B, c->S, m->h, m->d, a.qkv, c->x_flat, c->fnp, a.ctx, a.lse, m->dctx,
                                 m->delta, m->dqkv, delta_ready));
     {  // dWqkv = x_in^T dqkv
       GemmArgs g = gemm_nn(E, 3 * E, N, x_in, E, m->dqkv, 3 * E, m->G + o.wqkv, 3 * E);
       g.trans_a = true;
-      NLPS_TRY(gemm_dispatch(st, prec, g));
+      NLPS_TRY(wgrad_fork(m, &ws));
+      NLPS_TRY(gemm_dispatch(ws, prec, g));
+      NLPS_TRY(wgrad_done(m, W_DWQKV));
     }
     {  // dx_in = dqkv Wqkv^T + d_r1
       GemmArgs g = gemm_nn(N, E, 3 * E, m->dqkv, 3 * E, m->P + o.wqkv, 3 * E, m->g0, E);
@@ -312,9 +377,10 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
       g.residual = m->g1; g.ldr = E;
       NLPS_TRY(gemm_dispatch(st, prec, g));
     }
-    NLPS_TRY(record_bucket(m, 1 + (m->L - 1 - l)));
+    NLPS_TRY(record_bucket(m, 1 + (m->L - 1 - l), /*on_wstream=*/true));
   }
   NLPS_TRY(embed_backward(st, N, E, m->V, c->x_flat, m->g0, m->G + m->off_We, m->iscratch));
+  NLPS_TRY(wgrad_join(m));                             // every gradient is complete on the main stream from here on
   NLPS_TRY(record_bucket(m, m->L + 1));
   return 0;
 }
@@ -449,9 +515,18 @@ int nlps_create(const nlps_config* cfg, int device, nlps_model** out) {
     // gets a stream of its own -- a BLOCKING one: it stays ordered with everything the caller does on stream 0.
     const char* e = getenv("NLPS_GRAPH");
     m->graph_mode = (e && e[0] == '0') ? 0 : 1;
+    int pri_least = 0, pri_greatest = 0;
+    NLPS_CUDA(cudaDeviceGetStreamPriorityRange(&pri_least, &pri_greatest));
     if (m->graph_mode) {
-      NLPS_CUDA(cudaStreamCreate(&m->own_stream));
+      NLPS_CUDA(cudaStreamCreateWithPriority(&m->own_stream, cudaStreamDefault, pri_greatest));
       m->stream = m->own_stream;
+    }
+    // NLPS_WGRAD_STREAM=0 keeps the weight gradients on the main stream (A/B measurements, bitwise-equality test)
+    const char* w = getenv("NLPS_WGRAD_STREAM");
+    if (!(w && w[0] == '0')) {
+      NLPS_CUDA(cudaStreamCreateWithPriority(&m->wstream, cudaStreamNonBlocking, pri_least));
+      NLPS_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+      for (auto& e : m->ev_w) NLPS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
   }
   m->bucket_ev.resize(m->buckets.size());
@@ -467,7 +542,8 @@ int nlps_destroy(nlps_model* m) {
   cudaDeviceSynchronize();
   for (nlps_cache* c : m->pool) { if (c->base) cudaFree(c->base); delete c; }
   float* bufs[] = {m->P, m->G, m->M, m->Vv, m->pe, m->g0, m->g1, m->gdrop, m->dctx, m->dqkv, m->dhid, m->delta,
-                   m->row_loss, m->rows_tmp, m->ln_partial, m->colsum_scratch, m->sumsq_scratch, m->scalars, m->colsum32};
+                   m->row_loss, m->rows_tmp, m->ln_partial, m->colsum_scratch, m->sumsq_scratch, m->scalars, m->colsum32,
+                   m->g1b, m->gdropb};
   for (float* b : bufs) if (b) cudaFree(b);
   if (m->iscratch) cudaFree(m->iscratch);
   if (m->err_flag) cudaFree(m->err_flag);
@@ -475,6 +551,9 @@ int nlps_destroy(nlps_model* m) {
   if (m->hyper) cudaFree(m->hyper);
   drop_step_graphs(m);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  if (m->wstream) cudaStreamDestroy(m->wstream);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  for (auto& e : m->ev_w) if (e) cudaEventDestroy(e);
   for (auto& e : m->bucket_ev) cudaEventDestroy(e);
   if (m->aux_ev) cudaEventDestroy(m->aux_ev);
   delete m;
@@ -758,7 +837,10 @@ int nlps_backward(nlps_model* m, nlps_cache* c, const float* d_dlogits, int64_t 
   {  // dW_vocab = H^T dlogits ; db_vocab                               (transformer.py:352-353)
     GemmArgs g = gemm_nn(E, m->V, N, h_final, E, d_dlogits, ldd, m->G + m->off_Wvocab, m->ldV);
     g.trans_a = true;
-    NLPS_TRY(gemm_dispatch(st, m->precision, g));
+    cudaStream_t ws = st;
+    NLPS_TRY(wgrad_fork(m, &ws));                      // off the critical path: weight-gradient stream
+    NLPS_TRY(gemm_dispatch(ws, m->precision, g));
+    NLPS_TRY(wgrad_done(m, W_VOCAB));
     NLPS_TRY(colsum(st, N, m->V, d_dlogits, ldd, m->G + m->off_bvocab, m->colsum_scratch, colsum_tickets_for(m, m->V)));
   }
   {  // dH = dlogits W_vocab^T                                          (:355)
@@ -766,7 +848,7 @@ int nlps_backward(nlps_model* m, nlps_cache* c, const float* d_dlogits, int64_t 
     g.trans_b = true;
     NLPS_TRY(gemm_dispatch(st, m->precision, g));
   }
-  NLPS_TRY(record_bucket(m, 0));
+  NLPS_TRY(record_bucket(m, 0, /*on_wstream=*/true));
   return backward_stack(m, c);
 }
 

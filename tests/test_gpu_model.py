@@ -523,3 +523,45 @@ np.savez(sys.argv[1], **{k: np.asarray(g[k].get()) for k in ("Wq", "Wk", "Wv", "
         assert np.isfinite(b).all()
         # delta itself moves by ~1e-7 relative; dS is then rounded onto the TF32 grid, where a flipped rounding is 2^-11
         assert np.linalg.norm(a - b) <= 5e-4 * np.linalg.norm(a), (k, np.linalg.norm(a - b) / np.linalg.norm(a))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+def test_weight_gradient_stream_is_bitwise_the_single_stream_step(precision):
+    """dW2 / dW1 / dWo / dWqkv / dW_vocab run on a second stream, ordered by events against the buffers they read
+    (NLPS_WGRAD_STREAM=0 keeps them on the main stream).  Same kernels, same arguments, one owner per output: fused steps
+    (eager, captured, replayed), the unfused forward/backward API and the last-token driver step must all give the same
+    bits, dropout on."""
+    import subprocess, sys, os, json
+    code = r"""
+import json, sys, hashlib, numpy as np
+sys.path.insert(0, %r)
+from nlpscratch_b200 import Transformer
+from nlpscratch_b200.array import DeviceArray
+np.random.seed(5)
+m = Transformer(300, 128, 4, 256, 3, 96, dropout_p=0.1, precision=%r)
+rng = np.random.default_rng(1)
+xh = [rng.integers(1, 300, (6, 96)).astype(np.int32) for _ in range(2)]
+xh[1][2, 60:] = 0
+xs = [DeviceArray.from_host(a) for a in xh]
+ys = [DeviceArray.from_host(rng.integers(0, 300, (6, 96)).astype(np.int32)) for _ in range(2)]
+losses = []
+for i in range(8):
+    losses.append(float(m.train_step(xs[i %% 2], ys[i %% 2], learning_rate=1e-3, clip_grad_norm=1.0)).hex())
+logits, cache = m.forward(xh[0])                      # the unfused API
+loss, dl = m.calculate_loss_dlogits(logits, ys[0])
+g = m.backward(cache, dl)
+gh = hashlib.sha256(b"".join(np.ascontiguousarray(g[k].get()).tobytes() for k in sorted(g))).hexdigest()
+m.step(g, 1e-3)
+yl = rng.integers(0, 300, (6,)).astype(np.int32)      # the driver's last-token step
+losses.append(float(m.train_step_last_token(xh[1], yl, learning_rate=1e-3, clip_grad_norm=1.0)).hex())
+p = m.get_params()
+print(json.dumps({"losses": losses, "grads": gh, "params": hashlib.sha256(b"".join(np.ascontiguousarray(p[k]).tobytes() for k in sorted(p))).hexdigest()}))
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), precision)
+    out = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, NLPS_WGRAD_STREAM=flag)
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        out[flag] = json.loads(res.stdout.strip().splitlines()[-1])
+    assert out["0"] == out["1"]
