@@ -234,6 +234,9 @@ int layernorm_backward(cudaStream_t st, int64_t rows, int E, const float* dy, co
                        float* dbias = nullptr);   // optional: column sums of the branch gradient leaving the kernel (dx_dropped, else dx)
 size_t layernorm_backward_scratch_floats(int E);
 // rowstat != nullptr: per-32-column {max, sum exp} blocks from the vocab-head GEMM epilogue (see GemmArgs::rowstat_out)
+int softmax_xent_rows(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V, float inv,
+                      float* dlogits, int64_t ldd, float* row_loss);
+int row_loss_mean(cudaStream_t st, const float* row_loss, int64_t rows, float* loss);
 int softmax_xent_stats(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
                        float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss, const float2* rowstat);
 int softmax_xent(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,

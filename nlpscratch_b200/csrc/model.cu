@@ -83,8 +83,8 @@ struct nlps_model {
   // split-K reducers).  ev_fork: main -> wstream; ev_w[k]: "the k-th kind of weight gradient has been formed" (guards the
   // buffers it read); w_pending[k]: recorded in this pass.
   cudaStream_t wstream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_w[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  bool w_pending[6] = {false, false, false, false, false, false};
+  cudaEvent_t ev_fork = nullptr, ev_w[8] = {};
+  bool w_pending[8] = {};
   float *delta = nullptr, *row_loss = nullptr, *small = nullptr, *rows_tmp = nullptr;
   int32_t* iscratch = nullptr;
   int64_t rows_tmp_cap = 0;
@@ -227,7 +227,7 @@ inline void adam_bias_corrections(int64_t t, float* bc1, float* bc2) {
 }
 
 // ---- weight-gradient stream plumbing (no-ops when the model has none) ----
-enum { W_DW2 = 0, W_DW1 = 1, W_DWO = 2, W_DWQKV = 3, W_VOCAB = 4, W_JOIN = 5 };
+enum { W_DW2 = 0, W_DW1 = 1, W_DWO = 2, W_DWQKV = 3, W_VOCAB = 4, W_JOIN = 5, W_XENT = 6 };
 // the stream the next weight-gradient product goes to, ordered after everything enqueued on the main stream so far
 int wgrad_fork(nlps_model* m, cudaStream_t* out) {
   if (!m->wstream) { *out = m->stream; return 0; }
@@ -919,12 +919,43 @@ int nlps_adam_t(nlps_model* m, int64_t* t, int set, int64_t value) {
 // the fused step as it always ran: forward, loss (dlogits in place), backward, clip, update
 static int train_step_body(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_y, float lr,
                            float max_norm, float grad_scale, int defer_update, float* d_loss) {
+  // Row-chunked vocabulary head (needs the second stream): the cross-entropy of chunk k (bandwidth-bound, in place) runs on
+  // the second stream while the tensor pipe forms the logits of chunk k+1.  Rows are independent in both kernels and the
+  // loss is reduced over all rows afterwards, so the bits equal the one-shot form.  OPT-IN (NLPS_VOCAB_CHUNKS=4): same-box
+  // A/B at c4 and c3 showed no gain (13.17 vs 13.17 ms; 2, 4, 8 chunks) -- the K = 512 vocabulary product already writes
+  // 2.4 TB/s, so the cross-entropy next to it only trades places with it on the memory system.
+  static int want_chunks = -1;
+  if (want_chunks < 0) { const char* e = getenv("NLPS_VOCAB_CHUNKS"); want_chunks = e ? std::max(1, atoi(e)) : 1; }
+  static int fuse_ce_on = -1;
+  if (fuse_ce_on < 0) { const char* e = getenv("NLPS_FUSE_CE"); fuse_ce_on = (e && e[0] == '1') ? 1 : 0; }
+  const int64_t chunk_rows = round_up(ceil_div(c->N, (int64_t)want_chunks), 256);
+  if (m->wstream != nullptr && want_chunks > 1 && !fuse_ce_on && chunk_rows < c->N) {
+    NLPS_TRY(nlps_forward(m, c, d_x, xs, 1, nullptr, 0));
+    NLPS_CUDA(cudaSetDevice(m->device));
+    NLPS_TRY(ensure_rows_tmp(m, c->N));
+    const float* h_final = m->L > 0 ? c->layers.back().y2 : c->h0;
+    const float inv = (float)((double)grad_scale / (double)c->N);
+    for (int64_t r0 = 0; r0 < c->N; r0 += chunk_rows) {
+      const int64_t n = std::min<int64_t>(chunk_rows, c->N - r0);
+      float* lg = c->logits + r0 * m->ldV;
+      GemmArgs g = gemm_nn((int)n, m->V, m->E, h_final + r0 * m->E, m->E, m->P + m->off_Wvocab, m->ldV, lg, m->ldV);
+      g.bias = m->P + m->off_bvocab;                                     // logits = H W_vocab + b_vocab  (:191)
+      NLPS_TRY(gemm_dispatch(m->stream, m->precision, g));
+      cudaStream_t ws = m->stream;
+      NLPS_TRY(wgrad_fork(m, &ws));
+      NLPS_TRY(softmax_xent_rows(ws, lg, m->ldV, d_y + r0, n, m->V, inv, lg, m->ldV, m->rows_tmp + r0));
+    }
+    NLPS_TRY(wgrad_done(m, W_XENT));
+    NLPS_TRY(wgrad_need(m, W_XENT));                                     // the second stream is in order: this covers every chunk
+    NLPS_TRY(row_loss_mean(m->stream, m->rows_tmp, c->N, d_loss ? d_loss : m->scalars + 3));
+  } else {
   NLPS_TRY(nlps_forward(m, c, d_x, xs, 0, nullptr, 0));
   // dlogits overwrite the logits in place: 8V bytes of HBM traffic per token for the loss
   NLPS_CUDA(cudaSetDevice(m->device));
   NLPS_TRY(ensure_rows_tmp(m, c->N));
   NLPS_TRY(softmax_xent_stats(m->stream, c->logits, m->ldV, d_y, c->N, m->V, grad_scale, d_loss ? d_loss : m->scalars + 3, c->logits,
                               m->ldV, m->rows_tmp, c->rowstat_valid ? c->rowstat : nullptr));
+  }
   c->has_logits = false;
   c->rowstat_valid = false;
   NLPS_TRY(nlps_backward(m, c, c->logits, m->ldV));

@@ -565,6 +565,22 @@ int softmax_xent(cudaStream_t st, const float* logits, int64_t ld, const int32_t
   return 0;
 }
 
+// the two halves of softmax_xent for a row-chunked pipeline: dlogits + per-row losses of `rows` rows with an explicit
+// factor (grad_scale / total rows), then the mean over all rows -- same kernels, same bits as the one-call form
+int softmax_xent_rows(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V, float inv,
+                      float* dlogits, int64_t ldd, float* row_loss) {
+  if (rows <= 0) return 0;
+  const int vec_ok = (V % 4 == 0 && ld % 4 == 0 && ldd % 4 == 0 && aligned16(logits) && aligned16(dlogits)) ? 1 : 0;
+  xent_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, ld, y, V, inv, dlogits, ldd, row_loss, vec_ok);
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+int row_loss_mean(cudaStream_t st, const float* row_loss, int64_t rows, float* loss) {
+  sum_to_scalar_kernel<<<1, 1024, 0, st>>>(row_loss, rows, (float)(1.0 / (double)rows), loss);
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+
 int softmax_xent_stats(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
                        float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss, const float2* rowstat) {
   const bool vec_ok = V % 4 == 0 && ld % 4 == 0 && ldd % 4 == 0 && aligned16(logits) && aligned16(dlogits);
