@@ -254,6 +254,8 @@ int embed_forward(cudaStream_t st, int B, int S, int E, int V, const int32_t* x,
                   const float* We, const float* pe, float* out, int32_t* x_flat, int32_t* err_flag);
 int embed_backward(cudaStream_t st, int64_t N, int E, int V, const int32_t* x_flat, const float* dh,
                    float* dWe, int32_t* scratch_i32);
+int embed_backward_sort(cudaStream_t st, int64_t N, int V, const int32_t* x_flat, int32_t* scratch_i32);   // ids only
+int embed_backward_apply(cudaStream_t st, int64_t N, int E, int V, const float* dh, float* dWe, const int32_t* scratch_i32);
 size_t embed_backward_scratch_ints(int64_t N, int V);
 int scatter_rows(cudaStream_t st, int B, int S, int E, const int32_t* t, const float* rows, float* out);
 

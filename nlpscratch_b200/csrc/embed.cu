@@ -220,8 +220,9 @@ size_t embed_backward_scratch_ints(int64_t N, int V) {
   return n;
 }
 
-int embed_backward(cudaStream_t st, int64_t N, int E, int V, const int32_t* x_flat, const float* dh, float* dWe,
-                   int32_t* scratch) {
+// Two halves: the counting sort of the ids depends on x only (it can run long before dH exists, on another stream); the
+// scatter reads its result.  embed_backward = sort + apply.
+int embed_backward_sort(cudaStream_t st, int64_t N, int V, const int32_t* x_flat, int32_t* scratch) {
   int32_t* count = scratch;
   int32_t* start = scratch + (V + 1);
   int32_t* order = scratch + 2 * ((int64_t)V + 1);
@@ -251,10 +252,23 @@ int embed_backward(cudaStream_t st, int64_t N, int E, int V, const int32_t* x_fl
       NLPS_LAUNCH_CHECK();
     }
   }
+  return 0;
+}
+
+int embed_backward_apply(cudaStream_t st, int64_t N, int E, int V, const float* dh, float* dWe, const int32_t* scratch) {
+  (void)N;
+  const int32_t* start = scratch + (V + 1);
+  const int32_t* order = scratch + 2 * ((int64_t)V + 1);
   const int vec = (E % 4 == 0 && aligned16(dh) && aligned16(dWe)) ? 1 : 0;
   scatter_sum_kernel<<<(unsigned)ceil_div(V, 8), 256, 0, st>>>(V, E, start, order, dh, dWe, vec);
   NLPS_LAUNCH_CHECK();
   return 0;
+}
+
+int embed_backward(cudaStream_t st, int64_t N, int E, int V, const int32_t* x_flat, const float* dh, float* dWe,
+                   int32_t* scratch) {
+  NLPS_TRY(embed_backward_sort(st, N, V, x_flat, scratch));
+  return embed_backward_apply(st, N, E, V, dh, dWe, scratch);
 }
 
 int scatter_rows(cudaStream_t st, int B, int S, int E, const int32_t* t, const float* rows, float* out) {

@@ -227,7 +227,7 @@ inline void adam_bias_corrections(int64_t t, float* bc1, float* bc2) {
 }
 
 // ---- weight-gradient stream plumbing (no-ops when the model has none) ----
-enum { W_DW2 = 0, W_DW1 = 1, W_DWO = 2, W_DWQKV = 3, W_VOCAB = 4, W_JOIN = 5, W_XENT = 6 };
+enum { W_DW2 = 0, W_DW1 = 1, W_DWO = 2, W_DWQKV = 3, W_VOCAB = 4, W_JOIN = 5, W_XENT = 6, W_SORT = 7 };
 // the stream the next weight-gradient product goes to, ordered after everything enqueued on the main stream so far
 int wgrad_fork(nlps_model* m, cudaStream_t* out) {
   if (!m->wstream) { *out = m->stream; return 0; }
@@ -288,6 +288,16 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
   float* g1b = m->wstream ? m->g1b : m->g1;            // one buffer set is enough without the second stream
   float* gdropb = m->wstream ? m->gdropb : m->gdrop;
   for (int k = 0; k < W_VOCAB; ++k) m->w_pending[k] = false;   // nothing of an earlier (possibly failed) pass is waited for
+  // the counting sort of the token ids for the embedding scatter depends on x only: on the second stream it is done long
+  // before dH of layer 0 exists instead of sitting at the very end of the step (NLPS_EARLY_SORT=0: A/B)
+  static int early_sort = -1;
+  if (early_sort < 0) { const char* e = getenv("NLPS_EARLY_SORT"); early_sort = (e && e[0] == '0') ? 0 : 1; }
+  const bool sorted_early = m->wstream != nullptr && early_sort;
+  if (sorted_early) {
+    NLPS_TRY(wgrad_fork(m, &ws));
+    NLPS_TRY(embed_backward_sort(ws, N, m->V, c->x_flat, m->iscratch));
+    NLPS_TRY(wgrad_done(m, W_SORT));
+  }
   for (int l = m->L - 1; l >= 0; --l) {
     const LayerOff& o = m->lo[l];
     const nlps_cache::L& a = c->layers[l];
@@ -379,7 +389,12 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
     }
     NLPS_TRY(record_bucket(m, 1 + (m->L - 1 - l), /*on_wstream=*/true));
   }
-  NLPS_TRY(embed_backward(st, N, E, m->V, c->x_flat, m->g0, m->G + m->off_We, m->iscratch));
+  if (sorted_early) {
+    NLPS_TRY(wgrad_need(m, W_SORT));
+    NLPS_TRY(embed_backward_apply(st, N, E, m->V, m->g0, m->G + m->off_We, m->iscratch));
+  } else {
+    NLPS_TRY(embed_backward(st, N, E, m->V, c->x_flat, m->g0, m->G + m->off_We, m->iscratch));
+  }
   NLPS_TRY(wgrad_join(m));                             // every gradient is complete on the main stream from here on
   NLPS_TRY(record_bucket(m, m->L + 1));
   return 0;
@@ -524,7 +539,8 @@ int nlps_create(const nlps_config* cfg, int device, nlps_model** out) {
     // NLPS_WGRAD_STREAM=0 keeps the weight gradients on the main stream (A/B measurements, bitwise-equality test)
     const char* w = getenv("NLPS_WGRAD_STREAM");
     if (!(w && w[0] == '0')) {
-      NLPS_CUDA(cudaStreamCreateWithPriority(&m->wstream, cudaStreamNonBlocking, pri_least));
+      const char* pr = getenv("NLPS_WGRAD_PRIO");          // "same": no priority difference between the two streams (A/B)
+      NLPS_CUDA(cudaStreamCreateWithPriority(&m->wstream, cudaStreamNonBlocking, (pr && pr[0] == 's') ? pri_greatest : pri_least));
       NLPS_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
       for (auto& e : m->ev_w) NLPS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
