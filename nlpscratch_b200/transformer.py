@@ -28,6 +28,9 @@ from . import _lib
 from . import array as _array
 from .array import DeviceArray, b200np
 
+import os as _os
+_STATIC_INPUTS_OFF = _os.environ.get("NLPS_STATIC_INPUTS", "1") == "0"
+
 PARAM_NAMES = ("We", "Wq", "Wk", "Wv", "Wo", "W1", "W2", "b1", "b2", "W_vocab", "b_vocab",
                "ln1_gamma", "ln1_beta", "ln2_gamma", "ln2_beta")
 # key order of the dict returned by the reference's two backward variants
@@ -402,6 +405,7 @@ class Transformer:
         if yd.bounds is not None and not (0 <= yd.bounds[0] and yd.bounds[1] < self.vocab_size):
             raise IndexError("target id out of bounds for %d classes" % self.vocab_size)
         yd = yd.contiguous()
+        xd, yd = self._static_inputs(xd, yd)
         B, S = xd.shape
         ch = C.c_void_p()
         _lib.call("nlps_cache_create", self._h, C.c_int(B), C.c_int(S), C.byref(ch))
@@ -414,6 +418,25 @@ class Transformer:
         object.__setattr__(self, "_last_cache", cache)       # keep x/y/activations alive until the next step
         object.__setattr__(self, "_last_y", yd)
         return DeviceScalar(loss)
+
+    def _static_inputs(self, xd: DeviceArray, yd: DeviceArray):
+        """A captured CUDA graph replays fixed addresses, and ``nlps_train_step`` keys its graphs on the id buffers.  Every
+        batch of a shape is therefore copied (two device copies of 4*B*S bytes, ordered before the step) into one pair of
+        staging buffers per model, so that fresh batches from a loader replay the same graph instead of running eagerly
+        (and instead of a capture per distinct buffer).  NLPS_STATIC_INPUTS=0 passes the caller's buffers through."""
+        if _STATIC_INPUTS_OFF:
+            return xd, yd
+        st = self.__dict__.get("_stage")
+        if st is None or st[0].shape != xd.shape:
+            st = (DeviceArray.empty(xd.shape, np.int32), DeviceArray.empty(xd.shape, np.int32))
+            object.__setattr__(self, "_stage", st)
+        sx, sy = st
+        if xd.ptr != sx.ptr:
+            _array._strided_copy(xd, sx)
+        if yd.ptr != sy.ptr:
+            _array._strided_copy(yd, sy)
+        sx.bounds, sy.bounds = xd.bounds, yd.bounds
+        return sx, sy
 
     def train_step_last_token(self, xb, yb, lens=None, learning_rate=1e-4, clip_grad_norm: Optional[float] = 1.0,
                               grad_scale: float = 1.0, defer_update: bool = False) -> DeviceScalar:
