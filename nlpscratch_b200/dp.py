@@ -132,6 +132,13 @@ class DataParallel:
         return loss
 
 
+def save_checkpoint_rank0(dp: "DataParallel", filename: str):
+    """Replicas are identical after every step, so rank 0 alone writes the resume checkpoint; everyone waits for it."""
+    if dp.rank == 0:
+        dp.model.save_checkpoint(filename)
+    dp._dist.barrier(group=dp.group)
+
+
 def _merge_adjacent(ranges):
     out = []
     for first, cnt in sorted(ranges):

@@ -490,6 +490,30 @@ class Transformer:
         with open(filename, "rb") as f:
             self.load_params(pickle.load(f))
 
+    def save_checkpoint(self, filename):
+        """Resume checkpoint (the reference only has the parameter pickle of ``save``, transformer.py:551-572):
+        the reference-format parameter dict plus Adam's moments and step count, all as host float32 arrays."""
+        state = {"format": "nlpscratch_b200.checkpoint.v1",
+                 "params": self.get_params(),
+                 "m": {k: np.ascontiguousarray(a.get()) for k, a in self.m.items()},
+                 "v": {k: np.ascontiguousarray(a.get()) for k, a in self.v.items()},
+                 "adam_t": int(self.adam_t)}
+        with open(filename, "wb") as f:
+            pickle.dump(state, f)
+
+    def load_checkpoint(self, filename):
+        """Inverse of ``save_checkpoint``; a plain reference-format pickle (``save``) loads as parameters with fresh Adam state."""
+        with open(filename, "rb") as f:
+            state = pickle.load(f)
+        if "params" not in state:
+            self.load_params(state)
+            return
+        self.load_params(state["params"])
+        for k in PARAM_NAMES:
+            self._view(_lib.BUF_M, k).set(np.asarray(state["m"][k], dtype=np.float32))
+            self._view(_lib.BUF_V, k).set(np.asarray(state["v"][k], dtype=np.float32))
+        self.adam_t = int(state["adam_t"])
+
     def close(self):
         h = self.__dict__.get("_h")
         if h is not None:

@@ -565,3 +565,37 @@ print(json.dumps({"losses": losses, "grads": gh, "params": hashlib.sha256(b"".jo
         assert res.returncode == 0, res.stderr[-2000:]
         out[flag] = json.loads(res.stdout.strip().splitlines()[-1])
     assert out["0"] == out["1"]
+
+
+@pytest.mark.gpu
+def test_resume_checkpoint_restores_parameters_and_adam_state(tmp_path):
+    """save_checkpoint / load_checkpoint: a model restored from the checkpoint continues bit for bit like the
+    one that wrote it (Adam moments and step count included); a reference-format ``save`` pickle loads with fresh Adam."""
+    from nlpscratch_b200 import Transformer
+    cfg = (97, 64, 2, 128, 2, 24)
+    rng = np.random.default_rng(0)
+    x = rng.integers(1, 97, (4, 24)).astype(np.int32)
+    y = rng.integers(0, 97, (4, 24)).astype(np.int32)
+    np.random.seed(1)
+    a = Transformer(*cfg, dropout_p=0.0, precision="fp32")
+    for _ in range(2):
+        a.train_step(x, y, 1e-3, 1.0)
+    ck, ref_fmt = os.path.join(tmp_path, "ck.pkl"), os.path.join(tmp_path, "ref.pkl")
+    a.save_checkpoint(ck)
+    a.save(ref_fmt)
+    for _ in range(2):
+        a.train_step(x, y, 1e-3, 1.0)
+    want = a.get_params()
+    np.random.seed(2)
+    b = Transformer(*cfg, dropout_p=0.0, precision="fp32")
+    b.load_checkpoint(ck)
+    assert b.adam_t == 2
+    for _ in range(2):
+        b.train_step(x, y, 1e-3, 1.0)
+    got = b.get_params()
+    for k in want:
+        assert np.array_equal(want[k], got[k]), k
+    b.load_checkpoint(ref_fmt)                      # reference-format pickle: parameters only, Adam restarts
+    assert b.adam_t == 0
+    assert float(np.abs(b.m["We"].get()).max()) == 0.0
+    a.close(); b.close()
