@@ -67,6 +67,21 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.proc, self.lines, self.index = None, [], index
+        self.begin, self.end = 0, None
+
+    # nvidia-smi's start-up and tear-down (NVML initialisation) can stall CUDA calls of other processes for tens of
+    # milliseconds, so the sampler is started BEFORE the warm-up and stopped AFTER the last timed leg; only the samples
+    # taken between mark_begin() and mark_end() -- the timed region -- are reported.
+    def wait_ready(self, seconds=3.0):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < seconds:
+            time.sleep(0.02)
+
+    def mark_begin(self):
+        self.begin = len(self.lines)
+
+    def mark_end(self):
+        self.end = len(self.lines)
 
     def start(self):
         try:
@@ -91,7 +106,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        window = self.lines[self.begin:self.end] if self.end is not None else self.lines[self.begin:]
+        if not window:                       # a timed region shorter than one sampling period: nearest samples
+            window = self.lines[max(0, self.begin - 1):(self.end + 1 if self.end is not None else None)]
+        for ln in window:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -227,24 +245,29 @@ def run_ours(args, wl):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                      # before the warm-up: its start-up must not fall into the timed region
     for i in range(args.warmup):
         loss = step(i)
     fence()
     first_loss = float(loss) if args.warmup else None
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.wait_ready()
     model.launch_count(reset=True)
+    if dp is not None:
+        dp.launches = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
+    sampler.mark_begin()
     ev0.record()
     for i in range(args.steps):
         loss = step(i)
     ev1.record()
     fence()
+    sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     launches = model.launch_count() + (dp.launches if dp else 0)
-    clocks = sampler.stop() if rank == 0 else None
     last_loss = float(loss)
     if distributed:
         t = torch.tensor([ms], device="cuda")
@@ -254,6 +277,7 @@ def run_ours(args, wl):
     value = tokens / (ms * 1e-3)
     if args.quick:
         if rank == 0:
+            sampler.stop()
             print(json.dumps({"metric": METRIC, "value": value, "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
                               "quick": True, "loss_last": last_loss}), flush=True)
         if distributed:
@@ -307,6 +331,7 @@ def run_ours(args, wl):
                         "frac_of_tf32_peak": fpt * value / world / 1e12 / tf32_peak,
                         "tf32_peak_tflops": tf32_peak,
                         "peak_note": "TF32 dense = 1/2 of the %s sustained BF16 peak in MEASURED_PEAKS.json" % peaks["source"]}
+    clocks = sampler.stop() if rank == 0 else None      # after the last GPU-timed leg (see ClockSampler)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample(wl)
