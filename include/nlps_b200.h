@@ -96,8 +96,10 @@ int nlps_set_training(nlps_model* m, int training);          /* train()/eval(), 
 int nlps_set_dropout(nlps_model* m, float p, uint64_t seed);
 int nlps_sync(nlps_model* m);
 
-/* flat buffers: [W_vocab b_vocab | layer L-1 ... layer 0 | We] -- backward-completion order,
- * so that data-parallel buckets become ready front to back. */
+/* flat buffers (params, grads, Adam m, Adam v): [We | layer 0 ... layer L-1 | W_vocab b_vocab], every tensor 256-B
+ * aligned.  The gradient BUCKETS (nlps_bucket_range) enumerate contiguous ranges of that buffer in
+ * backward-completion order -- [vocab] [layer L-1] ... [layer 0] [We] -- so that data-parallel reductions can start
+ * as backward finishes them. */
 int nlps_flat_size(const nlps_model* m, int64_t* n_floats);
 int nlps_flat_ptr(nlps_model* m, int which_buf, void** d_ptr);
 int nlps_param_view(nlps_model* m, int which_buf, int param_id, nlps_view* out);
@@ -154,7 +156,30 @@ int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t x_
 int nlps_train_step_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t x_row_stride,
                                const int32_t* d_t, const int32_t* d_y, float lr, float max_norm,
                                float grad_scale, int defer_update, float* d_loss);
-int nlps_launch_count(nlps_model* m, int64_t* launches, int reset);  /* kernels launched so far */
+int nlps_launch_count(nlps_model* m, int64_t* launches, int reset);  /* kernels launched so far (process-wide counter) */
+
+/* Dispatch statistics (process-wide): counts[k] = calls served by implementation k since the last reset, k =
+ * 0 tcgen05 CTA-pair GEMM, 1 tcgen05 single-CTA GEMM, 2 CUDA-core FP32 GEMM, 3 3xTF32 GEMM, 4 tcgen05 attention forward,
+ * 5 tcgen05 attention backward, 6 mma.sync attention, 7 CUDA-core FP32 attention, 8 first-generation tcgen05 attention.
+ * The parity tests use it to assert that the benchmarked kernels -- not a fallback -- produced the checked numbers. */
+int nlps_kernel_stats(int64_t* counts, int n, int reset);
+
+/* Error word of the asynchronous kernels, read and cleared (synchronises the model's stream).  The reference raises
+ * IndexError from NumPy's fancy indexing at once; kernels cannot, so they clamp the id, raise a bit, and the host turns
+ * it into IndexError at its next synchronisation point (float(loss), synchronize(), get()):
+ *   bit 0 (1): token id outside [-V, V) in We[x]                       (transformer.py:114)
+ *   bit 1 (2): target id outside [-V, V) in log_probs[rows, y]         (transformer.py:538-546) */
+int nlps_check_errors(nlps_model* m, int* flags);
+
+/* Transformer._dropout, transformer.py:102-108.  The reference draws its keep-masks from NumPy's global generator; here a
+ * mask is the pure function Philox4x32-10(key = seed; counter = element >> 3, layer*2 + branch, forward-call counter)
+ * compared with round(keep * 2^16) per 16-bit field, evaluated in the forward epilogue and again in backward.
+ * nlps_dropout_counter reads / sets the forward-call counter (the `step` of the next forward; part of a resume
+ * checkpoint); nlps_dropout_mask writes the keep decisions (1.0 / 0.0) of n consecutive elements of the (B*S, E) tensor at
+ * (layer, branch: 0 attention output, 1 FFN output) for forward call `step` -- the hook the parity tests use to replay the
+ * masks inside the CPU oracle. */
+int nlps_dropout_counter(nlps_model* m, int64_t* value, int set, int64_t new_value);
+int nlps_dropout_mask(nlps_model* m, int layer, int which, int64_t step, int64_t n, float* d_out);
 
 /* ---- stand-alone operators (tests, the array shim and the benchmarks call these) --------- */
 /* C[M,N] = op(A)[M,K] * op(B)[K,N] (+bias[N]) (relu) (*gate>0) (+residual) ; trans flags say the
@@ -195,6 +220,9 @@ int nlps_strided_copy(void* stream, int elem_size, int ndim, const int64_t* shap
                       const void* d_src, const int64_t* src_stride, void* d_dst, const int64_t* dst_stride);
 int nlps_gather_rows(void* stream, int elem_size, int64_t n_out, int64_t row_elems, const void* d_src,
                      int64_t src_row_stride, const int32_t* d_index, int64_t n_src, void* d_dst);
+/* H[idx, t, :] on a dense (n0, n1, row_elems) source, each index wrapped on its own axis (utils/train.py:113-115) */
+int nlps_gather_rows2(void* stream, int elem_size, int64_t n_out, int64_t row_elems, const void* d_src, int64_t n0,
+                      int64_t n1, const int32_t* d_i0, const int32_t* d_i1, void* d_dst);
 int nlps_gather_last(void* stream, int B, int S, int E, const float* d_h, const int32_t* d_t, float* d_out);
 int nlps_count_nonzero_rows(void* stream, int64_t rows, int64_t cols, const int32_t* d_x,
                             int64_t row_stride, int32_t* d_out);

@@ -303,12 +303,16 @@ class DeviceArray:
                 raise IndexError("shape mismatch: indexing arrays could not be broadcast together")
             src = self.contiguous()
             n0, n1 = src.shape[0], src.shape[1]
-            flat = i0 * n1 + i1                                 # row index into (n0*n1, rest); indices >= 0
+            for ix, n, ax in ((i0, n0, 0), (i1, n1, 1)):        # host-known ranges raise like NumPy; device-built ones wrap/clamp
+                if ix.bounds is not None and not (-n <= ix.bounds[0] and ix.bounds[1] < n):
+                    bad = ix.bounds[1] if ix.bounds[1] >= n else ix.bounds[0]
+                    raise IndexError("index %d is out of bounds for axis %d with size %d" % (bad, ax, n))
             rest = src.shape[2:]
             row = int(np.prod(rest)) if rest else 1
             out = DeviceArray.empty((i0.shape[0],) + rest, self.dtype)
-            _lib.call("nlps_gather_rows", _lib.stream_ptr(), C.c_int(4), C.c_int64(i0.shape[0]), C.c_int64(row),
-                      _lib.vp(src.ptr), C.c_int64(row), _lib.vp(flat.ptr), C.c_int64(n0 * n1), _lib.vp(out.ptr))
+            # each index wraps on its own axis (t = lens - 1 is -1 for an all-PAD row: NumPy picks that row's last position)
+            _lib.call("nlps_gather_rows2", _lib.stream_ptr(), C.c_int(4), C.c_int64(i0.shape[0]), C.c_int64(row),
+                      _lib.vp(src.ptr), C.c_int64(n0), C.c_int64(n1), _lib.vp(i0.ptr), _lib.vp(i1.ptr), _lib.vp(out.ptr))
             return out
         raise IndexError("unsupported advanced index pattern on a device array: %r" % (key,))
 
@@ -429,7 +433,19 @@ class _Squared:
         return _unary(self.base, 2)
 
 
-matmul_precision = "tf32"        # arithmetic of `@` on device arrays; the last constructed model sets it
+matmul_precision = "tf32"        # arithmetic of `@` when neither operand belongs to a model (see _operand_precision)
+
+
+def _operand_precision(*arrays):
+    """The arithmetic mode of `@`: that of the model an operand is a view of (a parameter such as ``model.W_vocab``, or an
+    activation held by one of its caches) -- per model, not process-wide state."""
+    for a in arrays:
+        owner = getattr(a, "_owner", None)
+        for cand in (owner, getattr(owner, "_model", None)):
+            prec = getattr(cand, "precision", None)
+            if isinstance(prec, str) and prec in _lib.PREC:
+                return prec
+    return matmul_precision
 
 
 def _strided_copy(src: DeviceArray, dst: DeviceArray):
@@ -492,7 +508,7 @@ def matmul(a: DeviceArray, b: DeviceArray, precision: Optional[str] = None) -> D
         b = b.copy()
     M, K, N = a2.shape[0], a2.shape[1], b.shape[1]
     out = DeviceArray.empty((M, N), _F32)
-    prec = _lib.PREC[precision or matmul_precision]
+    prec = _lib.PREC[precision or _operand_precision(b, a)]
     lda = a2.strides[0] if M > 1 else max(K, 1)
     ldb = b.strides[0] if K > 1 else max(N, 1)
     if prec != 0 and (a2.ptr % 16 or b.ptr % 16 or lda % 4 or ldb % 4):

@@ -97,6 +97,23 @@ __global__ void unary_kernel(int op, int64_t n, const float* __restrict__ a, flo
     out[i] = o;
   }
 }
+// out[r] = src[i0[r], i1[r], :] for a dense (n0, n1, row_elems) source: NumPy's H[idx, t, :] (utils/train.py:113-115),
+// each index wrapped on its own axis like NumPy does (t = lens - 1 is -1 for an all-PAD row and selects the row's own
+// last position), then clamped into range
+template <typename T>
+__global__ void gather_rows2_kernel(int64_t n_out, int64_t row_elems, const T* __restrict__ src, int64_t n0, int64_t n1,
+                                    const int32_t* __restrict__ i0, const int32_t* __restrict__ i1, T* __restrict__ dst) {
+  const int64_t total = n_out * row_elems;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / row_elems, c = i - r * row_elems;
+    int64_t a = i0[r], b = i1[r];
+    if (a < 0) a += n0;
+    if (b < 0) b += n1;
+    a = a < 0 ? 0 : (a >= n0 ? n0 - 1 : a);
+    b = b < 0 ? 0 : (b >= n1 ? n1 - 1 : b);
+    dst[i] = src[(a * n1 + b) * row_elems + c];
+  }
+}
 
 // single-CTA reductions: the shim only reduces small arrays (lens, logits of one row, grads go
 // through sumsq()); fixed order => deterministic
@@ -167,6 +184,17 @@ int gather_rows(cudaStream_t st, int elem_size, int64_t n_out, int64_t row_elems
   if (n_out * row_elems <= 0) return 0;
   gather_rows_kernel<uint32_t><<<grid_for(n_out * row_elems), 256, 0, st>>>(
       n_out, row_elems, static_cast<const uint32_t*>(src), src_stride, index, n_src, static_cast<uint32_t*>(dst));
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+
+int gather_rows2(cudaStream_t st, int elem_size, int64_t n_out, int64_t row_elems, const void* src, int64_t n0, int64_t n1,
+                 const int32_t* i0, const int32_t* i1, void* dst) {
+  NLPS_REQUIRE(elem_size == 4, "gather_rows2: only 4-byte elements are supported");
+  if (n_out * row_elems <= 0) return 0;
+  NLPS_REQUIRE(n0 > 0 && n1 > 0, "gather_rows2: empty source");
+  gather_rows2_kernel<uint32_t><<<grid_for(n_out * row_elems), 256, 0, st>>>(
+      n_out, row_elems, static_cast<const uint32_t*>(src), n0, n1, i0, i1, static_cast<uint32_t*>(dst));
   NLPS_LAUNCH_CHECK();
   return 0;
 }

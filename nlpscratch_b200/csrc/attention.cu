@@ -542,10 +542,12 @@ int attention_forward(cudaStream_t st, int precision, int B, int S, int h, int d
                       const int32_t* x, const int32_t* fnp, float* ctx, float* lse) {
   NLPS_TRY(check_dims(B, S, h, d));
   if (precision == 1 && attention_tc_supported(d, h * d, qkv) && attn_impl() != 1) {
-    if (attn_impl() == 2) return attention_forward_tc(st, B, S, h, d, qkv, x, fnp, ctx, lse);
+    if (attn_impl() == 2) { count_kind(KIND_ATTN_SS); return attention_forward_tc(st, B, S, h, d, qkv, x, fnp, ctx, lse); }
+    count_kind(KIND_ATTN_TS_FWD);
     return attention_forward_ts(st, B, S, h, d, qkv, x, fnp, ctx, lse);
   }
-  if (precision == 1 && d <= 64 && d % 4 == 0) return attention_forward_mma(st, B, S, h, d, qkv, x, fnp, ctx, lse);
+  if (precision == 1 && d <= 64 && d % 4 == 0) { count_kind(KIND_ATTN_MMA); return attention_forward_mma(st, B, S, h, d, qkv, x, fnp, ctx, lse); }
+  count_kind(KIND_ATTN_FP32);
   AttnDims p{B, S, h, d, h * d, (float)(1.0 / sqrt((double)d))};
   if (d <= 8) return fwd_launch<8>(st, p, qkv, x, fnp, ctx, lse);
   if (d <= 16) return fwd_launch<16>(st, p, qkv, x, fnp, ctx, lse);
@@ -573,10 +575,12 @@ int attention_backward(cudaStream_t st, int precision, int B, int S, int h, int 
 delta_done:
   if (precision == 1 && attention_tc_supported(d, h * d, qkv) && attn_impl() != 1 &&
       (reinterpret_cast<uintptr_t>(dctx) & 15u) == 0) {
-    if (attn_impl() == 2) return attention_backward_tc(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv);
+    if (attn_impl() == 2) { count_kind(KIND_ATTN_SS); return attention_backward_tc(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv); }
+    count_kind(KIND_ATTN_TS_BWD);
     return attention_backward_ts(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv);
   }
-  if (precision == 1 && d <= 64 && d % 4 == 0) return attention_backward_mma(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv);
+  if (precision == 1 && d <= 64 && d % 4 == 0) { count_kind(KIND_ATTN_MMA); return attention_backward_mma(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv); }
+  count_kind(KIND_ATTN_FP32);
   if (d <= 8) return bwd_launch<8>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
   if (d <= 16) return bwd_launch<16>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
   if (d <= 32) return bwd_launch<32>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);

@@ -13,6 +13,11 @@ namespace nlps {
 void set_error(const char* fmt, ...);
 const char* get_error();
 void count_launch(int n = 1);         // every kernel launch of ours goes through this counter
+// dispatch statistics: how often each implementation of a contraction / attention served a call (nlps_kernel_stats)
+enum { KIND_GEMM_PAIR = 0, KIND_GEMM_TC_SINGLE, KIND_GEMM_SIMT, KIND_GEMM_X3, KIND_ATTN_TS_FWD, KIND_ATTN_TS_BWD,
+       KIND_ATTN_MMA, KIND_ATTN_FP32, KIND_ATTN_SS, KIND_COUNT };
+void count_kind(int kind);
+long long kind_count(int kind, bool reset);
 long long launch_count(bool reset);
 void ensure_mempool_config();
 unsigned long long alloc_epoch();      // see util.cu: invalidates captured CUDA graphs after a re-allocation
@@ -235,12 +240,14 @@ int layernorm_backward(cudaStream_t st, int64_t rows, int E, const float* dy, co
 size_t layernorm_backward_scratch_floats(int E);
 // rowstat != nullptr: per-32-column {max, sum exp} blocks from the vocab-head GEMM epilogue (see GemmArgs::rowstat_out)
 int softmax_xent_rows(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V, float inv,
-                      float* dlogits, int64_t ldd, float* row_loss);
+                      float* dlogits, int64_t ldd, float* row_loss, int32_t* err = nullptr);
 int row_loss_mean(cudaStream_t st, const float* row_loss, int64_t rows, float* loss);
 int softmax_xent_stats(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
-                       float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss, const float2* rowstat);
+                       float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss, const float2* rowstat,
+                       int32_t* err = nullptr);
 int softmax_xent(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
-                 float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss_scratch);
+                 float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss_scratch,
+                 int32_t* err = nullptr);   // err: model error word, bit 1 = target id out of range
 // tickets: ceil(cols/128) zero-initialised counters (self-resetting) -> the reduction finishes inside the one kernel;
 // nullptr -> separate finish kernel
 int colsum(cudaStream_t st, int64_t rows, int cols, const float* x, int64_t ld, float* out, float* scratch,
@@ -277,7 +284,12 @@ int strided_copy(cudaStream_t st, int elem_size, int ndim, const int64_t* shape,
                  const int64_t* sstr, void* dst, const int64_t* dstr);
 int gather_rows(cudaStream_t st, int elem_size, int64_t n_out, int64_t row_elems, const void* src, int64_t src_stride,
                 const int32_t* index, int64_t n_src, void* dst);
+int gather_rows2(cudaStream_t st, int elem_size, int64_t n_out, int64_t row_elems, const void* src, int64_t n0, int64_t n1,
+                 const int32_t* i0, const int32_t* i1, void* dst);
 int gather_last(cudaStream_t st, int B, int S, int E, const float* h, const int32_t* t, float* out);
+// keep-mask (1.0 / 0.0) of a dropout stream over n elements: the decisions dropout_one() takes in the GEMM epilogues (forward)
+// and in the LayerNorm backward (regenerated), exported for the dropout parity tests
+int dropout_mask(cudaStream_t st, const DropoutParams& d, int64_t n, float* out);
 int count_nonzero_rows(cudaStream_t st, int64_t rows, int64_t cols, const int32_t* x, int64_t stride, int32_t* out);
 int binary_f32(cudaStream_t st, int op, int64_t n, int64_t cols, const float* a, const float* b, float bs, int mode, float* out);
 int binary_i32(cudaStream_t st, int op, int64_t n, const int32_t* a, const int32_t* b, int32_t bs, int mode, int32_t* out);

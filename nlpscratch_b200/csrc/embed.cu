@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(int B, int S, int E, int
   int id = x[(int64_t)b * xs + s];
   if (id < 0) id += V;                      // numpy-style negative index
   if (id < 0 || id >= V) {                  // numpy raises IndexError; flag it and clamp
-    if (lane == 0 && err) atomicExch(err, 1);
+    if (lane == 0 && err) atomicOr(err, 1);
     id = 0;
   }
   if (lane == 0 && x_flat) x_flat[tok] = id;

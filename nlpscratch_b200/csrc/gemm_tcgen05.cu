@@ -877,6 +877,7 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
   if (g.trans_b) NLPS_TRY(make_map(&mb, g.B, (uint64_t)g.K, (uint64_t)g.N, g.ldb, BK, b_rows, round_tf32, false));
   else NLPS_TRY(make_map(&mb, g.B, (uint64_t)g.N, (uint64_t)g.K, g.ldb, 32, BK, round_tf32, true));
   const int items = tiles * splits;
+  count_kind(pair ? KIND_GEMM_PAIR : KIND_GEMM_TC_SINGLE);
   if (pair) {
     NLPS_TRY(launch_pair(st, ma, mb, ka, 2 * std::min(items, units)));
   } else {
@@ -966,8 +967,8 @@ int gemm_tf32x3(cudaStream_t st, const GemmArgs& g) {
 }
 
 int gemm_dispatch(cudaStream_t st, int precision, const GemmArgs& g) {
-  if (precision == 0 || !gemm_tf32_supported(g)) return gemm_fp32(st, g);
-  if (precision == 2) return gemm_tf32x3(st, g);
+  if (precision == 0 || !gemm_tf32_supported(g)) { count_kind(KIND_GEMM_SIMT); return gemm_fp32(st, g); }
+  if (precision == 2) { count_kind(KIND_GEMM_X3); return gemm_tf32x3(st, g); }
   return gemm_tf32(st, g);
 }
 

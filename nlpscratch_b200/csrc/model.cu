@@ -839,7 +839,7 @@ int nlps_loss_dlogits(nlps_model* m, const float* d_logits, int64_t ld, const in
   NLPS_CUDA(cudaSetDevice(m->device));
   NLPS_TRY(ensure_rows_tmp(m, rows));
   float* loss = d_loss ? d_loss : m->scalars + 3;
-  return softmax_xent(m->stream, d_logits, ld, d_y, rows, m->V, grad_scale, loss, d_dlogits, ldd, m->rows_tmp);
+  return softmax_xent(m->stream, d_logits, ld, d_y, rows, m->V, grad_scale, loss, d_dlogits, ldd, m->rows_tmp, m->err_flag);
 }
 
 int nlps_backward(nlps_model* m, nlps_cache* c, const float* d_dlogits, int64_t ldd) {
@@ -959,7 +959,7 @@ static int train_step_body(nlps_model* m, nlps_cache* c, const int32_t* d_x, int
       NLPS_TRY(gemm_dispatch(m->stream, m->precision, g));
       cudaStream_t ws = m->stream;
       NLPS_TRY(wgrad_fork(m, &ws));
-      NLPS_TRY(softmax_xent_rows(ws, lg, m->ldV, d_y + r0, n, m->V, inv, lg, m->ldV, m->rows_tmp + r0));
+      NLPS_TRY(softmax_xent_rows(ws, lg, m->ldV, d_y + r0, n, m->V, inv, lg, m->ldV, m->rows_tmp + r0, m->err_flag));
     }
     NLPS_TRY(wgrad_done(m, W_XENT));
     NLPS_TRY(wgrad_need(m, W_XENT));                                     // the second stream is in order: this covers every chunk
@@ -970,7 +970,7 @@ static int train_step_body(nlps_model* m, nlps_cache* c, const int32_t* d_x, int
   NLPS_CUDA(cudaSetDevice(m->device));
   NLPS_TRY(ensure_rows_tmp(m, c->N));
   NLPS_TRY(softmax_xent_stats(m->stream, c->logits, m->ldV, d_y, c->N, m->V, grad_scale, d_loss ? d_loss : m->scalars + 3, c->logits,
-                              m->ldV, m->rows_tmp, c->rowstat_valid ? c->rowstat : nullptr));
+                              m->ldV, m->rows_tmp, c->rowstat_valid ? c->rowstat : nullptr, m->err_flag));
   }
   c->has_logits = false;
   c->rowstat_valid = false;
@@ -1125,11 +1125,47 @@ int nlps_train_step_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x,
   }
   float* loss = d_loss ? d_loss : m->scalars + 3;
   // row-loss scratch: the first B floats of rows_tmp are free until backward_last_token runs
-  NLPS_TRY(softmax_xent(m->stream, logits, m->ldV, d_y, B, m->V, grad_scale, loss, logits, m->ldV, m->rows_tmp));
+  NLPS_TRY(softmax_xent(m->stream, logits, m->ldV, d_y, B, m->V, grad_scale, loss, logits, m->ldV, m->rows_tmp, m->err_flag));
   NLPS_TRY(nlps_backward_last_token(m, c, d_t, logits, m->ldV));
   if (defer_update) return 0;
   if (max_norm > 0.f) NLPS_TRY(nlps_clip_compute(m, max_norm));
   return nlps_step(m, lr, max_norm > 0.f ? 1 : 0);
+}
+
+int nlps_kernel_stats(int64_t* counts, int n, int reset) {
+  NLPS_REQUIRE(counts && n >= 0, "nlps_kernel_stats: null argument");
+  for (int k = 0; k < n; ++k) counts[k] = kind_count(k, reset != 0);
+  return 0;
+}
+
+int nlps_check_errors(nlps_model* m, int* flags) {
+  NLPS_REQUIRE(m && flags, "nlps_check_errors: null argument");
+  NLPS_CUDA(cudaSetDevice(m->device));
+  int32_t word = 0;
+  NLPS_CUDA(cudaMemcpyAsync(&word, m->err_flag, sizeof(word), cudaMemcpyDeviceToHost, m->stream));
+  NLPS_CUDA(cudaStreamSynchronize(m->stream));
+  if (word != 0) NLPS_CUDA(cudaMemsetAsync(m->err_flag, 0, sizeof(word), m->stream));
+  *flags = word;
+  return 0;
+}
+
+int nlps_dropout_counter(nlps_model* m, int64_t* value, int set, int64_t new_value) {
+  NLPS_REQUIRE(m, "null model");
+  if (set) {
+    NLPS_REQUIRE(new_value >= 0 && new_value <= 0xFFFFFFFFll, "dropout counter %lld out of range", (long long)new_value);
+    m->fwd_counter = (uint32_t)new_value;
+  }
+  if (value) *value = m->fwd_counter;
+  return 0;
+}
+
+int nlps_dropout_mask(nlps_model* m, int layer, int which, int64_t step, int64_t n, float* d_out) {
+  NLPS_REQUIRE(m && d_out, "nlps_dropout_mask: null argument");
+  NLPS_REQUIRE(layer >= 0 && layer < m->L && (which == 0 || which == 1), "nlps_dropout_mask: no dropout site (layer %d, branch %d)", layer, which);
+  NLPS_REQUIRE(step >= 0 && step <= 0xFFFFFFFFll, "nlps_dropout_mask: step out of range");
+  NLPS_CUDA(cudaSetDevice(m->device));
+  const DropoutParams d = make_dropout(m->dropout_p, m->seed, (uint32_t)(layer * 2 + which), (uint32_t)step);
+  return dropout_mask(m->stream, d, n, d_out);
 }
 
 int nlps_launch_count(nlps_model*, int64_t* launches, int reset) {
@@ -1237,6 +1273,10 @@ int nlps_strided_copy(void* stream, int es, int nd, const int64_t* shape, const 
 int nlps_gather_rows(void* stream, int es, int64_t n_out, int64_t row_elems, const void* src, int64_t stride,
                      const int32_t* index, int64_t n_src, void* dst) {
   return gather_rows((cudaStream_t)stream, es, n_out, row_elems, src, stride, index, n_src, dst);
+}
+int nlps_gather_rows2(void* stream, int es, int64_t n_out, int64_t row_elems, const void* src, int64_t n0, int64_t n1,
+                      const int32_t* i0, const int32_t* i1, void* dst) {
+  return gather_rows2((cudaStream_t)stream, es, n_out, row_elems, src, n0, n1, i0, i1, dst);
 }
 int nlps_gather_last(void* stream, int B, int S, int E, const float* h, const int32_t* t, float* out) {
   return gather_last((cudaStream_t)stream, B, S, E, h, t, out);

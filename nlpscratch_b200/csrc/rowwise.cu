@@ -215,11 +215,24 @@ __device__ __forceinline__ void online_merge(float& m, float& s, float m2, float
   m = mn;
 }
 
+// Target id of a row as NumPy's fancy index reads it (transformer.py:538-546 `log_probs[rows, y]`): negative ids wrap once
+// (-V <= y < 0 means y + V); anything else out of range is an IndexError in the reference -- here the id is clamped to 0 so
+// that no access leaves the row, and bit 1 of the model's error word is raised (nlps_check_errors turns it into IndexError).
+__device__ __forceinline__ int xent_target(const int32_t* __restrict__ y, int64_t row, int V, int32_t* err) {
+  int t = y[row];
+  if (t < 0) t += V;
+  if (t < 0 || t >= V) {
+    if (err != nullptr) atomicOr(err, 2);
+    t = 0;
+  }
+  return t;
+}
+
 // Cross-entropy whose (max, sum exp) come from the vocab-head GEMM's epilogue as one pair per 32 columns: one read of
 // the logits instead of two.  Same merge and the same second phase as xent_kernel.
 __global__ void __launch_bounds__(256) xent_stats_kernel(const float* logits, int64_t ld, const int32_t* __restrict__ y, int V,
                                                          float inv_rows_scaled, float* dlogits, int64_t ldd,
-                                                         float* __restrict__ row_loss, const float2* __restrict__ rowstat) {
+                                                         float* __restrict__ row_loss, const float2* __restrict__ rowstat, int32_t* err) {
   __shared__ float sm_m[8], sm_s[8];
   __shared__ float bc[2];
   const int64_t row = blockIdx.x;
@@ -244,12 +257,12 @@ __global__ void __launch_bounds__(256) xent_stats_kernel(const float* logits, in
     for (int w = 1; w < 8; ++w)
       if (sm_m[w] > -INFINITY) { if (M > -INFINITY) online_merge(M, S, sm_m[w], sm_s[w]); else { M = sm_m[w]; S = sm_s[w]; } }
     bc[0] = M; bc[1] = S;
-    const int t = y[row];
+    const int t = xent_target(y, row, V, err);
     row_loss[row] = -(z[t] - M - logf(S));
   }
   __syncthreads();
   const float M = bc[0], invS = 1.f / bc[1];
-  const int target = y[row];
+  const int target = xent_target(y, row, V, nullptr);
   for (int c = tid * 4; c < V; c += 1024) {                // V % 4 == 0 and 16-B aligned rows (checked by the launcher)
     const float4 v = *reinterpret_cast<const float4*>(z + c);
     float4 o;
@@ -264,7 +277,7 @@ __global__ void __launch_bounds__(256) xent_stats_kernel(const float* logits, in
 __global__ void __launch_bounds__(256) xent_kernel(const float* logits, int64_t ld,
                                                    const int32_t* __restrict__ y, int V, float inv_rows_scaled,
                                                    float* dlogits, int64_t ldd,
-                                                   float* __restrict__ row_loss, int vec_ok) {
+                                                   float* __restrict__ row_loss, int vec_ok, int32_t* err) {
   __shared__ float sm_m[8], sm_s[8];
   __shared__ float bc[2];
   const int64_t row = blockIdx.x;
@@ -299,13 +312,13 @@ __global__ void __launch_bounds__(256) xent_kernel(const float* logits, int64_t 
     for (int w = 1; w < 8; ++w)
       if (sm_m[w] > -INFINITY) { if (M > -INFINITY) online_merge(M, S, sm_m[w], sm_s[w]); else { M = sm_m[w]; S = sm_s[w]; } }
     bc[0] = M; bc[1] = S;
-    const int t = y[row];
+    const int t = xent_target(y, row, V, err);
     // loss_row = -(z_t - max - log(sum))
     row_loss[row] = -(z[t] - M - logf(S));
   }
   __syncthreads();
   const float M = bc[0], invS = 1.f / bc[1];
-  const int target = y[row];
+  const int target = xent_target(y, row, V, nullptr);
   if (vec_ok) {
     for (int c = tid * 4; c < V; c += 1024) {
       const float4 v = *reinterpret_cast<const float4*>(z + c);
@@ -554,11 +567,11 @@ int layernorm_backward(cudaStream_t st, int64_t rows, int E, const float* dy, co
 }
 
 int softmax_xent(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
-                 float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss) {
+                 float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss, int32_t* err) {
   NLPS_REQUIRE(rows > 0 && V > 0, "softmax_xent: empty input");
   const int vec_ok = (V % 4 == 0 && ld % 4 == 0 && ldd % 4 == 0 && aligned16(logits) && aligned16(dlogits)) ? 1 : 0;
   const float inv = (float)((double)grad_scale / (double)rows);
-  xent_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, ld, y, V, inv, dlogits, ldd, row_loss, vec_ok);
+  xent_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, ld, y, V, inv, dlogits, ldd, row_loss, vec_ok, err);
   NLPS_LAUNCH_CHECK();
   sum_to_scalar_kernel<<<1, 1024, 0, st>>>(row_loss, rows, (float)(1.0 / (double)rows), loss);
   NLPS_LAUNCH_CHECK();
@@ -568,10 +581,10 @@ int softmax_xent(cudaStream_t st, const float* logits, int64_t ld, const int32_t
 // the two halves of softmax_xent for a row-chunked pipeline: dlogits + per-row losses of `rows` rows with an explicit
 // factor (grad_scale / total rows), then the mean over all rows -- same kernels, same bits as the one-call form
 int softmax_xent_rows(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V, float inv,
-                      float* dlogits, int64_t ldd, float* row_loss) {
+                      float* dlogits, int64_t ldd, float* row_loss, int32_t* err) {
   if (rows <= 0) return 0;
   const int vec_ok = (V % 4 == 0 && ld % 4 == 0 && ldd % 4 == 0 && aligned16(logits) && aligned16(dlogits)) ? 1 : 0;
-  xent_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, ld, y, V, inv, dlogits, ldd, row_loss, vec_ok);
+  xent_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, ld, y, V, inv, dlogits, ldd, row_loss, vec_ok, err);
   NLPS_LAUNCH_CHECK();
   return 0;
 }
@@ -582,14 +595,29 @@ int row_loss_mean(cudaStream_t st, const float* row_loss, int64_t rows, float* l
 }
 
 int softmax_xent_stats(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
-                       float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss, const float2* rowstat) {
+                       float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss, const float2* rowstat, int32_t* err) {
   const bool vec_ok = V % 4 == 0 && ld % 4 == 0 && ldd % 4 == 0 && aligned16(logits) && aligned16(dlogits);
-  if (rowstat == nullptr || !vec_ok) return softmax_xent(st, logits, ld, y, rows, V, grad_scale, loss, dlogits, ldd, row_loss);
+  if (rowstat == nullptr || !vec_ok) return softmax_xent(st, logits, ld, y, rows, V, grad_scale, loss, dlogits, ldd, row_loss, err);
   NLPS_REQUIRE(rows > 0 && V > 0, "softmax_xent: empty input");
   const float inv = (float)((double)grad_scale / (double)rows);
-  xent_stats_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, ld, y, V, inv, dlogits, ldd, row_loss, rowstat);
+  xent_stats_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, ld, y, V, inv, dlogits, ldd, row_loss, rowstat, err);
   NLPS_LAUNCH_CHECK();
   sum_to_scalar_kernel<<<1, 1024, 0, st>>>(row_loss, rows, (float)(1.0 / (double)rows), loss);
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+
+namespace {
+__global__ void dropout_mask_kernel(DropoutParams d, int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = dropout_one(d, (uint64_t)i, 1.f) != 0.f ? 1.f : 0.f;
+}
+}  // namespace
+
+int dropout_mask(cudaStream_t st, const DropoutParams& d, int64_t n, float* out) {
+  if (n <= 0) return 0;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), kNumSMs * 8));
+  dropout_mask_kernel<<<grid, 256, 0, st>>>(d, n, out);
   NLPS_LAUNCH_CHECK();
   return 0;
 }

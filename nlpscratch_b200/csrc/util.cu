@@ -15,6 +15,14 @@ long long launch_count(bool reset) {
   return reset ? g_launches.exchange(0, std::memory_order_relaxed) : g_launches.load(std::memory_order_relaxed);
 }
 
+// which implementation served a call (tests assert that the tensor-core kernels -- not a fallback -- ran)
+static std::atomic<long long> g_kinds[KIND_COUNT];
+void count_kind(int kind) { if (kind >= 0 && kind < KIND_COUNT) g_kinds[kind].fetch_add(1, std::memory_order_relaxed); }
+long long kind_count(int kind, bool reset) {
+  if (kind < 0 || kind >= KIND_COUNT) return 0;
+  return reset ? g_kinds[kind].exchange(0, std::memory_order_relaxed) : g_kinds[kind].load(std::memory_order_relaxed);
+}
+
 // Bumped whenever a device buffer that a captured CUDA graph may point into is re-allocated (split-K workspace,
 // model workspaces, activation caches): graphs captured under an older epoch are dropped instead of replayed.
 static std::atomic<unsigned long long> g_alloc_epoch{1};

@@ -72,11 +72,15 @@ class DeviceScalar:
     """A float that still lives on the device; ``float()`` is the synchronisation point
     (utils/train.py:138 ``float(loss)``)."""
 
-    def __init__(self, arr: DeviceArray):
+    def __init__(self, arr: DeviceArray, model: "Optional[Transformer]" = None):
         self._arr = arr
+        self._model = model
 
     def __float__(self):
-        return float(self._arr.item())
+        value = float(self._arr.item())
+        if self._model is not None:              # the read synchronised: surface what the kernels flagged on the way
+            self._model._check_errors()
+        return value
 
     def item(self):
         return float(self)
@@ -139,7 +143,6 @@ class Transformer:
         object.__setattr__(self, "_training", True)
         object.__setattr__(self, "_dropout_p", float(dropout_p))
         object.__setattr__(self, "_seed", int(seed))
-        _array.matmul_precision = self.precision
         self._views: Dict[int, Dict[str, DeviceArray]] = {}
         ld = C.c_int64()
         _lib.call("nlps_logits_ld", self._h, C.byref(ld))
@@ -237,7 +240,6 @@ class Transformer:
     def set_precision(self, precision: str):
         _lib.call("nlps_set_precision", self._h, C.c_int(_lib.PREC[precision]))
         object.__setattr__(self, "precision", precision)
-        _array.matmul_precision = precision
 
     def train(self):                                   # transformer.py:96-97
         self.training = True
@@ -247,6 +249,43 @@ class Transformer:
 
     def synchronize(self):
         _lib.call("nlps_sync", self._h)
+        self._check_errors()
+
+    def _check_errors(self):
+        """Out-of-range ids cannot raise from inside an asynchronous kernel: the kernels clamp the id and raise a bit in
+        the model's error word; it is read (and cleared) at the host's synchronisation points -- ``float(loss)``,
+        ``synchronize()``, ``get_params()`` -- and becomes the IndexError NumPy raises in the reference
+        (transformer.py:114 ``We[x]``, :538-546 ``log_probs[rows, y]``)."""
+        if self.__dict__.get("_h") is None:
+            return
+        flags = C.c_int(0)
+        _lib.call("nlps_check_errors", self._h, C.byref(flags))
+        if flags.value & 1:
+            raise IndexError("token id out of bounds for axis 0 with size %d (found by the embedding kernel)" % self.vocab_size)
+        if flags.value & 2:
+            raise IndexError("target id out of bounds for %d classes (found by the cross-entropy kernel)" % self.vocab_size)
+
+    # ---- dropout state (transformer.py:102-108; masks are Philox, keyed by seed / site / forward-call counter) -------
+    @property
+    def dropout_counter(self) -> int:
+        """Forward calls so far = the Philox `step` the NEXT forward draws its masks with."""
+        v = C.c_int64()
+        _lib.call("nlps_dropout_counter", self._h, C.byref(v), C.c_int(0), C.c_int64(0))
+        return v.value
+
+    @dropout_counter.setter
+    def dropout_counter(self, value):
+        _lib.call("nlps_dropout_counter", self._h, None, C.c_int(1), C.c_int64(int(value)))
+
+    def dropout_mask(self, layer: int, which: int, step: int, shape) -> np.ndarray:
+        """Keep-mask (1.0 / 0.0, host array of `shape` = (B, S, E)) that forward call `step` applied -- and backward
+        regenerated -- at (layer, which: 0 attention branch, 1 FFN branch).  Debug / parity hook."""
+        n = int(np.prod(shape))
+        out = DeviceArray.empty((n,), np.float32)
+        _lib.call("nlps_dropout_mask", self._h, C.c_int(int(layer)), C.c_int(int(which)), C.c_int64(int(step)),
+                  C.c_int64(n), _lib.vp(out.ptr))
+        self.synchronize()
+        return out.get().reshape(shape)
 
     def load_params(self, arrays):
         """Copy host arrays (reference shapes) into the parameters; resets Adam like a fresh model."""
@@ -258,6 +297,7 @@ class Transformer:
         self.adam_t = 0
 
     def get_params(self) -> Dict[str, np.ndarray]:
+        self.synchronize()
         return {k: self._view(_lib.BUF_PARAM, k).get() for k in PARAM_NAMES}
 
     # ---- forward (transformer.py:110-199) ----------------------------------------------------------
@@ -335,7 +375,7 @@ class Transformer:
                   C.c_float(grad_scale), _lib.vp(loss.ptr), _lib.vp(store.ptr), C.c_int64(ldd))
         dlogits = DeviceArray(store._owner, store.ptr, (B, S, V), (S * ldd, ldd, 1), np.float32)
         del keep
-        return DeviceScalar(loss), dlogits
+        return DeviceScalar(loss, self), dlogits
 
     # ---- backward (transformer.py:327-459 and :201-325) ---------------------------------------------------
     def _grad_dict(self, order):
@@ -402,7 +442,7 @@ class Transformer:
         yd = y if isinstance(y, DeviceArray) else DeviceArray.from_host(np.asarray(y), np.int32)
         if yd.shape != xd.shape:
             raise ValueError("y %s must match x %s" % (yd.shape, xd.shape))
-        if yd.bounds is not None and not (0 <= yd.bounds[0] and yd.bounds[1] < self.vocab_size):
+        if yd.bounds is not None and not (-self.vocab_size <= yd.bounds[0] and yd.bounds[1] < self.vocab_size):
             raise IndexError("target id out of bounds for %d classes" % self.vocab_size)
         yd = yd.contiguous()
         xd, yd = self._static_inputs(xd, yd)
@@ -417,7 +457,7 @@ class Transformer:
                   C.c_int(int(defer_update)), _lib.vp(loss.ptr))
         object.__setattr__(self, "_last_cache", cache)       # keep x/y/activations alive until the next step
         object.__setattr__(self, "_last_y", yd)
-        return DeviceScalar(loss)
+        return DeviceScalar(loss, self)
 
     def _static_inputs(self, xd: DeviceArray, yd: DeviceArray):
         """A captured CUDA graph replays fixed addresses, and ``nlps_train_step`` keys its graphs on the id buffers.  Every
@@ -449,7 +489,7 @@ class Transformer:
         B, S = xd.shape
         if yd.shape != (B,):
             raise ValueError("yb %s must have shape (%d,)" % (yd.shape, B))
-        if yd.bounds is not None and not (0 <= yd.bounds[0] and yd.bounds[1] < self.vocab_size):
+        if yd.bounds is not None and not (-self.vocab_size <= yd.bounds[0] and yd.bounds[1] < self.vocab_size):
             raise IndexError("target id out of bounds for %d classes" % self.vocab_size)
         if lens is None:
             t = b200np.sum(xd != 0, axis=1) - 1
@@ -468,7 +508,7 @@ class Transformer:
                   C.c_int(int(defer_update)), _lib.vp(loss.ptr))
         object.__setattr__(self, "_last_cache", cache)
         object.__setattr__(self, "_last_y", (yd, t))
-        return DeviceScalar(loss)
+        return DeviceScalar(loss, self)
 
     def apply_update(self, learning_rate, clip_grad_norm: Optional[float] = 1.0):
         """Second half of a deferred ``train_step`` (after the data-parallel all-reduce)."""
@@ -492,8 +532,11 @@ class Transformer:
 
     def save_checkpoint(self, filename):
         """Resume checkpoint (the reference only has the parameter pickle of ``save``, transformer.py:551-572):
-        the reference-format parameter dict plus Adam's moments and step count, all as host float32 arrays."""
-        state = {"format": "nlpscratch_b200.checkpoint.v1",
+        the reference-format parameter dict plus Adam's moments and step count (host float32 arrays) and the dropout
+        stream's position (Philox seed + forward-call counter), so that a resumed run with dropout_p > 0 draws the masks
+        the uninterrupted run would have drawn."""
+        state = {"format": "nlpscratch_b200.checkpoint.v2",
+                 "dropout_counter": int(self.dropout_counter), "dropout_seed": int(self._seed),
                  "params": self.get_params(),
                  "m": {k: np.ascontiguousarray(a.get()) for k, a in self.m.items()},
                  "v": {k: np.ascontiguousarray(a.get()) for k, a in self.v.items()},
@@ -513,6 +556,10 @@ class Transformer:
             self._view(_lib.BUF_M, k).set(np.asarray(state["m"][k], dtype=np.float32))
             self._view(_lib.BUF_V, k).set(np.asarray(state["v"][k], dtype=np.float32))
         self.adam_t = int(state["adam_t"])
+        if "dropout_counter" in state:               # v2: the Philox stream continues where the writer stopped
+            object.__setattr__(self, "_seed", int(state["dropout_seed"]))
+            _lib.call("nlps_set_dropout", self._h, C.c_float(self._dropout_p), C.c_uint64(self._seed))
+            self.dropout_counter = int(state["dropout_counter"])
 
     def close(self):
         h = self.__dict__.get("_h")

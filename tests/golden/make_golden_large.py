@@ -1,0 +1,137 @@
+"""Golden fixtures at the model sizes that are benchmarked, generated from the REAL reference.
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_large.py
+
+Cases (VERDICT r01 "pin the benchmarked configuration to the reference"):
+  default_full_seq    the reference's default hyper-parameters (transformer_train.py:28-44: V574 E256 h8 F1024 L3
+                      max_len 320), B16, S=49, full-sequence objective, 2 Adam steps
+  default_last_token  same model, the driver's last-token path (utils/train.py:104-131) with clip 1.0, 2 steps
+  c4_full_seq         BASELINE.json configs[3] model (L6 E512 h8 F2048 S512 V8192) at B=2, one padded row, 2 steps
+  c5_full_seq         configs[4] model (L12 E768 h12 F3072 S2048 V8192) at B=1, padded tail: the long-sequence attention
+  c3_full_seq         configs[2] (default model, BPE-sized vocabulary 32768, S320) at B=2: vocab head + cross-entropy
+
+Parameters are seed-derived (not stored); large tensors are stored as deterministic samples + f64 norms
+(tests/helpers.py: perturb_params, sampled).
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+REF = os.environ.get("NLPS_REFERENCE", "/root/reference")
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REF)
+sys.path.insert(1, os.path.dirname(HERE))
+
+from Transformer.transformer import Transformer  # noqa: E402
+from utils.function import clip_grads  # noqa: E402
+from helpers import NAMES, perturb_params, sampled, sha16  # noqa: E402
+
+
+def make_model(cfg, seed):
+    np.random.seed(seed)
+    model = Transformer(*cfg, dropout_p=0.0)
+    perturb_params({n: getattr(model, n) for n in NAMES}, seed + 1)
+    return model
+
+
+def norm64(a):
+    return float(np.sqrt(np.sum(np.square(np.asarray(a, dtype=np.float64)))))
+
+
+def run_case(name, cfg, seed, x, y, mode, lr, clip, steps=2):
+    t0 = time.time()
+    model = make_model(cfg, seed)
+    out = {"cfg": np.array(cfg), "seed": np.array(seed), "x": x, "y": y, "lr": np.array(lr),
+           "clip": np.array(-1.0 if clip is None else clip), "mode": np.array(mode)}
+    meta = {"p0_sha": {n: sha16(getattr(model, n)) for n in NAMES}}
+    npb = model.np
+    for s in range(steps):
+        if mode == "full":
+            logits, cache = model.forward(x)
+            loss, dlogits = model.calculate_loss_dlogits(logits, y)
+            grads = model.backward(cache, dlogits)
+            if s == 0:
+                out["logits_s"] = sampled(logits).astype(np.float64)
+                out["logits_norm"] = np.array(norm64(logits))
+                out["H_s"] = sampled(cache["H_final"]).astype(np.float64)
+                out["H_norm"] = np.array(norm64(cache["H_final"]))
+        else:                                    # utils/train.py:104-131
+            lens = npb.sum(x != 0, axis=1).astype(npb.int32)
+            xb = x[:, :int(npb.max(lens))]
+            H, cache = model.forward(xb, return_hidden_only=True)
+            t = lens - 1
+            logits_last = H[npb.arange(len(y)), t, :] @ model.W_vocab + model.b_vocab
+            loss, dlog = model.calculate_loss_dlogits(logits_last, y)
+            grads = model.backward_last_token(cache, t, dlog[:, 0, :])
+            if s == 0:
+                out["logits_s"] = sampled(logits_last).astype(np.float64)
+                out["logits_norm"] = np.array(norm64(logits_last))
+                out["H_s"] = sampled(H).astype(np.float64)
+                out["H_norm"] = np.array(norm64(H))
+        if s == 0:
+            for k in NAMES:
+                out["graw_s_" + k] = sampled(grads[k])
+                out["graw_norm_" + k] = np.array(norm64(grads[k]))
+        if clip is not None:
+            clip_grads(list(grads.values()), clip, lib=npb)
+        out["loss%d" % s] = np.array(float(loss))
+        model.step(grads, lr)
+        for k in NAMES:
+            out["p%d_s_%s" % (s + 1, k)] = sampled(getattr(model, k))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    meta.update(bytes=os.path.getsize(path), seconds=round(time.time() - t0, 1),
+                losses=[float(out["loss%d" % s]) for s in range(steps)])
+    print(name, meta["bytes"], "bytes", meta["seconds"], "s", meta["losses"], flush=True)
+    return meta
+
+
+def main():
+    rng = np.random.default_rng(2026)
+    man = {"numpy": np.__version__, "cases": {}}
+    V = 574
+    cfg = (V, 256, 8, 1024, 3, 320)              # transformer_train.py:28-44
+    x = rng.integers(1, V, (16, 49)).astype(np.int32)
+    for b, n in ((3, 30), (7, 11), (12, 1)):     # tail padding like the prefix dataset
+        x[b, n:] = 0
+    y = rng.integers(0, V, (16, 49)).astype(np.int32)
+    man["cases"]["default_full_seq"] = run_case("default_full_seq", cfg, 101, x, y, "full", 1e-4, 1.0)
+
+    xl = np.zeros((16, 320), np.int32)           # prefix-style rows: ragged lengths up to 49, <START>=2 first
+    for b in range(16):
+        n = int(rng.integers(1, 50))
+        xl[b, :n] = rng.integers(2, V, n)
+        xl[b, 0] = 2
+    yl = rng.integers(0, V, (16,)).astype(np.int32)
+    man["cases"]["default_last_token"] = run_case("default_last_token", cfg, 102, xl, yl, "last", 1e-4, 1.0)
+
+    V4 = 8192
+    cfg4 = (V4, 512, 8, 2048, 6, 512)
+    x4 = rng.integers(1, V4, (2, 512)).astype(np.int32)
+    x4[1, 400:] = 0
+    y4 = rng.integers(1, V4, (2, 512)).astype(np.int32)
+    man["cases"]["c4_full_seq"] = run_case("c4_full_seq", cfg4, 104, x4, y4, "full", 1e-4, 1.0)
+
+    cfg5 = (V4, 768, 12, 3072, 12, 2048)
+    x5 = rng.integers(1, V4, (1, 2048)).astype(np.int32)
+    x5[0, 1900:] = 0
+    y5 = rng.integers(1, V4, (1, 2048)).astype(np.int32)
+    man["cases"]["c5_full_seq"] = run_case("c5_full_seq", cfg5, 105, x5, y5, "full", 1e-4, 1.0, steps=1)
+
+    V3 = 32768
+    cfg3 = (V3, 256, 8, 1024, 3, 320)
+    x3 = rng.integers(1, V3, (2, 320)).astype(np.int32)
+    x3[0, 300:] = 0
+    y3 = rng.integers(0, V3, (2, 320)).astype(np.int32)
+    man["cases"]["c3_full_seq"] = run_case("c3_full_seq", cfg3, 103, x3, y3, "full", 1e-4, 1.0)
+
+    with open(os.path.join(HERE, "manifest_large.json"), "w") as fh:
+        json.dump(man, fh, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,3 +31,39 @@ def rel_err(got, want):
 
 def params_from_case(case, step=0):
     return {k: case["p%d_%s" % (step, k)] for k in NAMES}
+
+
+# ---- large-model fixtures (tests/golden/make_golden_large.py) -------------------------------------------
+# Parameters are NOT stored: the reference draws them from NumPy's global generator in a fixed order
+# (transformer.py:34-55), so (seed, perturbation recipe) reproduces them bit for bit on either side; the
+# fixture pins that with a SHA-256 per tensor.
+LARGE_CASES = ("default_full_seq", "default_last_token", "c3_full_seq", "c4_full_seq", "c5_full_seq")
+
+
+def perturb_params(params, seed):
+    """Make biases / LayerNorm parameters non-trivial (they start at 0 / 1): same recipe in the golden
+    generator (applied to the real reference model) and in the tests (applied to the model under test)."""
+    rng = np.random.default_rng(seed)
+    for n in ("b1", "b2", "b_vocab", "ln1_beta", "ln2_beta"):
+        params[n][...] = rng.uniform(-0.2, 0.2, params[n].shape).astype(np.float32)
+    for n in ("ln1_gamma", "ln2_gamma"):
+        params[n][...] = rng.uniform(0.5, 1.5, params[n].shape).astype(np.float32)
+    return params
+
+
+def sample_idx(size, n=4096):
+    """Deterministic spread of flat indices used to keep large tensors out of the fixtures."""
+    size = int(size)
+    if size <= n:
+        return np.arange(size, dtype=np.int64)
+    return np.unique(np.linspace(0, size - 1, n).astype(np.int64))
+
+
+def sampled(a, n=4096):
+    a = np.ascontiguousarray(a)
+    return a.reshape(-1)[sample_idx(a.size, n)]
+
+
+def sha16(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]

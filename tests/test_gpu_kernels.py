@@ -80,7 +80,9 @@ def _attention_case(B, S, h, d, pad_mode, seed):
                                          (8, 512, 6, 64, "tail"), (40, 130, 4, 32, "lead"), (33, 65, 5, 64, "tail"),
                                          (16, 320, 8, 32, "tail"),
                                          # beyond the staged PAD-mask capacity of the forward (2048) and dQ (4096) kernels
-                                         (1, 2100, 1, 64, "tail"), (1, 4200, 1, 32, "none")])
+                                         (1, 2100, 1, 64, "tail"), (1, 4200, 1, 32, "none"),
+                                         # the benchmarked attention shapes: c4 (S512 h8 d64) and c5 (S2048 h12 d64)
+                                         (4, 512, 8, 64, "tail"), (1, 2048, 12, 64, "tail")])
 @pytest.mark.parametrize("prec", ["fp32", "tf32"])
 def test_attention_forward_backward(B, S, h, d, pad, prec):
     # fp32: CUDA-core kernels (attention.cu); tf32: mma.sync tensor-core kernels (attention_mma.cu,
