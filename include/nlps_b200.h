@@ -120,6 +120,10 @@ int nlps_forward(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t x_row
                  int hidden_only, float* d_out, int64_t ld_out);
 int nlps_cache_hidden_ptr(nlps_cache* c, void** d_h_final);  /* (B*S,E), cache['H_final'] */
 int nlps_cache_logits_ptr(nlps_cache* c, void** d_logits, int64_t* ld);
+/* cache['layers'][layer][...] of the reference's cache dict (transformer.py:163-171): which = 0 'attn_input' (B*S,E),
+ * 1 'ffn_input' (B*S,E), 2 'ffn_hidden' (B*S,F); plus 3 = merged heads of P@V (B*S,E) and 4 = packed Q|K|V rows (B*S,3E),
+ * which this build stores instead of the (B,h,S,S) attention weights. */
+int nlps_cache_layer_ptr(nlps_model* m, nlps_cache* c, int layer, int which, void** d_ptr);
 int nlps_logits_ld(const nlps_model* m, int64_t* ld);        /* padded row stride of (N,V) buffers */
 
 /* Transformer.calculate_loss_dlogits, transformer.py:515-549.  rows = B*S (or B for the
@@ -157,6 +161,12 @@ int nlps_train_step_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x,
                                const int32_t* d_t, const int32_t* d_y, float lr, float max_norm,
                                float grad_scale, int defer_update, float* d_loss);
 int nlps_launch_count(nlps_model* m, int64_t* launches, int reset);  /* kernels launched so far (process-wide counter) */
+
+/* Roofline denominator, measured: the tcgen05.mma kind::tf32 issue ceiling of this GPU with FP32 operands resident in
+ * shared memory and accumulators in TMEM (the GEMM kernel's MMA loop with TMA, epilogue and global traffic removed;
+ * csrc/tf32_peak.cu).  cta_group 1: M128 N256 per SM; 2: M256 N256 per SM pair.  iters groups of 16 MMAs per issuing unit,
+ * best of `reps` launches, timed with CUDA events inside the call (synchronises the device). */
+int nlps_tf32_mma_peak(int device, int cta_group, int iters, int reps, float* h_tflops, float* h_ms);
 
 /* Dispatch statistics (process-wide): counts[k] = calls served by implementation k since the last reset, k =
  * 0 tcgen05 CTA-pair GEMM, 1 tcgen05 single-CTA GEMM, 2 CUDA-core FP32 GEMM, 3 3xTF32 GEMM, 4 tcgen05 attention forward,

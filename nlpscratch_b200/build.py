@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libnlps_b200.so")
 SOURCES = ["util.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "attention.cu", "attention_mma.cu", "attention_tc.cu", "attention_ts.cu", "rowwise.cu", "embed.cu", "dataset.cu",
-           "optimizer.cu", "array_ops.cu", "model.cu"]
+           "optimizer.cu", "array_ops.cu", "tf32_peak.cu", "model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -192,6 +192,8 @@ bool gemm_tf32_supported(const GemmArgs& g);
 bool gemm_tf32_colsum_fusable(const GemmArgs& g);   // colsum32_out may be set for this product
 bool gemm_tf32_rowdot_fusable(const GemmArgs& g);   // rowdot_out may be set for this product (rowdot_* fields filled in)
 int gemm_dispatch(cudaStream_t st, int precision, const GemmArgs& g);
+// tf32_peak.cu: measured tcgen05 kind::tf32 issue ceiling (operands resident in shared memory, accumulators in TMEM)
+int tf32_mma_peak(int cta_group, int iters, int reps, float* tflops, float* ms);
 
 // dataset.cu
 int prefix_dataset(cudaStream_t st, int n_sent, int64_t n_rows, int max_len, int32_t pad, const int32_t* ids,

@@ -751,6 +751,21 @@ int nlps_cache_hidden_ptr(nlps_cache* c, void** p) {
   *p = c->layers.empty() ? c->h0 : c->layers.back().y2;
   return 0;
 }
+int nlps_cache_layer_ptr(nlps_model* m, nlps_cache* c, int layer, int which, void** p) {
+  NLPS_REQUIRE(m && c && p, "null argument");
+  NLPS_REQUIRE(layer >= 0 && layer < (int)c->layers.size(), "layer %d out of range", layer);
+  const nlps_cache::L& a = c->layers[layer];
+  switch (which) {
+    case 0: *p = layer == 0 ? c->h0 : c->layers[layer - 1].y2; break;   // attn_input
+    case 1: *p = a.y1; break;                                           // ffn_input
+    case 2: *p = a.hid; break;                                          // ffn_hidden
+    case 3: *p = a.ctx; break;                                          // merged heads of P@V (the reference recomputes it)
+    case 4: *p = a.qkv; break;                                          // packed Q|K|V rows
+    default: NLPS_REQUIRE(false, "unknown cache tensor %d", which);
+  }
+  return 0;
+}
+
 int nlps_cache_logits_ptr(nlps_cache* c, void** p, int64_t* ld) {
   NLPS_REQUIRE(c && p, "null argument");
   *p = c->logits;
@@ -1130,6 +1145,14 @@ int nlps_train_step_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x,
   if (defer_update) return 0;
   if (max_norm > 0.f) NLPS_TRY(nlps_clip_compute(m, max_norm));
   return nlps_step(m, lr, max_norm > 0.f ? 1 : 0);
+}
+
+int nlps_tf32_mma_peak(int device, int cta_group, int iters, int reps, float* h_tflops, float* h_ms) {
+  int ndev = 0;
+  nlps_device_count(&ndev);
+  NLPS_REQUIRE(ndev > 0, "no CUDA device: libnlps_b200 has no CPU fallback");
+  NLPS_CUDA(cudaSetDevice(device));
+  return tf32_mma_peak(cta_group, iters, reps, h_tflops, h_ms);
 }
 
 int nlps_kernel_stats(int64_t* counts, int n, int reset) {

@@ -65,7 +65,27 @@ class Cache:
             return self.x
         if key == "H_final":
             return self._model._hidden_view(self)
+        if key == "layers":                  # cache['layers'][l]['ffn_hidden'] ... (transformer.py:163-171)
+            return [_LayerCache(self, l) for l in range(self._model.num_layers)]
         raise KeyError(key)
+
+
+class _LayerCache:
+    """Read-only view of one layer's cached activations under the reference's key names."""
+    _KEYS = {"attn_input": (0, "E"), "ffn_input": (1, "E"), "ffn_hidden": (2, "F"), "ctx": (3, "E"), "qkv": (4, "3E")}
+
+    def __init__(self, cache: Cache, layer: int):
+        self._cache, self._layer = cache, layer
+
+    def __getitem__(self, key):
+        if key not in self._KEYS:
+            raise KeyError("%r is not cached by this build (never materialised: attention weights, masks, dropout masks)" % key)
+        which, width = self._KEYS[key]
+        m, c = self._cache._model, self._cache
+        cols = {"E": m.embed_dim, "F": m.ff_dim, "3E": 3 * m.embed_dim}[width]
+        p = C.c_void_p()
+        _lib.call("nlps_cache_layer_ptr", m._h, c._h, C.c_int(self._layer), C.c_int(which), C.byref(p))
+        return DeviceArray(c, p.value, (c.B, c.S, cols), (c.S * cols, cols, 1), np.float32)
 
 
 class DeviceScalar:

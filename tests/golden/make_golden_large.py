@@ -73,6 +73,15 @@ def run_case(name, cfg, seed, x, y, mode, lr, clip, steps=2):
                 out["H_s"] = sampled(H).astype(np.float64)
                 out["H_norm"] = np.array(norm64(H))
         if s == 0:
+            # ReLU gates within 2e-5 sigma of zero: a float32 implementation may legitimately land on the other side of
+            # 0 for these (the gradient is discontinuous there); the tests use the list to tell such a flip from a bug
+            fl, fi, fz = [], [], []
+            for l, lc in enumerate(cache["layers"]):
+                z = lc["ffn_input"] @ model.W1[l] + model.b1[l]          # transformer.py:388 recomputes exactly this
+                z2 = np.asarray(z).reshape(-1)
+                idx = np.nonzero(np.abs(z2) < 2e-5 * z2.std())[0]
+                fl += [l] * len(idx); fi += list(idx); fz += list(z2[idx] / z2.std())
+            out["frag_layer"], out["frag_index"], out["frag_z"] = np.array(fl, np.int32), np.array(fi, np.int64), np.array(fz)
             for k in NAMES:
                 out["graw_s_" + k] = sampled(grads[k])
                 out["graw_norm_" + k] = np.array(norm64(grads[k]))

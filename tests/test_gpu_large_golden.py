@@ -7,6 +7,17 @@ tcgen05 GEMM and the persistent tcgen05 attention.  Tolerances (norm-wise relati
   fp32, tf32x3 : 1e-4 logits / hidden / loss / every gradient tensor; updated weights 1e-4
   tf32         : 5e-3 logits / hidden, 2e-3 loss, 5e-2 gradients (10-bit operand mantissas: the reference's own cuBLAS TF32 mode),
                  updated weights within 2.5*lr*steps (Adam's first steps are +-lr*sign(g))
+ReLU gates within float32 rounding of zero.  The gradient of the network is discontinuous where a hidden pre-activation
+z = y1 W1 + b1 crosses 0 (function.py:53-56 zeroes dz where z <= 0).  The reference evaluates z in float64 (NumPy >= 2
+promotion); any float32 implementation lands on the other side of 0 for a few of the 10^6..10^8 gates of these
+models (|z| ~ 1e-7 sigma), and ONE flipped gate moves the bias gradient b1 by ~4e-4 -- measured: the fp32 CUDA path
+differs from the reference at default_full_seq by exactly the gate at z = -1.07e-7 (layer 1, row 60, column 773), and
+flipping that one gate inside the float64 oracle reproduces every per-tensor error to two digits.  The fixtures therefore
+list the gates with |z| < 2e-5 sigma; when a gradient misses the tolerance the test reads our cached ffn_hidden at those
+gates, and if (and only if) some of THEM differ from the reference's sign it re-evaluates the reference gradient with
+those gates flipped (oracle.gate_flips; the oracle is pinned to the reference at these sizes by
+tests/test_oracle_golden_large.py) and holds the CUDA path to the same tolerance against that.  A flip outside the list,
+or any other error, still fails.  Flip counts are reported.
 Observed errors are written to gpurun_out/parity_large.json when that directory exists.
 """
 import ctypes as C
@@ -21,6 +32,7 @@ from helpers import GOLDEN, LARGE_CASES, NAMES, load_case, perturb_params, rel_e
 pytestmark = pytest.mark.gpu
 
 from nlpscratch_b200 import Transformer, _lib  # noqa: E402
+from oracle.transformer_oracle import OracleTransformer  # noqa: E402
 
 TOL = {"fp32": dict(act=1e-4, grad=1e-4, loss=1e-5, param=1e-4),
        "tf32x3": dict(act=1e-4, grad=1e-4, loss=1e-5, param=1e-4),
@@ -37,6 +49,50 @@ def kernel_stats(reset=False):
 
 def norm64(a):
     return float(np.sqrt(np.sum(np.square(np.asarray(a, dtype=np.float64)))))
+
+
+def fragile_gate_flips(case, cache):
+    """{layer: flat indices} of the listed near-zero gates where our float32 gate (ffn_hidden > 0) differs from the
+    reference's float64 one (z > 0)."""
+    flips = {}
+    layers = cache["layers"]
+    for l in np.unique(case["frag_layer"]):
+        sel = case["frag_layer"] == l
+        idx, z = case["frag_index"][sel], case["frag_z"][sel]
+        ours = layers[int(l)]["ffn_hidden"].get().reshape(-1)[idx] > 0
+        bad = idx[ours != (z > 0)]
+        if len(bad):
+            flips[int(l)] = bad
+    return flips
+
+
+def flipped_z(case, flips):
+    worst = 0.0
+    for l, idx in flips.items():
+        sel = case["frag_layer"] == l
+        lut = dict(zip(case["frag_index"][sel].tolist(), case["frag_z"][sel].tolist()))
+        worst = max([worst] + [abs(lut[int(i)]) for i in idx])
+    return worst
+
+
+def oracle_grads_with_flips(case, cfg, seed, flips, mode):
+    """The reference gradient (float64 oracle, pinned to the reference at this size) evaluated with the listed gates flipped."""
+    np.random.seed(seed)
+    o = OracleTransformer(*cfg, dropout_p=0.0)
+    perturb_params(o.params, seed + 1)
+    o.gate_flips = flips
+    x, y = case["x"], case["y"]
+    if mode == "full":
+        lo, co = o.forward(x)
+        _, dl = o.calculate_loss_dlogits(lo, y)
+        g = o.backward(co, dl)
+    else:
+        lens = (x != 0).sum(1)
+        H, co = o.forward(x[:, :lens.max()], return_hidden_only=True)
+        lg = H[np.arange(len(y)), lens - 1] @ o.params["W_vocab"] + o.params["b_vocab"]
+        _, dl = o.calculate_loss_dlogits(lg, y)
+        g = o.backward_last_token(co, lens - 1, dl[:, 0, :])
+    return {k: sampled(g[k]) for k in NAMES}, {k: norm64(g[k]) for k in NAMES}
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3", "tf32"])
@@ -57,7 +113,11 @@ def test_benchmarked_sizes_against_reference_fixtures(name, precision):
     lr, clip, mode = float(case["lr"]), float(case["clip"]), str(case["mode"])
     x, y = case["x"], case["y"]
     steps = sum(1 for k in case if k.startswith("loss"))
-    rep = {}
+    rep, failures = {}, []
+
+    def check(ok, what):
+        if not ok:
+            failures.append(what)
     kernel_stats(reset=True)
     for s in range(steps):
         if mode == "full":
@@ -77,21 +137,33 @@ def test_benchmarked_sizes_against_reference_fixtures(name, precision):
             grads = m.backward_last_token(cache, t, dl[:, 0, :])
         want = float(case["loss%d" % s])
         rep["loss%d" % s] = abs(float(loss) - want) / max(1.0, abs(want))
-        assert rep["loss%d" % s] < tol["loss"], (s, float(loss), want)
+        check(rep["loss%d" % s] < tol["loss"], ("loss", s, float(loss), want))
         if s == 0:
             rep["logits"] = rel_err(sampled(logits.get()), case["logits_s"])
             rep["hidden"] = rel_err(sampled(H.get()), case["H_s"])
-            assert rep["logits"] < tol["act"] and rep["hidden"] < tol["act"], rep
+            check(rep["logits"] < tol["act"] and rep["hidden"] < tol["act"], ("act", rep["logits"], rep["hidden"]))
             ln = float(case["logits_norm"])
-            assert abs(norm64(logits.get()) - ln) < tol["act"] * ln
+            check(abs(norm64(logits.get()) - ln) < tol["act"] * ln, ("logits norm",))
+            got_g = {k: grads[k].get() for k in NAMES}
+            want_s = {k: case["graw_s_" + k] for k in NAMES}
+            want_n = {k: float(case["graw_norm_" + k]) for k in NAMES}
+            worst = max(rel_err(sampled(got_g[k]), want_s[k]) for k in NAMES)
+            rep["grad_worst_vs_reference_gates"] = worst
+            rep["gate_flips"] = 0
+            if worst >= tol["grad"]:
+                flips = fragile_gate_flips(case, cache)
+                rep["gate_flips"] = int(sum(len(v) for v in flips.values()))
+                rep["gate_flips_max_abs_z_over_sigma"] = flipped_z(case, flips)
+                if rep["gate_flips"]:
+                    want_s, want_n = oracle_grads_with_flips(case, cfg, seed, flips, mode)
             for k in NAMES:
-                g = grads[k].get()
+                g = got_g[k]
                 assert g.dtype == np.float32 and g.shape == params[k].shape
-                e = rel_err(sampled(g), case["graw_s_" + k])
-                gn = float(case["graw_norm_" + k])
+                e = rel_err(sampled(g), want_s[k])
                 rep["grad_" + k] = e
-                assert e < tol["grad"], (k, e)
-                assert abs(norm64(g) - gn) < tol["grad"] * max(gn, 1e-12), (k, norm64(g), gn)
+                rep["gradnorm_" + k] = abs(norm64(g) - want_n[k]) / max(want_n[k], 1e-12)
+                check(e < tol["grad"], ("grad", k, e))
+                check(rep["gradnorm_" + k] < tol["grad"], ("grad norm", k, norm64(g), want_n[k]))
         if clip > 0:
             m.clip_gradients(clip)                          # clip_grads(list(grads.values()), clip), function.py:27-38
         m.step(grads, lr)
@@ -99,9 +171,9 @@ def test_benchmarked_sizes_against_reference_fixtures(name, precision):
         for k in NAMES:
             w = case["p%d_s_%s" % (s + 1, k)]
             if tol["param"] is not None:
-                assert rel_err(sampled(got[k]), w) < tol["param"], (k, s)
+                check(rel_err(sampled(got[k]), w) < tol["param"], ("param", k, s))
             else:
-                assert float(np.max(np.abs(sampled(got[k]).astype(np.float64) - w))) <= 2.5 * lr * (s + 1), (k, s)
+                check(float(np.max(np.abs(sampled(got[k]).astype(np.float64) - w))) <= 2.5 * lr * (s + 1), ("param", k, s))
     stats = kernel_stats()
     rep["kernels"] = stats
     if precision == "tf32":
@@ -113,8 +185,10 @@ def test_benchmarked_sizes_against_reference_fixtures(name, precision):
     else:
         assert stats["gemm_pair"] == 0 and stats["gemm_tc_single"] == 0 and stats["attn_ts_fwd"] == 0, stats
     m.close()
+    rep["failures"] = [str(f) for f in failures]
     REPORT["%s/%s" % (name, precision)] = rep
     out_dir = os.path.join(os.path.dirname(GOLDEN), os.pardir, "gpurun_out")
     if os.path.isdir(out_dir):
         with open(os.path.join(out_dir, "parity_large.json"), "w") as fh:
             json.dump(REPORT, fh, indent=1, sort_keys=True)
+    assert not failures, failures
