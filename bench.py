@@ -128,45 +128,90 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+def host_threads():
+    """Give the BLAS under NumPy every host core, explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    would turn the CPU arm into a one-core measurement.  Returns the thread count actually in effect."""
+    want = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=want)                       # stays in effect (no context manager): whole process
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return 1
+
+
+def reference_model(wl, dropout):
+    """(kind, model, step_fn): the UNMODIFIED reference (baseline/_ref, or /root/reference in the build container) when it
+    is installed -- kind "reference" -- else the oracle port."""
+    L, E, h, F, S, B, V = wl
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from install_reference import reference_path
+    ref = reference_path()
+    np.random.seed(0)
+    if ref is not None:
+        sys.dont_write_bytecode = True
+        if ref not in sys.path:
+            sys.path.insert(0, ref)
+        from Transformer.transformer import Transformer as RefTransformer
+        from utils.function import clip_grads
+        model = RefTransformer(V, E, h, F, L, S, dropout_p=dropout)
+
+        def step(x, y):                                      # transformer.py:635-641 with the clip of utils/train.py:122-129
+            logits, cache = model.forward(x)
+            loss, dlogits = model.calculate_loss_dlogits(logits, y)
+            grads = model.backward(cache, dlogits)
+            clip_grads(list(grads.values()), 1.0, lib=model.np)
+            model.step(grads, 1e-4)
+            return float(loss)
+        return "reference", model, step
+    from oracle.transformer_oracle import OracleTransformer, full_sequence_step
+    model = OracleTransformer(V, E, h, F, L, S, dropout_p=dropout)
+    return "port", model, lambda x, y: full_sequence_step(model, x, y, lr=1e-4, clip=1.0)[0]
+
+
+def cpu_sample_batch(wl):
+    """Sequences per CPU step: the bounded sample of the workload (a c4 step at batch 64 would take ~50 s)."""
+    L, E, h, F, S, B, V = wl
+    return max(1, min(B, 4 if S <= 512 else 1))
+
+
 def run_reference(args, wl):
-    """The reference's CPU algorithm (oracle port) on the host cores, bounded sample of the workload."""
+    """The reference's own CPU implementation of the step on the host cores, on a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.transformer_oracle import OracleTransformer, full_sequence_step
+    threads = host_threads()
     L, E, h, F, S, B, V = wl
-    sample_B = min(B, 4)
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count() or 1
-    np.random.seed(0)
-    model = OracleTransformer(V, E, h, F, L, S, dropout_p=0.1)
+    sample_B = cpu_sample_batch(wl)
+    kind, model, step = reference_model(wl, 0.1)
     rng = np.random.default_rng(1234)
     x = rng.integers(1, V, (sample_B, S)).astype(np.int32)
     y = rng.integers(1, V, (sample_B, S)).astype(np.int32)
     budget = 240.0
     t_start = time.perf_counter()
     for _ in range(args.warmup):
-        full_sequence_step(model, x, y, lr=1e-4, clip=1.0)
+        step(x, y)
         if time.perf_counter() - t_start > budget / 3:
             break
     done, t0 = 0, time.perf_counter()
     for _ in range(args.steps):
-        full_sequence_step(model, x, y, lr=1e-4, clip=1.0)
+        step(x, y)
         done += 1
         if time.perf_counter() - t_start > budget:
             break
     dt = time.perf_counter() - t0
     tok_s = done * sample_B * S / dt
-    sample = "oracle port (NumPy, f64 activations like the reference under numpy>=2), batch %d x seq %d, %d steps" % (
-        sample_B, S, done)
+    what = ("the unmodified reference (Transformer/transformer.py, NumPy %s, f64 activations under numpy>=2)" % np.__version__
+            if kind == "reference" else "oracle port (NumPy, f64 activations like the reference under numpy>=2)")
+    sample = "%s, batch %d x seq %d per step (sample of the batch-%d workload), %d steps, %d BLAS threads" % (
+        what, sample_B, S, B, done, threads)
+    cfg = workload_config(args.workload, wl, 1, "reference CPU path, sampled at batch %d" % sample_B)
+    cfg["batch_per_gpu"] = cfg["global_batch"] = sample_B
+    cfg["sample_of_batch_per_gpu"] = B
     line = {"impl": "reference", "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.workload, wl, 1, "reference CPU path"),
-            "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -180,27 +225,21 @@ def workload_config(name, wl, n_gpus, note):
 
 
 def cpu_baseline_sample(wl, seconds=20.0):
-    from oracle.transformer_oracle import OracleTransformer, full_sequence_step
+    threads = host_threads()
     L, E, h, F, S, B, V = wl
-    sample_B = min(B, 4)
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count() or 1
-    np.random.seed(0)
-    model = OracleTransformer(V, E, h, F, L, S, dropout_p=0.1)
+    sample_B = cpu_sample_batch(wl)
+    kind, model, step = reference_model(wl, 0.1)
     rng = np.random.default_rng(1234)
     x = rng.integers(1, V, (sample_B, S)).astype(np.int32)
     y = rng.integers(1, V, (sample_B, S)).astype(np.int32)
     t0, done = time.perf_counter(), 0
     while done < 1 or (time.perf_counter() - t0 < seconds and done < 8):
-        full_sequence_step(model, x, y, lr=1e-4, clip=1.0)
+        step(x, y)
         done += 1
     dt = time.perf_counter() - t0
-    return {"value": done * sample_B * S / dt, "unit": "tokens/s", "cores": threads, "kind": "port",
-            "sample": "oracle port, batch %d x seq %d, %d steps in %.1f s (f64 activations, OpenBLAS)" % (
-                sample_B, S, done, dt)}
+    return {"value": done * sample_B * S / dt, "unit": "tokens/s", "cores": threads, "kind": kind,
+            "sample": "%s, batch %d x seq %d (sample of the batch-%d workload), %d steps in %.1f s (f64 activations, OpenBLAS, %d threads)" % (
+                "unmodified reference" if kind == "reference" else "oracle port", sample_B, S, B, done, dt, threads)}
 
 
 def run_ours(args, wl):
@@ -215,8 +254,11 @@ def run_ours(args, wl):
     torch.cuda.set_device(local)
     distributed = world > 1
     if distributed:
-        # keep stdout to the one JSON line (NCCL prints its version banner there at VERSION/INFO level)
-        os.environ["NCCL_DEBUG"] = os.environ.get("NLPS_NCCL_DEBUG", "WARN")
+        # NCCL's INFO lines (communicator size, rings, NVLS) go to stderr so that the driver can verify the rank count;
+        # stdout stays the one JSON line.  Only the INIT subsystem: nothing is printed inside the timed region.
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     L, E, h, F, S, B, V = wl
     np.random.seed(1234)
@@ -319,18 +361,35 @@ def run_ours(args, wl):
         e_ms = float(t.item())
     e2e_value = B * S * world * e_steps / (e_ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (the tcgen05 GEMM), timed alone with CUDA events ----------
+    # ---- data parallel: every replica must hold the same weights after the timed steps ------------------------------
+    replicas_identical = None
+    if distributed:
+        import hashlib
+        model.synchronize()
+        digest = hashlib.sha256(model.flat("param").get().tobytes()).hexdigest()
+        digests = [None] * world
+        dist.all_gather_object(digests, digest)
+        replicas_identical = len(set(digests)) == 1
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM), timed alone with CUDA events; the denominator is the
+    #      tcgen05 kind::tf32 issue ceiling MEASURED in this run (csrc/tf32_peak.cu), one denominator for both fractions ----
     roof = None
     if rank == 0:
-        roof = gemm_roofline(torch, _lib, B * S, E, F, args.precision)
+        peak = measured_tf32_peak(_lib, local)
+        roof = gemm_roofline(torch, _lib, B * S, E, F, args.precision, peak)
         fpt = flops_per_token(L, E, F, S, V)
-        peaks = measured_peaks()
-        tf32_peak = peaks["bf16_sustained"] / 2.0
-        roof["step"] = {"algorithmic_tflop_per_step_per_gpu": fpt * B * S / 1e12,
-                        "achieved_tflops_per_gpu": fpt * value / world / 1e12,
-                        "frac_of_tf32_peak": fpt * value / world / 1e12 / tf32_peak,
-                        "tf32_peak_tflops": tf32_peak,
-                        "peak_note": "TF32 dense = 1/2 of the %s sustained BF16 peak in MEASURED_PEAKS.json" % peaks["source"]}
+        ach = fpt * value / world / 1e12
+        roof["step"] = {"algorithmic_tflop_per_step_per_gpu": fpt * B * S / 1e12, "achieved_tflops_per_gpu": ach,
+                        "frac_of_tf32_peak": ach / peak["tflops"], "tf32_peak_tflops": peak["tflops"],
+                        "frac_of_half_bf16_sustained": ach / (measured_peaks()["bf16_sustained"] / 2.0),
+                        "peak_note": peak["note"]}
+    # ---- other modes / configurations, a few steps each (device-resident), so that the FP32-faithful modes and
+    #      BASELINE.json configs[2] / configs[4] get numbers from the same driver-run command -------------------------
+    other = None
+    if not args.no_other and args.workload == "c4" and args.precision == "tf32":
+        model.close()
+        model = None
+        other = measure_others(args, torch, dist if distributed else None, rank, world, local)
     clocks = sampler.stop() if rank == 0 else None      # after the last GPU-timed leg (see ClockSampler)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -349,10 +408,84 @@ def run_ours(args, wl):
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": int(2 * nbytes),
                     "d2h_bytes_per_step": 4, "steps": e_steps, "ms_per_step": e_ms / e_steps},
             "roofline": roof, "cpu_baseline": cpu, "loss_first": first_loss, "loss_last": last_loss}
+    if replicas_identical is not None:
+        line["replicas_identical"] = replicas_identical
+    if other is not None:
+        line["other"] = other
     print(json.dumps(line), flush=True)
 
 
-def gemm_roofline(torch, _lib, N, E, F, precision):
+def measured_tf32_peak(_lib, device):
+    """tcgen05 kind::tf32 issue ceiling of THIS GPU, measured now (operands resident in shared memory, accumulators in
+    TMEM, no TMA / epilogue / global traffic): the better of the single-CTA (M128 N256) and CTA-pair (M256 N256) forms."""
+    best = None
+    for group in (1, 2):
+        tf, ms = C.c_float(), C.c_float()
+        _lib.call("nlps_tf32_mma_peak", C.c_int(device), C.c_int(group), C.c_int(4000), C.c_int(3), C.byref(tf), C.byref(ms))
+        if best is None or tf.value > best[0]:
+            best = (tf.value, group, ms.value)
+    half_bf16 = measured_peaks()
+    if not best[0] > 0:                       # should not happen on a B200; keep the line well-formed and say so
+        return {"tflops": half_bf16["bf16_burst"] / 2, "cta_group": 0, "ms": 0.0,
+                "note": "tcgen05 tf32 probe returned nothing: FALLBACK 1/2 of the %s burst BF16 peak" % half_bf16["source"]}
+    return {"tflops": best[0], "cta_group": best[1], "ms": best[2],
+            "note": "tcgen05.mma kind::tf32 issue ceiling measured in this run (nlps_tf32_mma_peak, cta_group::%d, %.2f ms "
+                    "burst); for comparison 1/2 of the %s BF16 cuBLAS peaks: %.0f burst / %.0f sustained TFLOP/s" % (
+                        best[1], best[2], half_bf16["source"], half_bf16["bf16_burst"] / 2, half_bf16["bf16_sustained"] / 2)}
+
+
+def measure_others(args, torch, dist, rank, world, local, steps=5, warmup=2):
+    """{name: {tokens/s, ms_per_step, ...}} for the FP32-faithful arithmetic modes on the headline workload and for the
+    other BASELINE.json configurations, device-resident, `steps` timed steps each after `warmup` (graph capture included
+    in the warm-up: eager, capture, replay).  Under torchrun every rank runs them (data parallel); loss read once."""
+    from nlpscratch_b200 import Transformer
+    from nlpscratch_b200.array import DeviceArray
+    plan = [("c4/tf32x3", "c4", "tf32x3"), ("c4/fp32", "c4", "fp32"), ("c3/tf32", "c3", "tf32"), ("c5/tf32", "c5", "tf32"),
+            ("c4-32k/tf32", "c4-32k", "tf32")]
+    if world > 1:
+        plan = [("c5/tf32", "c5", "tf32")]            # BASELINE.json configs[4]: the long-context model, data parallel
+    out = {}
+    for name, wname, prec in plan:
+        L, E, h, F, S, B, V = WORKLOADS[wname]
+        np.random.seed(1234)
+        m = Transformer(V, E, h, F, L, S, dropout_p=args.dropout, precision=prec, device=local)
+        dp = None
+        if dist is not None:
+            from nlpscratch_b200.dp import DataParallel
+            dp = DataParallel(m)
+            dp.broadcast_parameters(0)
+        rng = np.random.default_rng(99 + rank)
+        xd = [DeviceArray.from_host(rng.integers(1, V, (B, S)).astype(np.int32)) for _ in range(2)]
+        yd = [DeviceArray.from_host(rng.integers(1, V, (B, S)).astype(np.int32)) for _ in range(2)]
+        run = (lambda i: dp.train_step(xd[i % 2], yd[i % 2], 1e-4, 1.0)) if dp else (lambda i: m.train_step(xd[i % 2], yd[i % 2], 1e-4, 1.0))
+        n_warm = warmup + 2                           # eager, capture, then replays
+        for i in range(n_warm):
+            loss = run(i)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            loss = run(n_warm + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        fpt = flops_per_token(L, E, F, S, V)
+        tok_s = B * S * world * steps / (ms * 1e-3)
+        out[name] = {"value": tok_s, "unit": "tokens/s", "ms_per_step": ms / steps, "steps": steps, "warmup": n_warm,
+                     "precision": prec, "achieved_tflops_per_gpu": fpt * tok_s / world / 1e12, "loss": float(loss),
+                     "config": "%dL d%d h%d ff%d seq%d vocab%d batch%d/GPU dropout %.2f" % (L, E, h, F, S, V, B, args.dropout)}
+        m.close()
+        del m, dp, xd, yd
+    return out
+
+
+def gemm_roofline(torch, _lib, N, E, F, precision, peak_info):
     """FFN up-projection GEMM (N,E)x(E,F), the most frequent shape of the step, timed alone."""
     from nlpscratch_b200.array import DeviceArray, b200np
     prec = _lib.PREC[precision]
@@ -377,22 +510,24 @@ def gemm_roofline(torch, _lib, N, E, F, precision):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     flops = 2.0 * N * E * F
-    peaks = measured_peaks()
-    peak = peaks["bf16_burst"] / 2.0
+    peak = peak_info["tflops"]
     ach = flops / (ms * 1e-3) / 1e12
-    traffic = None
-    try:        # DRAM bytes of the same launch from the committed `ncu --set full` capture (profiles/)
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_ffn1_ncu.json")) as fh:
-            m = json.load(fh)
-        if (N, E, F) == (32768, 512, 2048):
-            traffic = (float(m["dram__bytes_read.sum"]["value"]) + float(m["dram__bytes_write.sum"]["value"])) * 1e6
-    except Exception:
-        traffic = None
+    traffic, src = None, None
+    for cand in ("r02_gemm_ffn1_ncu.json", "r01_gemm_ffn1_ncu.json"):
+        try:    # DRAM bytes of the same launch: NOT measured in this run (that needs ncu) -- from the committed capture
+            with open(os.path.join(ROOT, "profiles", cand)) as fh:
+                m = json.load(fh)
+            if (N, E, F) == (32768, 512, 2048):
+                traffic = (float(m["dram__bytes_read.sum"]["value"]) + float(m["dram__bytes_write.sum"]["value"])) * 1e6
+                src = cand
+                break
+        except Exception:
+            continue
     return {"bound": "tensor", "kernel": "gemm_tf32_pair_kernel (tcgen05 cta_group::2 kind::tf32) %dx%dx%d" % (N, F, E),
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
-            "traffic_note": "dram__bytes_read+write of this launch (profiles/r01_gemm_ffn1_ncu.json); algorithmic bytes %.1f MB" % (
-                (N * E + E * F + N * F) * 4 / 1e6),
-            "ms_per_launch": ms, "peak_note": "TF32 dense = 1/2 of the %s burst BF16 peak" % peaks["source"]}
+            "traffic_note": "NOT from this run: dram__bytes_read+write of this launch in the committed `ncu --set full` capture "
+                            "profiles/%s; algorithmic bytes %.1f MB" % (src, (N * E + E * F + N * F) * 4 / 1e6),
+            "ms_per_launch": ms, "peak_note": peak_info["note"]}
 
 
 def synthetic_prefix_dataset(V, max_len, n_sent=69, seed=0):
@@ -469,6 +604,7 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "tf32x3"])
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the secondary modes / configurations (\"other\" key)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (for ncu launch lists)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -162,6 +162,23 @@ int nlps_train_step_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x,
                                float grad_scale, int defer_update, float* d_loss);
 int nlps_launch_count(nlps_model* m, int64_t* launches, int reset);  /* kernels launched so far (process-wide counter) */
 
+/* ---- data-parallel exchange (the reference has no distributed code) -------------------------------------
+ * One process per GPU, batch rows sharded; the only exchange of the step is the sum of the flat gradient buffer over
+ * ranks.  The library owns NCCL (bound at run time with dlopen, so this file loads without it): rank 0 calls
+ * nlps_comm_unique_id and ships the 128 bytes to the other ranks by any means (the Python host uses torch.distributed's
+ * store); every rank calls nlps_comm_init.  From then on the UNDEFERRED fused steps (nlps_train_step,
+ * nlps_train_step_last_token with defer_update = 0) are data-parallel steps: each rank passes grad_scale =
+ * n_local / n_global, the gradient buckets are summed with ncclAllReduce on a communication stream as backward completes
+ * them (buckets coalesced to >= min_bucket_floats), clip + update run on the summed gradients -- all inside the call and,
+ * after its second sighting, inside ONE CUDA graph.  nlps_comm_allreduce_grads serves the unfused forward / backward API. */
+int nlps_comm_available(int* nccl_version);                          /* 0 if libnccl could be loaded */
+int nlps_comm_unique_id(void* h_id128);
+int nlps_comm_init(nlps_model* m, const void* h_id128, int rank, int world, int64_t min_bucket_floats);
+int nlps_comm_destroy(nlps_model* m);
+int nlps_comm_info(const nlps_model* m, int* rank, int* world, int* n_exchanges);   /* world 0: no communicator */
+int nlps_comm_allreduce_grads(nlps_model* m);
+int nlps_comm_broadcast_params(nlps_model* m, int root);
+
 /* Roofline denominator, measured: the tcgen05.mma kind::tf32 issue ceiling of this GPU with FP32 operands resident in
  * shared memory and accumulators in TMEM (the GEMM kernel's MMA loop with TMA, epilogue and global traffic removed;
  * csrc/tf32_peak.cu).  cta_group 1: M128 N256 per SM; 2: M256 N256 per SM pair.  iters groups of 16 MMAs per issuing unit,

@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libnlps_b200.so")
 SOURCES = ["util.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "attention.cu", "attention_mma.cu", "attention_tc.cu", "attention_ts.cu", "rowwise.cu", "embed.cu", "dataset.cu",
-           "optimizer.cu", "array_ops.cu", "tf32_peak.cu", "model.cu"]
+           "optimizer.cu", "array_ops.cu", "tf32_peak.cu", "comm_nccl.cu", "model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -71,7 +71,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             list(ex.map(compile_one, jobs))
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if jobs or not os.path.exists(LIB):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))

@@ -192,6 +192,13 @@ bool gemm_tf32_supported(const GemmArgs& g);
 bool gemm_tf32_colsum_fusable(const GemmArgs& g);   // colsum32_out may be set for this product
 bool gemm_tf32_rowdot_fusable(const GemmArgs& g);   // rowdot_out may be set for this product (rowdot_* fields filled in)
 int gemm_dispatch(cudaStream_t st, int precision, const GemmArgs& g);
+// comm_nccl.cu: libnccl bound at run time (dlopen); all return 0 on success
+int comm_available(int* version);
+int comm_unique_id(void* out128);
+int comm_create(const void* id128, int rank, int world, void** comm_out);
+int comm_destroy(void* comm);
+int comm_allreduce_sum(void* comm, float* buf, size_t count, cudaStream_t st);
+int comm_broadcast(void* comm, float* buf, size_t count, int root, cudaStream_t st);
 // tf32_peak.cu: measured tcgen05 kind::tf32 issue ceiling (operands resident in shared memory, accumulators in TMEM)
 int tf32_mma_peak(int cta_group, int iters, int reps, float* tflops, float* ms);
 

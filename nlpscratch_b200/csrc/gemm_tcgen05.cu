@@ -51,9 +51,26 @@ struct KernelArgs {
   int64_t ws_ld;
   int vec_ok;           // float4 epilogue allowed (alignment of C / residual / gate / N)
   int direct_ok;        // 32-B aligned output/fused operands: epilogue stores rows straight from registers
+  int x3_kb;            // 3xTF32 by K-concatenation: k-blocks per operand segment (0 = plain product); operands are [Ah | Al]
+  int x3_cb;            // and [Bh ; Bl] along K.  The virtual K axis is cut into chunks of x3_cb k-blocks; chunk c walks
+                        // (Al,Bh), (Ah,Bl), (Ah,Bh) over its k-blocks -- see x3_coords
   int debug;            // NLPS_GEMM_DEBUG bits: 1 = skip global stores, 2 = skip the whole epilogue body, 4 = .release.cluster
                         // TMEM-buffer hand-over, 8 = releasing cluster barrier at the end (the two pre-fix forms, for A/B)
 };
+
+// 3xTF32 by K-concatenation: K coordinates (in floats) of the A and B boxes of virtual k-block kb.
+// The tensor core accumulates with truncation (measured: the error of a kind::tf32 chain grows linearly with its length,
+// ~1e-8 relative per k-block, even when the addends are tiny), so an FP32-faithful product keeps its chains short and its
+// small terms first: the virtual axis is cut into chunks of `cb` k-blocks of the original K; chunk c is one split-K item
+// that accumulates Al*Bh, then Ah*Bl (while the accumulator is still ~2^-11 of its final size), then Ah*Bh over the chunk's
+// k-blocks; the chunk partials are summed with round-to-nearest FP32 adds by the split-K reducer.
+__device__ __forceinline__ void x3_coords(int kb, int seg_kb, int cb, int& a_k, int& b_k) {
+  const int c = kb / (3 * cb), j = kb - c * 3 * cb;
+  const int nb = min(cb, seg_kb - c * cb);
+  const int seg = j / nb, r = c * cb + (j - seg * nb);
+  a_k = ((seg == 0 ? seg_kb : 0) + r) * BK;      // Al, Ah, Ah
+  b_k = ((seg == 1 ? seg_kb : 0) + r) * BK;      // Bh, Bl, Bh
+}
 
 // ---- epilogue store of one 32x32 fp32 block, coalesced ---------------------------------
 // The warp re-reads the block it just transposed through smem so that one store instruction covers
@@ -324,18 +341,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t a_dst = base + stage * Cfg::kStageBytes;
           const uint32_t b_dst = a_dst + Cfg::kABytes;
           mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          const int k0 = kb * BK;
+          int ka0 = kb * BK, kb0k = ka0;
+          if (ka.x3_kb) x3_coords(kb, ka.x3_kb, ka.x3_cb, ka0, kb0k);
           if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_dst + j * 4096, &map_a, full_bar(stage), m0 + 32 * j, k0);
+            for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_dst + j * 4096, &map_a, full_bar(stage), m0 + 32 * j, ka0);
           } else {
-            tma_load_2d(a_dst, &map_a, full_bar(stage), k0, m0);
+            tma_load_2d(a_dst, &map_a, full_bar(stage), ka0, m0);
           }
           if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_dst + j * 4096, &map_b, full_bar(stage), n0 + 32 * j, k0);
+            for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_dst + j * 4096, &map_b, full_bar(stage), n0 + 32 * j, kb0k);
           } else {
-            tma_load_2d(b_dst, &map_b, full_bar(stage), k0, n0);
+            tma_load_2d(b_dst, &map_b, full_bar(stage), kb0k, n0);
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
@@ -505,18 +523,19 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           const uint32_t b_dst = a_dst + BM * BK * 4;
           const uint32_t lead_full = mapa_rank(full_bar(stage), 0);
           if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * kPairStageBytes);   // both CTAs' bytes land here
-          const int k0 = kb * BK;
+          int ka0 = kb * BK, kb0k = ka0;
+          if (ka.x3_kb) x3_coords(kb, ka.x3_kb, ka.x3_cb, ka0, kb0k);
           if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_2d_pair(a_dst + j * 4096, &map_a, lead_full, m0 + 32 * j, k0);
+            for (int j = 0; j < 4; ++j) tma_load_2d_pair(a_dst + j * 4096, &map_a, lead_full, m0 + 32 * j, ka0);
           } else {
-            tma_load_2d_pair(a_dst, &map_a, lead_full, k0, m0);
+            tma_load_2d_pair(a_dst, &map_a, lead_full, ka0, m0);
           }
           if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_2d_pair(b_dst + j * 4096, &map_b, lead_full, n0 + 32 * j, k0);
+            for (int j = 0; j < 4; ++j) tma_load_2d_pair(b_dst + j * 4096, &map_b, lead_full, n0 + 32 * j, kb0k);
           } else {
-            tma_load_2d_pair(b_dst, &map_b, lead_full, k0, n0);
+            tma_load_2d_pair(b_dst, &map_b, lead_full, kb0k, n0);
           }
           if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
         }
@@ -726,18 +745,23 @@ __global__ void __launch_bounds__(256) splitk_reduce_vec_kernel(const KernelArgs
   }
 }
 
-// hi = round-to-nearest TF32 of x (low 13 mantissa bits zero), lo = x - hi (exact in FP32)
-__global__ void split_hi_lo_kernel(const float* __restrict__ src, int64_t ld, int rows, int cols, int64_t ldo,
-                                   float* __restrict__ hi, float* __restrict__ lo) {
-  const int64_t total = (int64_t)rows * ldo;
+// 3xTF32 operand: hi = round-to-nearest TF32 of x (low 13 mantissa bits zero), lo = x - hi (exact in FP32), written side by
+// side ALONG K into one buffer with segment stride Kp (a multiple of the 32-float k-block; the gap is zero-filled):
+//   k_cols != 0 (K is the contiguous axis, source rows x K):  out[r][k] = hi, out[r][Kp + k] = lo,        ldo >= 2*Kp
+//   k_cols == 0 (K is the row axis, source K x cols):          out[k][c] = hi, out[Kp + k][c] = lo,        ldo >= cols
+__global__ void split_concat_kernel(const float* __restrict__ src, int64_t ld, int rows, int cols, int k_cols, int Kp,
+                                    int64_t ldo, float* __restrict__ out) {
+  const int R = k_cols ? rows : Kp, Cn = k_cols ? Kp : (int)ldo;
+  const int64_t total = (int64_t)R * Cn;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / ldo), c = (int)(i - (int64_t)r * ldo);
-    float x = c < cols ? src[(int64_t)r * ld + c] : 0.f;
+    const int r = (int)(i / Cn), c = (int)(i - (int64_t)r * Cn);
+    const float x = (r < rows && c < cols) ? src[(int64_t)r * ld + c] : 0.f;
     uint32_t hb;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
     const float h = __uint_as_float(hb);
-    hi[i] = h;
-    lo[i] = x - h;
+    out[(int64_t)r * ldo + c] = h;
+    if (k_cols) out[(int64_t)r * ldo + Kp + c] = x - h;
+    else out[((int64_t)Kp + r) * ldo + c] = x - h;
   }
 }
 
@@ -760,6 +784,28 @@ int splitk_workspace(cudaStream_t st, size_t bytes, float** out) {
     bump_alloc_epoch();
     w.ptr = nullptr; w.bytes = 0;
     const size_t want = std::max(bytes, (size_t)64 << 20);
+    NLPS_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.ptr), want));
+    w.bytes = want;
+  }
+  *out = w.ptr;
+  return 0;
+}
+
+// 3xTF32 operand workspace: like the split-K workspace, one grow-only buffer per (device, stream) -- no allocator call on
+// the hot path, so a 3xTF32 step can be captured into a CUDA graph (a re-allocation bumps the epoch and drops graphs)
+int x3_workspace(cudaStream_t st, size_t bytes, float** out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, SplitWs> table;
+  int dev = 0;
+  NLPS_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  SplitWs& w = table[{dev, st}];
+  if (w.bytes < bytes) {
+    NLPS_CUDA(cudaStreamSynchronize(st));
+    if (w.ptr) NLPS_CUDA(cudaFree(w.ptr));
+    bump_alloc_epoch();
+    w.ptr = nullptr; w.bytes = 0;
+    const size_t want = std::max(bytes + bytes / 4, (size_t)64 << 20);
     NLPS_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.ptr), want));
     w.bytes = want;
   }
@@ -817,7 +863,9 @@ int pair_mode() {                 // NLPS_GEMM_PAIR=0 disables the CTA-pair kern
   return v;
 }
 
-int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
+// x3 != 0: g.A / g.B are K-concatenated hi|lo operands (split_concat_kernel) with segment stride ceil(K/32)*32 and g.K is
+// the K of the original product; the kernel walks 3 * ceil(K/32) virtual k-blocks (x3_coords).
+int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32, bool x3 = false) {
   if (g.M <= 0 || g.N <= 0) return 0;
   NLPS_REQUIRE(g.K > 0, "gemm_tf32: K must be positive");
   NLPS_REQUIRE(gemm_tf32_supported(g), "gemm_tf32: operands not TMA-addressable (need 16-B aligned bases, ld %% 4 == 0)");
@@ -830,10 +878,20 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
   ka.g = g;
   ka.num_m_tiles = (int)ceil_div(g.M, BMT);
   ka.num_n_tiles = (int)ceil_div(g.N, BN);
-  ka.kblocks_total = (int)ceil_div(g.K, BK);
+  const int seg_kb = (int)ceil_div(g.K, BK);
+  ka.x3_kb = x3 ? seg_kb : 0;
+  ka.kblocks_total = x3 ? 3 * seg_kb : seg_kb;
+  const uint64_t k_extent = x3 ? (uint64_t)2 * seg_kb * BK : (uint64_t)g.K;     // K extent of the tensor maps
   const int tiles = ka.num_m_tiles * ka.num_n_tiles;
   int splits = 1;
-  if (tiles < 2 * units && ka.kblocks_total >= 64) {
+  ka.x3_cb = 0;
+  if (x3) {
+    // one split-K item per chunk of x3_cb original k-blocks (default 8 = 256 floats of K); NLPS_X3_CHUNK overrides
+    static int cb_env = -1;
+    if (cb_env < 0) { const char* e = getenv("NLPS_X3_CHUNK"); cb_env = e ? std::max(1, atoi(e)) : 8; }
+    ka.x3_cb = std::min(cb_env, seg_kb);
+    splits = (int)ceil_div(seg_kb, ka.x3_cb);
+  } else if (tiles < 2 * units && ka.kblocks_total >= 64) {
     // weight-gradient shaped (few tiles, long K): pick the split that minimises
     //   waves(s) * (k-blocks per split + fixed per-tile cost)   with whole waves of CTAs / CTA pairs
     double best = 1e30;
@@ -843,7 +901,7 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
       if (t < best - 1e-9) { best = t; splits = s; }
     }
   }
-  ka.kblocks_per_split = (int)ceil_div(ka.kblocks_total, splits);
+  ka.kblocks_per_split = x3 ? 3 * ka.x3_cb : (int)ceil_div(ka.kblocks_total, splits);
   splits = (int)ceil_div(ka.kblocks_total, ka.kblocks_per_split);
   ka.splits = splits;
   ka.vec_ok = (aligned16(g.C) && g.ldc % 4 == 0 &&
@@ -872,10 +930,10 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32) {
   if (splits > 1) NLPS_TRY(splitk_workspace(st, (size_t)splits * g.M * ka.ws_ld * sizeof(float), &ka.ws));
   CUtensorMap ma, mb;
   const uint32_t b_rows = pair ? 128u : (uint32_t)BN;      // a CTA of a pair loads half of the B tile
-  if (g.trans_a) NLPS_TRY(make_map(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K, g.lda, 32, BK, round_tf32, true));
-  else NLPS_TRY(make_map(&ma, g.A, (uint64_t)g.K, (uint64_t)g.M, g.lda, BK, BM, round_tf32, false));
-  if (g.trans_b) NLPS_TRY(make_map(&mb, g.B, (uint64_t)g.K, (uint64_t)g.N, g.ldb, BK, b_rows, round_tf32, false));
-  else NLPS_TRY(make_map(&mb, g.B, (uint64_t)g.N, (uint64_t)g.K, g.ldb, 32, BK, round_tf32, true));
+  if (g.trans_a) NLPS_TRY(make_map(&ma, g.A, (uint64_t)g.M, k_extent, g.lda, 32, BK, round_tf32, true));
+  else NLPS_TRY(make_map(&ma, g.A, k_extent, (uint64_t)g.M, g.lda, BK, BM, round_tf32, false));
+  if (g.trans_b) NLPS_TRY(make_map(&mb, g.B, k_extent, (uint64_t)g.N, g.ldb, BK, b_rows, round_tf32, false));
+  else NLPS_TRY(make_map(&mb, g.B, (uint64_t)g.N, k_extent, g.ldb, 32, BK, round_tf32, true));
   const int items = tiles * splits;
   count_kind(pair ? KIND_GEMM_PAIR : KIND_GEMM_TC_SINGLE);
   if (pair) {
@@ -925,45 +983,32 @@ bool gemm_tf32_rowdot_fusable(const GemmArgs& g) {
   return g.rowdot_in != nullptr && (reinterpret_cast<uintptr_t>(g.rowdot_in) & 31u) == 0 && g.ld_rowdot % 8 == 0;
 }
 
-// 3xTF32: A = Ah + Al, B = Bh + Bl with Ah,Bh exactly representable in TF32;
-// T = Al*Bh + Ah*Bl + Ah*Bh (small terms first), dropping only Al*Bl (~2^-22 relative);
-// the fused epilogue then runs once over T.
+// 3xTF32: A = Ah + Al, B = Bh + Bl with Ah, Bh exactly representable in TF32; C = Al*Bh + Ah*Bl + Ah*Bh, dropping only
+// Al*Bl (~2^-22 relative).  ONE tensor-core launch over a virtual K axis three segments long: the operands are written once
+// as [Ah | Al] and [Bh ; Bl] (split_concat_kernel) and the kernel's TMA producer pairs the segments chunk by chunk
+// (x3_coords); chunks of 256 K are split-K items whose partials the reducer adds in FP32 (round to nearest) before the fused
+// epilogue (bias / ReLU / gate / dropout / residual) -- no allocator call (CUDA-graph capturable).
 int gemm_tf32x3(cudaStream_t st, const GemmArgs& g) {
   if (g.M <= 0 || g.N <= 0) return 0;
-  const int a_rows = g.trans_a ? g.K : g.M, a_cols = g.trans_a ? g.M : g.K;
-  const int b_rows = g.trans_b ? g.N : g.K, b_cols = g.trans_b ? g.K : g.N;
-  const int64_t lda2 = round_up(a_cols, 4), ldb2 = round_up(b_cols, 4), ldt = round_up(g.N, 4);
-  const size_t na = (size_t)a_rows * lda2, nb = (size_t)b_rows * ldb2, nt = (size_t)g.M * ldt;
+  const int Kp = (int)ceil_div(g.K, BK) * BK;
+  const int64_t lda2 = g.trans_a ? round_up(g.M, 4) : 2 * (int64_t)Kp;
+  const int64_t ldb2 = g.trans_b ? 2 * (int64_t)Kp : round_up(g.N, 4);
+  const size_t na = (size_t)(g.trans_a ? 2 * (int64_t)Kp : (int64_t)g.M) * lda2;
+  const size_t nb = (size_t)(g.trans_b ? (int64_t)g.N : 2 * (int64_t)Kp) * ldb2;
+  const size_t na_al = (na + 63) / 64 * 64;                      // keep B2 256-B aligned
   float* buf = nullptr;
-  ensure_mempool_config();
-  NLPS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&buf), (2 * na + 2 * nb + nt) * sizeof(float), st));
-  float *ah = buf, *al = buf + na, *bh = buf + 2 * na, *bl = buf + 2 * na + nb, *tmp = buf + 2 * na + 2 * nb;
-  split_hi_lo_kernel<<<(int)std::min<int64_t>(ceil_div((int64_t)na, 256), kNumSMs * 8), 256, 0, st>>>(
-      g.A, g.lda, a_rows, a_cols, lda2, ah, al);
+  NLPS_TRY(x3_workspace(st, (na_al + nb) * sizeof(float), &buf));
+  float *a2 = buf, *b2 = buf + na_al;
+  auto grid_for = [](int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), kNumSMs * 8)); };
+  if (g.trans_a) split_concat_kernel<<<grid_for((int64_t)Kp * lda2), 256, 0, st>>>(g.A, g.lda, g.K, g.M, 0, Kp, lda2, a2);
+  else split_concat_kernel<<<grid_for((int64_t)g.M * Kp), 256, 0, st>>>(g.A, g.lda, g.M, g.K, 1, Kp, lda2, a2);
   NLPS_LAUNCH_CHECK();
-  split_hi_lo_kernel<<<(int)std::min<int64_t>(ceil_div((int64_t)nb, 256), kNumSMs * 8), 256, 0, st>>>(
-      g.B, g.ldb, b_rows, b_cols, ldb2, bh, bl);
+  if (g.trans_b) split_concat_kernel<<<grid_for((int64_t)g.N * Kp), 256, 0, st>>>(g.B, g.ldb, g.N, g.K, 1, Kp, ldb2, b2);
+  else split_concat_kernel<<<grid_for((int64_t)Kp * ldb2), 256, 0, st>>>(g.B, g.ldb, g.K, g.N, 0, Kp, ldb2, b2);
   NLPS_LAUNCH_CHECK();
-  GemmArgs p{};
-  p.M = g.M; p.N = g.N; p.K = g.K; p.trans_a = g.trans_a; p.trans_b = g.trans_b;
-  p.lda = lda2; p.ldb = ldb2; p.C = tmp; p.ldc = ldt;
-  p.A = al; p.B = bh;
-  NLPS_TRY(gemm_tf32_impl(st, p, false));
-  p.accumulate = true;
-  p.A = ah; p.B = bl;
-  NLPS_TRY(gemm_tf32_impl(st, p, false));
-  p.A = ah; p.B = bh;
-  NLPS_TRY(gemm_tf32_impl(st, p, false));
-  KernelArgs ka{};
-  ka.g = g;
-  ka.splits = 1;
-  ka.ws = tmp;
-  ka.ws_ld = ldt;
-  const int64_t total = (int64_t)g.M * g.N;
-  splitk_reduce_kernel<<<(int)std::min<int64_t>(ceil_div(total, 256), kNumSMs * 8), 256, 0, st>>>(ka);
-  NLPS_LAUNCH_CHECK();
-  NLPS_CUDA(cudaFreeAsync(buf, st));
-  return 0;
+  GemmArgs p = g;
+  p.A = a2; p.lda = lda2; p.B = b2; p.ldb = ldb2;
+  return gemm_tf32_impl(st, p, false, /*x3=*/true);
 }
 
 int gemm_dispatch(cudaStream_t st, int precision, const GemmArgs& g) {

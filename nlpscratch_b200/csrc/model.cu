@@ -96,6 +96,15 @@ struct nlps_model {
 
   std::vector<nlps_cache*> pool;
 
+  // ---- data-parallel exchange owned by the library (nlps_comm_init): NCCL communicator, its stream, the coalesced bucket
+  // groups (ranges of bucket indices in completion order), and whether the current call reduces inside backward ----
+  void* comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t comm_done = nullptr;
+  std::vector<std::pair<int, int>> comm_plan;
+  bool comm_active = false;
+
   // ---- CUDA graph of the fused full-sequence step (nlps_train_step) ----
   // One graph per (cache, x, y, clip, scale, mode) signature; the only node whose parameters change from step to step is
   // the setter that publishes the step's scalars (dropout counter, lr, Adam bias corrections) to device memory.
@@ -258,19 +267,52 @@ int wgrad_join(nlps_model* m) {
   return 0;
 }
 
+// contiguous runs of the flat buffer covered by buckets [lo, hi) (adjacent layers are adjacent in memory)
+std::vector<std::pair<int64_t, int64_t>> merged_ranges(const nlps_model* m, int lo, int hi) {
+  std::vector<std::pair<int64_t, int64_t>> r(m->buckets.begin() + lo, m->buckets.begin() + hi);
+  std::sort(r.begin(), r.end());
+  std::vector<std::pair<int64_t, int64_t>> out;
+  for (auto& q : r) {
+    if (!out.empty() && out.back().first + out.back().second == q.first) out.back().second += q.second;
+    else out.push_back(q);
+  }
+  return out;
+}
+
+// bucket `bucket` is final (its event has been recorded): if it closes a group of the exchange plan, the communication
+// stream waits for that event and sums the group's ranges over ranks while backward goes on
+int comm_on_bucket(nlps_model* m, int bucket) {
+  for (auto& grp : m->comm_plan) {
+    if (grp.second - 1 != bucket) continue;
+    NLPS_CUDA(cudaStreamWaitEvent(m->comm_stream, m->bucket_ev[bucket], 0));
+    for (auto& r : merged_ranges(m, grp.first, grp.second))
+      NLPS_TRY(comm_allreduce_sum(m->comm, m->G + r.first, (size_t)r.second, m->comm_stream));
+  }
+  return 0;
+}
+// the main stream continues (clip + update) only after every reduction
+int comm_join(nlps_model* m) {
+  NLPS_CUDA(cudaEventRecord(m->comm_done, m->comm_stream));
+  NLPS_CUDA(cudaStreamWaitEvent(m->stream, m->comm_done, 0));
+  return 0;
+}
+
 int record_bucket(nlps_model* m, int bucket, bool on_wstream = false) {
+  // Who needs the event: the library's own exchange (comm_active), a caller-side exchange (eager step, or a captured
+  // deferred step whose records become EXTERNAL event-record nodes that a communication stream waits on after the graph
+  // launch).  A captured single-GPU step needs none.
+  const bool external = m->in_graph_body && m->graph_external_events && !m->comm_active;
+  const bool need_event = m->comm_active || !m->in_graph_body || m->graph_external_events;
+  if (!need_event) return 0;
   // a bucket that holds weight gradients is complete when the weight-gradient stream has passed this point too
   cudaStream_t rs = m->stream;
-  if (on_wstream && m->wstream && !(m->in_graph_body && !m->graph_external_events)) NLPS_TRY(wgrad_fork(m, &rs));
-  if (m->in_graph_body) {
-    // single-GPU captured step: nobody waits on the bucket events.  Deferred (data-parallel) captured step: the record
-    // becomes an external event-record node, so the communication stream's cudaStreamWaitEvent after the graph launch
-    // waits for this point of the replay.
-    if (!m->graph_external_events) return 0;
+  if (on_wstream && m->wstream) NLPS_TRY(wgrad_fork(m, &rs));
+  if (external) {
     NLPS_CUDA(cudaEventRecordWithFlags(m->bucket_ev[bucket], rs, cudaEventRecordExternal));
     return 0;
   }
   NLPS_CUDA(cudaEventRecord(m->bucket_ev[bucket], rs));
+  if (m->comm_active) NLPS_TRY(comm_on_bucket(m, bucket));
   return 0;
 }
 
@@ -566,6 +608,9 @@ int nlps_destroy(nlps_model* m) {
   if (m->colsum_tickets) cudaFree(m->colsum_tickets);
   if (m->hyper) cudaFree(m->hyper);
   drop_step_graphs(m);
+  if (m->comm) { comm_destroy(m->comm); m->comm = nullptr; }
+  if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
+  if (m->comm_done) cudaEventDestroy(m->comm_done);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   if (m->wstream) cudaStreamDestroy(m->wstream);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
@@ -991,18 +1036,32 @@ static int train_step_body(nlps_model* m, nlps_cache* c, const int32_t* d_x, int
   c->rowstat_valid = false;
   NLPS_TRY(nlps_backward(m, c, c->logits, m->ldV));
   if (defer_update) return 0;
+  if (m->comm_active) NLPS_TRY(comm_join(m));          // gradients are now the sum over ranks
   if (max_norm > 0.f) NLPS_TRY(nlps_clip_compute(m, max_norm));
   return nlps_step(m, lr, max_norm > 0.f ? 1 : 0);
 }
 
+static int train_step_graphed(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_y, float lr,
+                              float max_norm, float grad_scale, int defer_update, float* d_loss);
+
 int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_y, float lr,
                     float max_norm, float grad_scale, int defer_update, float* d_loss) {
   NLPS_REQUIRE(m && c && d_x && d_y, "nlps_train_step: null argument");
-  // CUDA graph path: single-GPU update in the same call, on a capturable stream, 1xTF32 or FP32 arithmetic (the 3xTF32
-  // split allocates stream-ordered scratch per product).  First sighting of a signature runs eagerly (it sizes every
-  // workspace), the second one is captured, later ones are replayed with one patched node.
+  // with a communicator attached (nlps_comm_init) the undeferred step is the data-parallel step: the gradient buckets are
+  // summed over ranks on the communication stream as backward completes them, and clip + update wait for the sums
+  m->comm_active = m->comm != nullptr && !defer_update;
+  const int rc = train_step_graphed(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
+  m->comm_active = false;
+  return rc;
+}
+
+static int train_step_graphed(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_y, float lr,
+                              float max_norm, float grad_scale, int defer_update, float* d_loss) {
+  // CUDA graph path, every arithmetic mode (the 3xTF32 operands live in a grow-only per-stream workspace).  First sighting
+  // of a signature runs eagerly (it sizes every workspace), the second one is captured, later ones are replayed with one
+  // patched node.
   static const bool dp_graph = [] { const char* e = getenv("NLPS_GRAPH_DP"); return !(e && e[0] == '0'); }();
-  const bool graphable = m->graph_mode == 1 && (!defer_update || dp_graph) && m->stream != nullptr && m->precision != NLPS_PREC_TF32X3;
+  const bool graphable = m->graph_mode == 1 && (!defer_update || dp_graph) && m->stream != nullptr;
   const bool deferred = defer_update != 0;
   if (!graphable) return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
   NLPS_CUDA(cudaSetDevice(m->device));
@@ -1141,10 +1200,88 @@ int nlps_train_step_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x,
   float* loss = d_loss ? d_loss : m->scalars + 3;
   // row-loss scratch: the first B floats of rows_tmp are free until backward_last_token runs
   NLPS_TRY(softmax_xent(m->stream, logits, m->ldV, d_y, B, m->V, grad_scale, loss, logits, m->ldV, m->rows_tmp, m->err_flag));
-  NLPS_TRY(nlps_backward_last_token(m, c, d_t, logits, m->ldV));
+  m->comm_active = m->comm != nullptr && !defer_update;
+  int rc = nlps_backward_last_token(m, c, d_t, logits, m->ldV);
+  if (rc == 0 && m->comm_active) rc = comm_join(m);
+  m->comm_active = false;
+  if (rc != 0) return rc;
   if (defer_update) return 0;
   if (max_norm > 0.f) NLPS_TRY(nlps_clip_compute(m, max_norm));
   return nlps_step(m, lr, max_norm > 0.f ? 1 : 0);
+}
+
+// ---- data-parallel exchange ------------------------------------------------------------------------------
+int nlps_comm_available(int* nccl_version) { return comm_available(nccl_version) ? 0 : (set_error("libnccl.so.2 could not be loaded"), 1); }
+
+int nlps_comm_unique_id(void* h_id128) {
+  NLPS_REQUIRE(h_id128, "nlps_comm_unique_id: null argument");
+  return comm_unique_id(h_id128);
+}
+
+int nlps_comm_init(nlps_model* m, const void* h_id128, int rank, int world, int64_t min_bucket_floats) {
+  NLPS_REQUIRE(m && h_id128, "nlps_comm_init: null argument");
+  NLPS_REQUIRE(m->comm == nullptr, "nlps_comm_init: the model already has a communicator");
+  NLPS_CUDA(cudaSetDevice(m->device));
+  NLPS_TRY(comm_create(h_id128, rank, world, &m->comm));
+  m->comm_rank = rank; m->comm_world = world;
+  int pri_least = 0, pri_greatest = 0;
+  NLPS_CUDA(cudaDeviceGetStreamPriorityRange(&pri_least, &pri_greatest));
+  NLPS_CUDA(cudaStreamCreateWithPriority(&m->comm_stream, cudaStreamNonBlocking, pri_greatest));
+  NLPS_CUDA(cudaEventCreateWithFlags(&m->comm_done, cudaEventDisableTiming));
+  // coalesce consecutive buckets (completion order) into exchanges of at least min_bucket_floats: NVSwitch collectives
+  // are latency-, not link-bound, so small buckets ride with their neighbours
+  m->comm_plan.clear();
+  int start = 0; int64_t acc = 0;
+  for (int b = 0; b < (int)m->buckets.size(); ++b) {
+    acc += m->buckets[b].second;
+    if (acc >= min_bucket_floats || b == (int)m->buckets.size() - 1) { m->comm_plan.push_back({start, b + 1}); start = b + 1; acc = 0; }
+  }
+  drop_step_graphs(m);
+  return 0;
+}
+
+int nlps_comm_destroy(nlps_model* m) {
+  NLPS_REQUIRE(m, "null model");
+  if (m->comm == nullptr) return 0;
+  NLPS_CUDA(cudaSetDevice(m->device));
+  NLPS_CUDA(cudaStreamSynchronize(m->stream));
+  NLPS_CUDA(cudaStreamSynchronize(m->comm_stream));
+  drop_step_graphs(m);
+  NLPS_TRY(comm_destroy(m->comm));
+  m->comm = nullptr; m->comm_world = 1; m->comm_rank = 0;
+  m->comm_plan.clear();
+  return 0;
+}
+
+int nlps_comm_info(const nlps_model* m, int* rank, int* world, int* n_exchanges) {
+  NLPS_REQUIRE(m, "null model");
+  if (rank) *rank = m->comm_rank;
+  if (world) *world = m->comm ? m->comm_world : 0;
+  if (n_exchanges) *n_exchanges = (int)m->comm_plan.size();
+  return 0;
+}
+
+// sum of the whole flat gradient buffer over ranks, after everything enqueued on the model's stream (the unfused API:
+// forward / backward / [this] / clip / step); the model's stream continues after the sum
+int nlps_comm_allreduce_grads(nlps_model* m) {
+  NLPS_REQUIRE(m && m->comm, "nlps_comm_allreduce_grads: no communicator (nlps_comm_init)");
+  NLPS_CUDA(cudaSetDevice(m->device));
+  NLPS_CUDA(cudaEventRecord(m->aux_ev, m->stream));
+  NLPS_CUDA(cudaStreamWaitEvent(m->comm_stream, m->aux_ev, 0));
+  NLPS_TRY(comm_allreduce_sum(m->comm, m->G, (size_t)m->flat, m->comm_stream));
+  return comm_join(m);
+}
+
+// identical replicas: rank `root`'s parameters (and Adam moments) everywhere
+int nlps_comm_broadcast_params(nlps_model* m, int root) {
+  NLPS_REQUIRE(m && m->comm, "nlps_comm_broadcast_params: no communicator (nlps_comm_init)");
+  NLPS_REQUIRE(root >= 0 && root < m->comm_world, "root %d out of range", root);
+  NLPS_CUDA(cudaSetDevice(m->device));
+  NLPS_CUDA(cudaEventRecord(m->aux_ev, m->stream));
+  NLPS_CUDA(cudaStreamWaitEvent(m->comm_stream, m->aux_ev, 0));
+  float* bufs[] = {m->P, m->M, m->Vv};
+  for (float* b : bufs) NLPS_TRY(comm_broadcast(m->comm, b, (size_t)m->flat, root, m->comm_stream));
+  return comm_join(m);
 }
 
 int nlps_tf32_mma_peak(int device, int cta_group, int iters, int reps, float* h_tflops, float* h_ms) {

@@ -8,10 +8,13 @@ equal shards), the flat gradient buffer is summed with NCCL, and clip + Adam the
 on every rank.
 
 Overlap: the C library records one CUDA event per gradient bucket ([vocab] [layer L-1] ... [layer 0]
-[We], contiguous ranges of the flat buffer) as backward completes it; the whole step is enqueued
-asynchronously, so the all-reduces are enqueued on a side stream right behind it and run on
-NVLink while earlier layers are still in backward.  torch is used for exactly two things here:
-``torch.distributed`` (NCCL / gloo) and a CUDA side stream.
+[We], contiguous ranges of the flat buffer) as backward completes it, and -- default backend ``"native"`` --
+owns the exchange itself: ``nlps_comm_init`` creates an NCCL communicator inside ``libnlps_b200.so``, and
+the undeferred fused step then sums each bucket group with ``ncclAllReduce`` on a communication stream
+while earlier layers are still in backward, followed by clip + Adam -- ONE library call, ONE CUDA graph
+after its second sighting.  ``torch.distributed`` is plumbing only: rendezvous, shipping the 128-byte
+NCCL id, barriers.  ``backend="torch"`` keeps the round-1 path (``dist.all_reduce`` per bucket from
+Python on a torch side stream, clip + Adam eager behind it) for A/B runs.
 """
 from __future__ import annotations
 
@@ -72,17 +75,32 @@ def allreduce_sum_host(arrays: Sequence[np.ndarray], group=None):
 class DataParallel:
     """Wraps a ``nlpscratch_b200.Transformer`` for one rank of a data-parallel job."""
 
-    def __init__(self, model, group=None, min_bucket_floats: int = 1 << 20, overlap: bool = True):
+    def __init__(self, model, group=None, min_bucket_floats: int = 1 << 20, overlap: bool = True,
+                 backend: Optional[str] = None):
         import ctypes as C
+        import os
         import torch
         import torch.distributed as dist
         from . import _lib
         if not dist.is_initialized():
-            raise RuntimeError("torch.distributed must be initialised (NCCL) before DataParallel")
+            raise RuntimeError("torch.distributed must be initialised before DataParallel")
         self.model, self.group, self.overlap = model, group, overlap
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self._torch, self._dist, self._lib, self._C = torch, dist, _lib, C
+        self.backend = backend or os.environ.get("NLPS_DP_BACKEND", "native")
+        if self.backend not in ("native", "torch"):
+            raise ValueError("backend must be 'native' or 'torch'")
+        if self.backend == "native":
+            # rank 0 makes the NCCL id, torch.distributed's store ships its 128 bytes, every rank joins
+            ident = [None]
+            if self.rank == 0:
+                buf = (C.c_char * 128)()
+                _lib.call("nlps_comm_unique_id", buf)
+                ident[0] = bytes(buf.raw)
+            dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            _lib.call("nlps_comm_init", model._h, C.c_char_p(ident[0]), C.c_int(self.rank), C.c_int(self.world),
+                      C.c_int64(int(min_bucket_floats)))
         n = C.c_int()
         _lib.call("nlps_num_buckets", model._h, C.byref(n))
         self.ranges = []
@@ -100,12 +118,20 @@ class DataParallel:
 
     def broadcast_parameters(self, src: int = 0):
         """Identical replicas: rank ``src``'s weights everywhere (the reference has one process)."""
+        if self.backend == "native":
+            self._lib.call("nlps_comm_broadcast_params", self.model._h, self._C.c_int(int(src)))
+            self.model.synchronize()
+            return
         self.model.synchronize()
         self._dist.broadcast(self._param_t, src=src, group=self.group)
         self._torch.cuda.current_stream().synchronize()
 
     def allreduce_gradients(self):
-        """Sum the flat gradient buffer over ranks, bucket by bucket as backward finishes them."""
+        """Sum the flat gradient buffer over ranks (after an unfused backward or a deferred step): bucket by bucket as
+        backward finishes them on the torch backend, one library call on the native one."""
+        if self.backend == "native":
+            self._lib.call("nlps_comm_allreduce_grads", self.model._h)
+            return
         torch, dist, C = self._torch, self._dist, self._C
         m = self.model
         cs = self.comm_stream
@@ -124,12 +150,19 @@ class DataParallel:
                    weight: Optional[float] = None):
         """One data-parallel step; returns this rank's local mean loss (device scalar)."""
         w = (1.0 / self.world) if weight is None else float(weight)
+        if self.backend == "native":       # forward, loss, backward || bucketed ncclAllReduce, clip, Adam: one call, one graph
+            return self.model.train_step(x_local, y_local, learning_rate, clip_grad_norm, grad_scale=w)
         loss = self.model.train_step(x_local, y_local, learning_rate, clip_grad_norm, grad_scale=w,
                                      defer_update=True)
         if self.world > 1:
             self.allreduce_gradients()
         self.model.apply_update(learning_rate, clip_grad_norm)
         return loss
+
+
+    def close(self):
+        if self.backend == "native" and self.model.__dict__.get("_h") is not None:
+            self._lib.call("nlps_comm_destroy", self.model._h)
 
 
 def save_checkpoint_rank0(dp: "DataParallel", filename: str):

@@ -81,11 +81,13 @@ class FakeModel:
     def __init__(self, *a, **k): self.n = 0
     def train_step(self, *a, **k): self.n += 1; return 9.0
     def launch_count(self, reset=False): return 174 * self.n
+    def close(self): pass
+    def synchronize(self): pass
 nlpscratch_b200.Transformer = FakeModel
 ctypes.memmove = lambda *a: None
 import importlib.util
 spec = importlib.util.spec_from_file_location("bench", %r); b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
-sys.argv = ["bench.py", "--steps", "4", "--warmup", "3", "--no-cpu-baseline"]
+sys.argv = ["bench.py", "--steps", "4", "--warmup", "3", "--no-cpu-baseline", "--no-other"]
 b.main()
 """
 
@@ -106,3 +108,20 @@ def test_bench_line_contract_dry_run(tmp_path):
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert "workload" in line["config"] and "model" not in line["config"]
     assert line["clocks"]["reasons"] == ["sw_power_cap"]
+    assert "FALLBACK" in line["roofline"]["peak_note"]          # the stand-in library measured nothing: said, not hidden
+
+
+def test_reference_arm_runs_the_real_reference_with_all_host_threads(tmp_path):
+    """`bench.py --impl reference` under torchrun's OMP_NUM_THREADS=1: the arm must still use every host core, must run the
+    unmodified reference when it is installed, and must state the batch it really ran (VERDICT r01 bench hygiene)."""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=240)
+    assert res.returncode == 0, res.stderr[-3000:]
+    line = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["e2e"]["value"] == line["value"]
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert line["config"]["batch_per_gpu"] == 4 and line["config"]["sample_of_batch_per_gpu"] == 4
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from install_reference import reference_path
+    assert line["cpu_baseline"]["kind"] == ("reference" if reference_path() else "port")
