@@ -253,12 +253,18 @@ def run_ours(args, wl):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     distributed = world > 1
+    real_stdout = sys.stdout
     if distributed:
-        # NCCL's INFO lines (communicator size, rings, NVLS) go to stderr so that the driver can verify the rank count;
-        # stdout stays the one JSON line.  Only the INIT subsystem: nothing is printed inside the timed region.
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        # NCCL's INFO lines (communicator size, rings, NVLS) must be visible so that the driver can verify the rank count,
+        # and stdout must stay the one JSON line: NCCL writes to the process's stdout (file descriptor 1), so descriptor 1
+        # is pointed at stderr for the whole run and the JSON line is written to a saved copy of the real stdout.
+        # Only the INIT subsystem is logged: nothing is printed inside the timed region.
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):     # the box's default is VERSION
+            os.environ["NCCL_DEBUG"] = os.environ.get("NLPS_NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        real_stdout = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     L, E, h, F, S, B, V = wl
     np.random.seed(1234)
@@ -268,6 +274,11 @@ def run_ours(args, wl):
         from nlpscratch_b200.dp import DataParallel
         dp = DataParallel(model)
         dp.broadcast_parameters(0)
+        if dp.backend == "native":
+            r_, w_, n_ = C.c_int(), C.c_int(), C.c_int()
+            _lib.call("nlps_comm_info", model._h, C.byref(r_), C.byref(w_), C.byref(n_))
+            print("[nlps] NCCL communicator owned by libnlps_b200.so: rank %d nranks %d (ncclCommCount), %d bucket exchanges per step"
+                  % (r_.value, w_.value, n_.value), file=sys.stderr, flush=True)
     rng = np.random.default_rng(1234 + rank)
     nbatches = 4
     xs = [rng.integers(1, V, (B, S)).astype(np.int32) for _ in range(nbatches)]
@@ -321,7 +332,7 @@ def run_ours(args, wl):
         if rank == 0:
             sampler.stop()
             print(json.dumps({"metric": METRIC, "value": value, "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
-                              "quick": True, "loss_last": last_loss}), flush=True)
+                              "quick": True, "loss_last": last_loss}), file=real_stdout, flush=True)
         if distributed:
             dist.barrier()
             dist.destroy_process_group()
@@ -412,7 +423,7 @@ def run_ours(args, wl):
         line["replicas_identical"] = replicas_identical
     if other is not None:
         line["other"] = other
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=real_stdout, flush=True)
 
 
 def measured_tf32_peak(_lib, device):

@@ -1226,7 +1226,10 @@ int nlps_comm_init(nlps_model* m, const void* h_id128, int rank, int world, int6
   m->comm_rank = rank; m->comm_world = world;
   int pri_least = 0, pri_greatest = 0;
   NLPS_CUDA(cudaDeviceGetStreamPriorityRange(&pri_least, &pri_greatest));
-  NLPS_CUDA(cudaStreamCreateWithPriority(&m->comm_stream, cudaStreamNonBlocking, pri_greatest));
+  // NLPS_COMM_PRIO=low|high (A/B): with high priority NCCL's CTAs take the first SMs that free up (earliest exchange);
+  // with low priority they fill SMs the compute streams leave idle
+  const char* cp = getenv("NLPS_COMM_PRIO");
+  NLPS_CUDA(cudaStreamCreateWithPriority(&m->comm_stream, cudaStreamNonBlocking, (cp && cp[0] == 'l') ? pri_least : pri_greatest));
   NLPS_CUDA(cudaEventCreateWithFlags(&m->comm_done, cudaEventDisableTiming));
   // coalesce consecutive buckets (completion order) into exchanges of at least min_bucket_floats: NVSwitch collectives
   // are latency-, not link-bound, so small buckets ride with their neighbours

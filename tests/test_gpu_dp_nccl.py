@@ -27,7 +27,7 @@ x = rng.integers(1, 211, (8, 48)).astype(np.int32); x[3, 30:] = 0
 y = rng.integers(0, 211, (8, 48)).astype(np.int32)
 np.random.seed(11 + rank)                      # ranks start from DIFFERENT weights: broadcast must fix it
 model = Transformer(*cfg, dropout_p=0.0, precision="fp32", device=local)
-dp = DataParallel(model, min_bucket_floats=1)  # one all-reduce per bucket: exercises the bucket events
+dp = DataParallel(model, min_bucket_floats=1, backend=os.environ.get("DP_BACKEND", "native"))  # one all-reduce per bucket
 dp.broadcast_parameters(0)
 b, e = shard_rows(8, rank, world)
 from nlpscratch_b200.array import DeviceArray
@@ -48,8 +48,19 @@ if rank == 0:
     worst = max(float(np.linalg.norm(got[k].astype(np.float64) - want[k]) / max(np.linalg.norm(want[k]), 1e-30)) for k in want)
     assert worst < 1e-5, worst
     assert abs(float(losses.item()) / world - float(l)) < 1e-4, (losses.item() / world, float(l))
-    print("dp ok", worst, dp.launches)
-dist.barrier(); dist.destroy_process_group()
+    print("dp ok", worst, dp.launches, dp.backend)
+# the unfused API under data parallelism: forward / loss / backward, then the library's whole-buffer exchange
+if dp.backend == "native":
+    logits, cache = model.forward(xd)
+    l2, dl = model.calculate_loss_dlogits(logits, yd, grad_scale=1.0 / world)
+    grads = model.backward(cache, dl)
+    dp.allreduce_gradients()
+    g = model.flat("grad").get()
+    digest = hashlib.sha256(g.tobytes()).hexdigest()
+    both = [None] * world
+    dist.all_gather_object(both, digest)
+    assert len(set(both)) == 1, both
+dist.barrier(); dp.close(); dist.destroy_process_group()
 '''
 
 
@@ -64,11 +75,17 @@ def test_two_rank_nccl_step_matches_single_gpu(tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29541", script]
     shas = {}
-    for graph_dp in ("1", "0"):                # the deferred step replayed as a CUDA graph (bucket events = external
-        env["NLPS_GRAPH_DP"] = graph_dp        # event-record nodes) must equal the eager data-parallel step bit for bit
-        res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=280)
-        assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    # native: NCCL owned by libnlps_b200.so, exchange + clip + Adam inside the one (captured) step call; graph on / off.
+    # torch: the round-1 path (dist.all_reduce per bucket from Python; the deferred half-step replayed as a CUDA graph whose
+    # bucket events are external event-record nodes, or eager).  All four must give the same bits on both ranks.
+    for backend, var, flag in (("native", "NLPS_GRAPH", "1"), ("native", "NLPS_GRAPH", "0"),
+                               ("torch", "NLPS_GRAPH_DP", "1"), ("torch", "NLPS_GRAPH_DP", "0")):
+        run_env = dict(env, DP_BACKEND=backend)
+        run_env[var] = flag
+        res = subprocess.run(cmd, env=run_env, capture_output=True, text=True, timeout=280)
+        assert res.returncode == 0, (backend, var, flag, res.stdout[-3000:] + res.stderr[-3000:])
         assert "dp ok" in res.stdout
-        shas[graph_dp] = re.findall(r"params sha ([0-9a-f]{64})", res.stdout)     # the ranks' lines may interleave
-        assert len(shas[graph_dp]) == 2 and shas[graph_dp][0] == shas[graph_dp][1], shas
-    assert shas["1"] == shas["0"], shas
+        key = (backend, flag)
+        shas[key] = re.findall(r"params sha ([0-9a-f]{64})", res.stdout)     # the ranks' lines may interleave
+        assert len(shas[key]) == 2 and shas[key][0] == shas[key][1], shas
+    assert len({tuple(v) for v in shas.values()}) == 1, shas
