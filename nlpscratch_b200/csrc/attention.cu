@@ -538,6 +538,12 @@ int first_nonpad(cudaStream_t st, int B, int S, const int32_t* x, int32_t* out) 
   return 0;
 }
 
+static bool x3_attention_on() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NLPS_X3_ATTN"); v = (e && e[0] == 'f') ? 0 : 1; }
+  return v == 1;
+}
+
 int attention_forward(cudaStream_t st, int precision, int B, int S, int h, int d, const float* qkv,
                       const int32_t* x, const int32_t* fnp, float* ctx, float* lse) {
   NLPS_TRY(check_dims(B, S, h, d));
@@ -547,6 +553,8 @@ int attention_forward(cudaStream_t st, int precision, int B, int S, int h, int d
     return attention_forward_ts(st, B, S, h, d, qkv, x, fnp, ctx, lse);
   }
   if (precision == 1 && d <= 64 && d % 4 == 0) { count_kind(KIND_ATTN_MMA); return attention_forward_mma(st, B, S, h, d, qkv, x, fnp, ctx, lse); }
+  // FP32-faithful tensor-core mode: 3xTF32 split products on mma.sync (NLPS_X3_ATTN=fp32 keeps the CUDA-core kernels, A/B)
+  if (precision == 2 && d <= 64 && d % 4 == 0 && x3_attention_on()) { count_kind(KIND_ATTN_MMA); return attention_forward_mma(st, B, S, h, d, qkv, x, fnp, ctx, lse, true); }
   count_kind(KIND_ATTN_FP32);
   AttnDims p{B, S, h, d, h * d, (float)(1.0 / sqrt((double)d))};
   if (d <= 8) return fwd_launch<8>(st, p, qkv, x, fnp, ctx, lse);
@@ -580,6 +588,7 @@ delta_done:
     return attention_backward_ts(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv);
   }
   if (precision == 1 && d <= 64 && d % 4 == 0) { count_kind(KIND_ATTN_MMA); return attention_backward_mma(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv); }
+  if (precision == 2 && d <= 64 && d % 4 == 0 && x3_attention_on()) { count_kind(KIND_ATTN_MMA); return attention_backward_mma(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv, true); }
   count_kind(KIND_ATTN_FP32);
   if (d <= 8) return bwd_launch<8>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
   if (d <= 16) return bwd_launch<16>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);

@@ -40,6 +40,50 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// 3xTF32 on mma.sync (the FP32-faithful `tf32x3` mode): operands stay FP32 in shared memory / registers and every product is
+// formed as a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (small terms first; a_lo*b_lo ~ 2^-22 is dropped), hi = cvt.rna.tf32(x), lo = x - hi.
+__device__ __forceinline__ void split_tf32(uint32_t raw, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(__uint_as_float(raw));
+  lo = __float_as_uint(__uint_as_float(raw) - __uint_as_float(hi));     // exact; the tensor core truncates it to TF32
+}
+template <bool X3>
+__device__ __forceinline__ void mma_op(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (!X3) { mma_tf32(c, a, b0, b1); return; }
+  uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[i], al[i]);
+  split_tf32(b0, bh0, bl0);
+  split_tf32(b1, bh1, bl1);
+  mma_tf32(c, al, bh0, bh1);
+  mma_tf32(c, ah, bl0, bl1);
+  mma_tf32(c, ah, bh0, bh1);
+}
+// a probability / dS value on its way into an A fragment: rounded to TF32 in the fast mode, raw FP32 bits under 3xTF32
+template <bool X3>
+__device__ __forceinline__ uint32_t frag(float x) { return X3 ? __float_as_uint(x) : to_tf32(x); }
+
+// Under 3xTF32 the long accumulations (over key tiles in the forward / dQ, over query tiles in dK/dV) do not run through the
+// tensor core's accumulator -- it adds with truncation, and the bias of a chain grows with its length (S/8 steps) -- but
+// through a per-tile temporary that is added to the running sum with round-to-nearest FP32 adds.
+template <bool X3, int NT, int N>
+__device__ __forceinline__ float (&pick_acc(float (&tmp)[NT][4], float (&run)[N][4]))[N][4] {
+  if constexpr (X3) { static_assert(NT == N, "temporary must match the accumulator"); return tmp; } else return run;
+}
+template <bool X3, int N>
+__device__ __forceinline__ void tile_begin(float (&tmp)[N][4]) {
+  if constexpr (X3) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) tmp[n][0] = tmp[n][1] = tmp[n][2] = tmp[n][3] = 0.f;
+  }
+}
+template <bool X3, int N, int NT>
+__device__ __forceinline__ void tile_end_acc(float (&run)[N][4], const float (&tmp)[NT][4]) {
+  if constexpr (X3) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) { run[n][0] += tmp[n][0]; run[n][1] += tmp[n][1]; run[n][2] += tmp[n][2]; run[n][3] += tmp[n][3]; }
+  }
+}
+
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
   return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
@@ -71,8 +115,9 @@ __device__ __forceinline__ void issue_tile(uint32_t* dst, const float* __restric
     cp_async16(dst + r * LD + c, valid ? src + (int64_t)gr * row_stride + c : src, valid);
   }
 }
-template <int D>
+template <int D, bool X3>
 __device__ __forceinline__ void round_tile(uint32_t* tile, int tid) {
+  if (X3) return;                       // 3xTF32 keeps the FP32 values; mma_op splits them
   constexpr int LD = D + 4, C4 = D / 4;
   for (int idx = tid; idx < TQ * C4; idx += kThreads) {
     const int r = idx / C4, c = (idx - r * C4) * 4;
@@ -84,13 +129,13 @@ __device__ __forceinline__ void round_tile(uint32_t* tile, int tid) {
   }
 }
 // synchronous variant for the one-off operand tiles whose fragments live in registers
-template <int D>
+template <int D, bool X3>
 __device__ __forceinline__ void stage_tile(uint32_t* dst, const float* __restrict__ src, int64_t row_stride,
                                            int first_row, int S, int d, int tid) {
   issue_tile<D>(dst, src, row_stride, first_row, S, d, tid);
   cp_async_commit();
   cp_async_wait_all();
-  round_tile<D>(dst, tid);
+  round_tile<D, X3>(dst, tid);
 }
 
 // A fragments of the warp's 16 rows for all D/8 k-chunks (standard k order): rows g, g+8; cols t, t+4
@@ -109,25 +154,25 @@ __device__ __forceinline__ void load_a_frags(uint32_t (&a)[D / 8][4], const uint
 }
 
 // c[4] = A(16 x D) . rows(8j..8j+7 of tile)^T : one 16x8 score tile, B read as [n=row][k=dim]
-template <int D>
+template <int D, bool X3>
 __device__ __forceinline__ void score_tile(float (&c)[4], const uint32_t (&a)[D / 8][4], const uint32_t* tile, int j,
                                            int g, int t) {
   constexpr int LD = D + 4;
   const uint32_t* row = tile + (j * 8 + g) * LD;
   c[0] = c[1] = c[2] = c[3] = 0.f;
 #pragma unroll
-  for (int kc = 0; kc < D / 8; ++kc) mma_tf32(c, a[kc], row[kc * 8 + t], row[kc * 8 + t + 4]);
+  for (int kc = 0; kc < D / 8; ++kc) mma_op<X3>(c, a[kc], row[kc * 8 + t], row[kc * 8 + t + 4]);
 }
 
 // acc(16 x D) += P(16 x 8 cols of score tile j, given as A fragment) . tile[rows 8j+2t, 8j+2t+1][dims]
-template <int D>
+template <int D, bool X3>
 __device__ __forceinline__ void accum_tile(float (&acc)[D / 8][4], const uint32_t (&pa)[4], const uint32_t* tile, int j,
                                            int g, int t) {
   constexpr int LD = D + 4;
   const uint32_t* r0 = tile + (j * 8 + 2 * t) * LD + g;
   const uint32_t* r1 = r0 + LD;
 #pragma unroll
-  for (int n = 0; n < D / 8; ++n) mma_tf32(acc[n], pa, r0[n * 8], r1[n * 8]);
+  for (int n = 0; n < D / 8; ++n) mma_op<X3>(acc[n], pa, r0[n * 8], r1[n * 8]);
 }
 
 __device__ __forceinline__ bool visible(int q, int k, int S, bool deg, bool key_is_pad) {
@@ -135,7 +180,7 @@ __device__ __forceinline__ bool visible(int q, int k, int S, bool deg, bool key_
 }
 
 // =========================================================================================
-template <int D>
+template <int D, bool X3>
 __global__ void __launch_bounds__(kThreads) attn_fwd_mma(Dims p, const float* __restrict__ qkv,
                                                          const int32_t* __restrict__ x,
                                                          const int32_t* __restrict__ fnp, float* __restrict__ ctx,
@@ -152,7 +197,7 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma(Dims p, const float* __
   const int first_real = fnp[b];
   const bool deg_block = q0 < first_real;
 
-  stage_tile<D>(smem_u, qbase, rs, q0, p.S, p.d, tid);
+  stage_tile<D, X3>(smem_u, qbase, rs, q0, p.S, p.d, tid);
   __syncthreads();
   uint32_t qa[D / 8][4];
   load_a_frags<D>(qa, smem_u, warp, g, t);
@@ -182,8 +227,8 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma(Dims p, const float* __
     uint32_t* Vs = Ks + TILE;
     const int* kpad = kpad_all + (kb & 1) * TQ;
     cp_async_wait_all();
-    round_tile<D>(Ks, tid);
-    round_tile<D>(Vs, tid);
+    round_tile<D, X3>(Ks, tid);
+    round_tile<D, X3>(Vs, tid);
     __syncthreads();
     if (kb + 1 < n_kv) issue(kb + 1);
 
@@ -191,7 +236,7 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma(Dims p, const float* __
     float mx0 = kNegBig, mx1 = kNegBig;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      score_tile<D>(s[j], qa, Ks, j, g, t);
+      score_tile<D, X3>(s[j], qa, Ks, j, g, t);
       const int c0 = k0 + j * 8 + 2 * t;
       const bool pd0 = kpad[j * 8 + 2 * t], pd1 = kpad[j * 8 + 2 * t + 1];
       const bool v00 = visible(row0, c0, p.S, deg0, pd0), v01 = visible(row0, c0 + 1, p.S, deg0, pd1);
@@ -211,6 +256,8 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma(Dims p, const float* __
     float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
     for (int n = 0; n < D / 8; ++n) { o[n][0] *= al0; o[n][1] *= al0; o[n][2] *= al1; o[n][3] *= al1; }
+    float ot[X3 ? D / 8 : 1][4];
+    tile_begin<X3>(ot);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       // masked entries hold the sentinel: exp underflows to exactly 0 unless the whole row is still
@@ -221,9 +268,10 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma(Dims p, const float* __
       const float p11 = s[j][3] > kNegBig ? expf(s[j][3] - mn1) : 0.f;
       rs0 += p00 + p01;
       rs1 += p10 + p11;
-      const uint32_t pa[4] = {to_tf32(p00), to_tf32(p10), to_tf32(p01), to_tf32(p11)};
-      accum_tile<D>(o, pa, Vs, j, g, t);
+      const uint32_t pa[4] = {frag<X3>(p00), frag<X3>(p10), frag<X3>(p01), frag<X3>(p11)};
+      accum_tile<D, X3>(pick_acc<X3>(ot, o), pa, Vs, j, g, t);
     }
+    tile_end_acc<X3>(o, ot);
     l0 = l0 * al0 + quad_sum(rs0);
     l1 = l1 * al1 + quad_sum(rs1);
   }
@@ -250,7 +298,7 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_mma(Dims p, const float* __
 
 // =========================================================================================
 // dK/dV: CTA owns 64 keys; warp owns 16 of them as MMA rows; loops over query tiles.
-template <int D>
+template <int D, bool X3>
 __global__ void __launch_bounds__(kThreads) attn_bwd_dkdv_mma(Dims p, const float* __restrict__ qkv,
                                                               const int32_t* __restrict__ x,
                                                               const int32_t* __restrict__ fnp,
@@ -276,8 +324,8 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkdv_mma(Dims p, const floa
   issue_tile<D>(smem_u + TILE, qbase + 2 * p.E, rs, k0, p.S, p.d, tid);
   cp_async_commit();
   cp_async_wait_all();
-  round_tile<D>(smem_u, tid);
-  round_tile<D>(smem_u + TILE, tid);
+  round_tile<D, X3>(smem_u, tid);
+  round_tile<D, X3>(smem_u + TILE, tid);
   __syncthreads();
   load_a_frags<D>(ka, smem_u, warp, g, t);
   load_a_frags<D>(va, smem_u + TILE, warp, g, t);
@@ -319,16 +367,19 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkdv_mma(Dims p, const floa
     const float* lse_s = stat + (it & 1) * 2 * TQ;
     const float* delta_s = lse_s + TQ;
     cp_async_wait_all();
-    round_tile<D>(Qs, tid);
-    round_tile<D>(dOs, tid);
+    round_tile<D, X3>(Qs, tid);
+    round_tile<D, X3>(dOs, tid);
     __syncthreads();
     if (it + 1 < n_it) issue(it + 1);
+    float dvt[X3 ? D / 8 : 1][4], dkt[X3 ? D / 8 : 1][4];
+    tile_begin<X3>(dvt);
+    tile_begin<X3>(dkt);
 #pragma unroll 4
     for (int j = 0; j < 8; ++j) {
       // transposed tiles: rows = this warp's keys, cols = queries q0+8j+2t, +1
       float st[4], dpt[4];
-      score_tile<D>(st, ka, Qs, j, g, t);           // S^T  = K Q^T
-      score_tile<D>(dpt, va, dOs, j, g, t);         // dP^T = V dO^T
+      score_tile<D, X3>(st, ka, Qs, j, g, t);           // S^T  = K Q^T
+      score_tile<D, X3>(dpt, va, dOs, j, g, t);         // dP^T = V dO^T
       const int qc = q0 + j * 8 + 2 * t;
       const float ls0 = lse_s[j * 8 + 2 * t], ls1 = lse_s[j * 8 + 2 * t + 1];
       const float dl0 = delta_s[j * 8 + 2 * t], dl1 = delta_s[j * 8 + 2 * t + 1];
@@ -337,12 +388,14 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkdv_mma(Dims p, const floa
       const float p01 = visible(qc + 1, key0, p.S, dg1, pad0) ? expf(st[1] * p.scale - ls1) : 0.f;
       const float p10 = visible(qc, key1, p.S, dg0, pad1) ? expf(st[2] * p.scale - ls0) : 0.f;
       const float p11 = visible(qc + 1, key1, p.S, dg1, pad1) ? expf(st[3] * p.scale - ls1) : 0.f;
-      const uint32_t pa[4] = {to_tf32(p00), to_tf32(p10), to_tf32(p01), to_tf32(p11)};
-      const uint32_t da[4] = {to_tf32(p00 * (dpt[0] - dl0)), to_tf32(p10 * (dpt[2] - dl0)),
-                              to_tf32(p01 * (dpt[1] - dl1)), to_tf32(p11 * (dpt[3] - dl1))};
-      accum_tile<D>(dv, pa, dOs, j, g, t);          // dV += P^T  dO
-      accum_tile<D>(dk, da, Qs, j, g, t);           // dK += dS^T Q
+      const uint32_t pa[4] = {frag<X3>(p00), frag<X3>(p10), frag<X3>(p01), frag<X3>(p11)};
+      const uint32_t da[4] = {frag<X3>(p00 * (dpt[0] - dl0)), frag<X3>(p10 * (dpt[2] - dl0)),
+                              frag<X3>(p01 * (dpt[1] - dl1)), frag<X3>(p11 * (dpt[3] - dl1))};
+      accum_tile<D, X3>(pick_acc<X3>(dvt, dv), pa, dOs, j, g, t);          // dV += P^T  dO
+      accum_tile<D, X3>(pick_acc<X3>(dkt, dk), da, Qs, j, g, t);           // dK += dS^T Q
     }
+    tile_end_acc<X3>(dv, dvt);
+    tile_end_acc<X3>(dk, dkt);
   }
 #pragma unroll
   for (int n = 0; n < D / 8; ++n) {
@@ -362,7 +415,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkdv_mma(Dims p, const floa
 
 // =========================================================================================
 // dQ: CTA owns 64 queries; loops over key tiles (same range as the forward).
-template <int D>
+template <int D, bool X3>
 __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma(Dims p, const float* __restrict__ qkv,
                                                             const int32_t* __restrict__ x,
                                                             const int32_t* __restrict__ fnp,
@@ -387,8 +440,8 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma(Dims p, const float*
   issue_tile<D>(smem_u + TILE, dobase, p.E, q0, p.S, p.d, tid);
   cp_async_commit();
   cp_async_wait_all();
-  round_tile<D>(smem_u, tid);
-  round_tile<D>(smem_u + TILE, tid);
+  round_tile<D, X3>(smem_u, tid);
+  round_tile<D, X3>(smem_u + TILE, tid);
   __syncthreads();
   load_a_frags<D>(qa, smem_u, warp, g, t);
   load_a_frags<D>(doa, smem_u + TILE, warp, g, t);
@@ -421,25 +474,28 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma(Dims p, const float*
     uint32_t* Vs = Ks + TILE;
     const int* kpad = kpad_all + (kb & 1) * TQ;
     cp_async_wait_all();
-    round_tile<D>(Ks, tid);
-    round_tile<D>(Vs, tid);
+    round_tile<D, X3>(Ks, tid);
+    round_tile<D, X3>(Vs, tid);
     __syncthreads();
     if (kb + 1 < n_kv) issue(kb + 1);
+    float dqt[X3 ? D / 8 : 1][4];
+    tile_begin<X3>(dqt);
 #pragma unroll 4
     for (int j = 0; j < 8; ++j) {
       float s[4], dp[4];
-      score_tile<D>(s, qa, Ks, j, g, t);            // S  = Q K^T
-      score_tile<D>(dp, doa, Vs, j, g, t);          // dP = dO V^T
+      score_tile<D, X3>(s, qa, Ks, j, g, t);            // S  = Q K^T
+      score_tile<D, X3>(dp, doa, Vs, j, g, t);          // dP = dO V^T
       const int c0 = k0 + j * 8 + 2 * t;
       const bool pd0 = kpad[j * 8 + 2 * t], pd1 = kpad[j * 8 + 2 * t + 1];
       const float p00 = visible(row0, c0, p.S, deg0, pd0) ? expf(s[0] * p.scale - ls0) : 0.f;
       const float p01 = visible(row0, c0 + 1, p.S, deg0, pd1) ? expf(s[1] * p.scale - ls0) : 0.f;
       const float p10 = visible(row1, c0, p.S, deg1, pd0) ? expf(s[2] * p.scale - ls1) : 0.f;
       const float p11 = visible(row1, c0 + 1, p.S, deg1, pd1) ? expf(s[3] * p.scale - ls1) : 0.f;
-      const uint32_t da[4] = {to_tf32(p00 * (dp[0] - dl0)), to_tf32(p10 * (dp[2] - dl1)),
-                              to_tf32(p01 * (dp[1] - dl0)), to_tf32(p11 * (dp[3] - dl1))};
-      accum_tile<D>(dq, da, Ks, j, g, t);           // dQ += dS K
+      const uint32_t da[4] = {frag<X3>(p00 * (dp[0] - dl0)), frag<X3>(p10 * (dp[2] - dl1)),
+                              frag<X3>(p01 * (dp[1] - dl0)), frag<X3>(p11 * (dp[3] - dl1))};
+      accum_tile<D, X3>(pick_acc<X3>(dqt, dq), da, Ks, j, g, t);           // dQ += dS K
     }
+    tile_end_acc<X3>(dq, dqt);
   }
 #pragma unroll
   for (int n = 0; n < D / 8; ++n) {
@@ -459,33 +515,33 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_mma(Dims p, const float*
 
 template <int D> constexpr size_t smem_bytes() { return (size_t)(4 * TQ * (D + 4)) * 4 + 4 * TQ * 4; }
 
-template <int D>
+template <int D, bool X3>
 int launch_fwd(cudaStream_t st, const Dims& p, const float* qkv, const int32_t* x, const int32_t* fnp, float* ctx,
                float* lse) {
   static bool once = false;
   if (!once) {
-    NLPS_CUDA(cudaFuncSetAttribute(attn_fwd_mma<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<D>()));
+    NLPS_CUDA(cudaFuncSetAttribute(attn_fwd_mma<D, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<D>()));
     once = true;
   }
   dim3 grid((unsigned)ceil_div(p.S, TQ), (unsigned)p.h, (unsigned)p.B);
-  attn_fwd_mma<D><<<grid, kThreads, smem_bytes<D>(), st>>>(p, qkv, x, fnp, ctx, lse);
+  attn_fwd_mma<D, X3><<<grid, kThreads, smem_bytes<D>(), st>>>(p, qkv, x, fnp, ctx, lse);
   NLPS_LAUNCH_CHECK();
   return 0;
 }
 
-template <int D>
+template <int D, bool X3>
 int launch_bwd(cudaStream_t st, const Dims& p, const float* qkv, const int32_t* x, const int32_t* fnp,
                const float* dctx, const float* lse, const float* delta, float* dqkv) {
   static bool once = false;
   if (!once) {
-    NLPS_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_mma<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<D>()));
-    NLPS_CUDA(cudaFuncSetAttribute(attn_bwd_dq_mma<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<D>()));
+    NLPS_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_mma<D, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<D>()));
+    NLPS_CUDA(cudaFuncSetAttribute(attn_bwd_dq_mma<D, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<D>()));
     once = true;
   }
   dim3 grid((unsigned)ceil_div(p.S, TQ), (unsigned)p.h, (unsigned)p.B);
-  attn_bwd_dkdv_mma<D><<<grid, kThreads, smem_bytes<D>(), st>>>(p, qkv, x, fnp, dctx, lse, delta, dqkv);
+  attn_bwd_dkdv_mma<D, X3><<<grid, kThreads, smem_bytes<D>(), st>>>(p, qkv, x, fnp, dctx, lse, delta, dqkv);
   NLPS_LAUNCH_CHECK();
-  attn_bwd_dq_mma<D><<<grid, kThreads, smem_bytes<D>(), st>>>(p, qkv, x, fnp, dctx, lse, delta, dqkv);
+  attn_bwd_dq_mma<D, X3><<<grid, kThreads, smem_bytes<D>(), st>>>(p, qkv, x, fnp, dctx, lse, delta, dqkv);
   NLPS_LAUNCH_CHECK();
   return 0;
 }
@@ -493,22 +549,32 @@ int launch_bwd(cudaStream_t st, const Dims& p, const float* qkv, const int32_t* 
 }  // namespace
 
 int attention_forward_mma(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
-                          const int32_t* fnp, float* ctx, float* lse) {
+                          const int32_t* fnp, float* ctx, float* lse, bool x3) {
   Dims p{B, S, h, d, h * d, (float)(1.0 / std::sqrt((double)d))};
-  if (d <= 16) return launch_fwd<16>(st, p, qkv, x, fnp, ctx, lse);
-  if (d <= 32) return launch_fwd<32>(st, p, qkv, x, fnp, ctx, lse);
   NLPS_REQUIRE(d <= 64 && d % 4 == 0, "attention_forward_mma: head_dim %d is served by the CUDA-core kernels", d);
-  return launch_fwd<64>(st, p, qkv, x, fnp, ctx, lse);
+  if (x3) {
+    if (d <= 16) return launch_fwd<16, true>(st, p, qkv, x, fnp, ctx, lse);
+    if (d <= 32) return launch_fwd<32, true>(st, p, qkv, x, fnp, ctx, lse);
+    return launch_fwd<64, true>(st, p, qkv, x, fnp, ctx, lse);
+  }
+  if (d <= 16) return launch_fwd<16, false>(st, p, qkv, x, fnp, ctx, lse);
+  if (d <= 32) return launch_fwd<32, false>(st, p, qkv, x, fnp, ctx, lse);
+  return launch_fwd<64, false>(st, p, qkv, x, fnp, ctx, lse);
 }
 
 int attention_backward_mma(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
                            const int32_t* fnp, const float* dctx, const float* lse, const float* delta,
-                           float* dqkv) {
+                           float* dqkv, bool x3) {
   Dims p{B, S, h, d, h * d, (float)(1.0 / std::sqrt((double)d))};
-  if (d <= 16) return launch_bwd<16>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
-  if (d <= 32) return launch_bwd<32>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
   NLPS_REQUIRE(d <= 64 && d % 4 == 0, "attention_backward_mma: head_dim %d is served by the CUDA-core kernels", d);
-  return launch_bwd<64>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
+  if (x3) {
+    if (d <= 16) return launch_bwd<16, true>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
+    if (d <= 32) return launch_bwd<32, true>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
+    return launch_bwd<64, true>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
+  }
+  if (d <= 16) return launch_bwd<16, false>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
+  if (d <= 32) return launch_bwd<32, false>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
+  return launch_bwd<64, false>(st, p, qkv, x, fnp, dctx, lse, delta, dqkv);
 }
 
 }  // namespace nlps

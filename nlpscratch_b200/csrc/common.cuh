@@ -233,10 +233,10 @@ int attention_backward_ts(cudaStream_t st, int B, int S, int h, int d, const flo
 
 // attention_mma.cu (TF32 tensor-core versions, head_dim <= 64)
 int attention_forward_mma(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
-                          const int32_t* first_nonpad, float* ctx, float* lse);
+                          const int32_t* first_nonpad, float* ctx, float* lse, bool x3 = false);
 int attention_backward_mma(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
                            const int32_t* first_nonpad, const float* dctx, const float* lse, const float* delta,
-                           float* dqkv);
+                           float* dqkv, bool x3 = false);   // x3: 3xTF32 split products (FP32-level accuracy)
 
 // rowwise.cu
 int layernorm_forward(cudaStream_t st, int64_t rows, int E, const float* x, const float* gamma,
