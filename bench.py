@@ -451,8 +451,8 @@ def measure_others(args, torch, dist, rank, world, local, steps=5, warmup=2):
     in the warm-up: eager, capture, replay).  Under torchrun every rank runs them (data parallel); loss read once."""
     from nlpscratch_b200 import Transformer
     from nlpscratch_b200.array import DeviceArray
-    plan = [("c4/tf32x3", "c4", "tf32x3"), ("c4/fp32", "c4", "fp32"), ("c3/tf32", "c3", "tf32"), ("c5/tf32", "c5", "tf32"),
-            ("c4-32k/tf32", "c4-32k", "tf32")]
+    plan = [("c4/tf32x3", "c4", "tf32x3"), ("c4/fp32", "c4", "fp32"), ("c2/fp32", "c2", "fp32"), ("c2/tf32", "c2", "tf32"),
+            ("c3/tf32", "c3", "tf32"), ("c5/tf32", "c5", "tf32"), ("c4-32k/tf32", "c4-32k", "tf32")]
     if world > 1:
         plan = [("c5/tf32", "c5", "tf32")]            # BASELINE.json configs[4]: the long-context model, data parallel
     out = {}
@@ -493,7 +493,30 @@ def measure_others(args, torch, dist, rank, world, local, steps=5, warmup=2):
                      "config": "%dL d%d h%d ff%d seq%d vocab%d batch%d/GPU dropout %.2f" % (L, E, h, F, S, V, B, args.dropout)}
         m.close()
         del m, dp, xd, yd
+    if world == 1:
+        out["c1/tf32"] = driver_epoch(args, torch)
     return out
+
+
+def driver_epoch(args, torch):
+    """BASELINE.json configs[0] on the device: one epoch of the driver loop (nlpscratch_b200.train.train_transformer: fused
+    last-token steps, device-side evaluation) over the reference's mini dataset, after one warm-up epoch."""
+    from nlpscratch_b200 import Transformer
+    from nlpscratch_b200.train import train_transformer
+    L, E, h, F, S, B, V = WORKLOADS["c1"]
+    X, Y, data_name = mini_dataset(V, S)
+    np.random.seed(0)
+    m = Transformer(V, E, h, F, L, S, dropout_p=args.dropout, precision="tf32")
+    quiet = lambda *_a, **_k: None
+    train_transformer(m, X, Y, learning_rate=1e-4, nepoch=1, evaluation_loss_after=1, batch_size=B, print_every=0,
+                      clip_grad_norm=1.0, log=quiet)
+    torch.cuda.synchronize()
+    stats = train_transformer(m, X, Y, learning_rate=1e-4, nepoch=1, evaluation_loss_after=1, batch_size=B, print_every=0,
+                              clip_grad_norm=1.0, log=quiet)
+    m.close()
+    return {"value": stats["tokens"] / stats["train_seconds"], "unit": "non-pad tokens/s", "ms_per_step": 1e3 * stats["train_seconds"] / stats["steps"],
+            "steps": stats["steps"], "precision": "tf32", "eval_loss_before_epoch": stats["losses"][-1][1],
+            "config": "driver loop, last-token loss, %s, %d prefixes x max_len %d, B%d, 3L d256 h8 ff1024 V%d" % (data_name, len(Y), S, B, V)}
 
 
 def gemm_roofline(torch, _lib, N, E, F, precision, peak_info):
@@ -555,14 +578,27 @@ def synthetic_prefix_dataset(V, max_len, n_sent=69, seed=0):
     return np.array(X, dtype=np.int32), np.array(Y, dtype=np.int32)
 
 
+def mini_dataset(V, S):
+    """The reference's own dataset for BASELINE.json configs[0]: the word-level prefix dataset of
+    dataset/tagged_train_mini.txt (1434 prefixes x max_len 320, V 574; integer arrays committed as
+    tests/golden/dataset_mini.npz); synthetic sentences of the same statistics only if that file is missing."""
+    path = os.path.join(ROOT, "tests", "golden", "dataset_mini.npz")
+    if os.path.exists(path):
+        with np.load(path) as z:
+            if int(z["vocab"]) == V and z["X"].shape[1] == S:
+                return z["X"], z["Y"], "dataset/tagged_train_mini.txt (word level)"
+    X, Y = synthetic_prefix_dataset(V, S)
+    return X, Y, "synthetic sentences with the mini corpus' statistics"
+
+
 def run_driver(args, wl):
-    """Workload c1: one epoch of the reference driver loop (last-token loss, B16, clip 1.0, Adam 1e-4)."""
+    """Workload c1: the reference driver loop (last-token loss, B16, clip 1.0, Adam 1e-4) on its own dataset."""
     import torch
     from nlpscratch_b200 import Transformer
     from nlpscratch_b200.train import train_transformer
     from oracle.transformer_oracle import OracleTransformer, last_token_step
     L, E, h, F, S, B, V = wl
-    X, Y = synthetic_prefix_dataset(V, S)
+    X, Y, data_name = mini_dataset(V, S)
     nonpad = int((X != 0).sum())
     if args.impl == "reference":
         np.random.seed(0)
@@ -595,7 +631,7 @@ def run_driver(args, wl):
     tok_s = stats["tokens"] / stats["train_seconds"]
     line = {"metric": METRIC, "value": tok_s, "unit": "non-pad tokens/s", "n_gpus": 1, "steps": stats["steps"], "warmup": 90,
             "ms_per_step": 1e3 * stats["train_seconds"] / stats["steps"], "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "vs_baseline": None, "dtype": args.precision, "data": data_name,
             "config": {"workload": "c1: reference driver loop (nlpscratch_b200.train.train_transformer), last-token loss, "
                                    "%d prefixes x max_len %d (%d non-PAD tokens/epoch), B%d, host->device copy of the dataset "
                                    "and shuffles inside the timed region" % (len(Y), S, nonpad, B)},

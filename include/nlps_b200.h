@@ -160,6 +160,18 @@ int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t x_
 int nlps_train_step_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t x_row_stride,
                                const int32_t* d_t, const int32_t* d_y, float lr, float max_norm,
                                float grad_scale, int defer_update, float* d_loss);
+/* The evaluation pass, the learning-rate schedule and the sampling block of the driver loop without per-batch host
+ * synchronisation.  nlps_eval_last_token = one batch of compute_eval_loss (utils/train.py:51-75): eval-mode
+ * hidden-only forward, last-real-token vocab head, per-row losses; adds their sum to d_accum[0] and the row count to
+ * d_accum[1].  nlps_eval_finish closes a pass: d_sched = {previous eval loss, passes so far, learning rate, halved flag,
+ * this eval loss}; eval = accum[0]/accum[1]; "if the loss went up, halve the learning rate" (utils/train.py:86-88) is taken
+ * on the device; the accumulator is cleared.  The host reads d_sched once per pass (it prints the loss, like the reference).
+ * nlps_topk_softmax = `probs = exp(l - max); probs /= sum; argsort()[-k:][::-1]` (utils/train.py:149-159) for one logits row:
+ * the k most probable ids, most probable first, and their probabilities; d_work: V floats of scratch. */
+int nlps_eval_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t x_row_stride, const int32_t* d_t,
+                         const int32_t* d_y, float* d_accum);
+int nlps_eval_finish(nlps_model* m, float* d_accum, float* d_sched);
+int nlps_topk_softmax(void* stream, const float* d_logits, int V, int k, float* d_work, int32_t* d_idx, float* d_prob);
 int nlps_launch_count(nlps_model* m, int64_t* launches, int reset);  /* kernels launched so far (process-wide counter) */
 
 /* ---- data-parallel exchange (the reference has no distributed code) -------------------------------------

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libnlps_b200.so")
-SOURCES = ["util.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "attention.cu", "attention_mma.cu", "attention_tc.cu", "attention_ts.cu", "rowwise.cu", "embed.cu", "dataset.cu",
+SOURCES = ["util.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "attention.cu", "attention_mma.cu", "attention_ts.cu", "rowwise.cu", "embed.cu", "dataset.cu",
            "optimizer.cu", "array_ops.cu", "tf32_peak.cu", "comm_nccl.cu", "model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

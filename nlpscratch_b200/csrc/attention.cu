@@ -524,11 +524,10 @@ int check_dims(int B, int S, int h, int d) {
 
 }  // namespace
 
-// NLPS_ATTN=mma forces the mma.sync kernels where the tcgen05 ones would run, NLPS_ATTN=ss the first-generation
-// tcgen05 kernels (operands in shared memory) where the TMEM-operand ones would run (A/B measurements)
+// NLPS_ATTN=mma forces the mma.sync kernels where the tcgen05 ones would run (A/B measurements)
 static int attn_impl() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("NLPS_ATTN"); v = (e && e[0] == 'm') ? 1 : ((e && e[0] == 's') ? 2 : 0); }
+  if (v < 0) { const char* e = getenv("NLPS_ATTN"); v = (e && e[0] == 'm') ? 1 : 0; }
   return v;
 }
 
@@ -536,6 +535,11 @@ int first_nonpad(cudaStream_t st, int B, int S, const int32_t* x, int32_t* out) 
   first_nonpad_kernel<<<B, 128, 0, st>>>(B, S, x, out);
   NLPS_LAUNCH_CHECK();
   return 0;
+}
+
+// the tcgen05 kernels serve head_dim 32 / 64 on TMA-addressable packed rows
+bool attention_tc_supported(int d, int E, const float* qkv) {
+  return (d == 32 || d == 64) && (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(qkv) & 15u) == 0);
 }
 
 static bool x3_attention_on() {
@@ -548,7 +552,6 @@ int attention_forward(cudaStream_t st, int precision, int B, int S, int h, int d
                       const int32_t* x, const int32_t* fnp, float* ctx, float* lse) {
   NLPS_TRY(check_dims(B, S, h, d));
   if (precision == 1 && attention_tc_supported(d, h * d, qkv) && attn_impl() != 1) {
-    if (attn_impl() == 2) { count_kind(KIND_ATTN_SS); return attention_forward_tc(st, B, S, h, d, qkv, x, fnp, ctx, lse); }
     count_kind(KIND_ATTN_TS_FWD);
     return attention_forward_ts(st, B, S, h, d, qkv, x, fnp, ctx, lse);
   }
@@ -583,7 +586,6 @@ int attention_backward(cudaStream_t st, int precision, int B, int S, int h, int 
 delta_done:
   if (precision == 1 && attention_tc_supported(d, h * d, qkv) && attn_impl() != 1 &&
       (reinterpret_cast<uintptr_t>(dctx) & 15u) == 0) {
-    if (attn_impl() == 2) { count_kind(KIND_ATTN_SS); return attention_backward_tc(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv); }
     count_kind(KIND_ATTN_TS_BWD);
     return attention_backward_ts(st, B, S, h, d, qkv, x, fnp, dctx, lse, delta, dqkv);
   }

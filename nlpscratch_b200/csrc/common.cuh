@@ -218,13 +218,8 @@ int attention_backward(cudaStream_t st, int precision, int B, int S, int h, int 
                        const float* dctx, float* delta_scratch, float* dqkv, bool delta_ready = false);
 // delta_ready: delta_scratch already holds sum(dO*O) per (b,h,i) (by-product of the Wo dgrad GEMM, GemmArgs::rowdot_out)
 int first_nonpad(cudaStream_t st, int B, int S, const int32_t* x, int32_t* out);
-// attention_tc.cu (tcgen05 / TMEM versions, head_dim 32 or 64)
+// which shapes the tcgen05 attention serves (head_dim 32 or 64, TMA-addressable rows); attention.cu
 bool attention_tc_supported(int d, int E, const float* qkv);
-int attention_forward_tc(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
-                         const int32_t* first_nonpad, float* ctx, float* lse);
-int attention_backward_tc(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
-                          const int32_t* first_nonpad, const float* dctx, const float* lse, const float* delta,
-                          float* dqkv);
 // attention_ts.cu (tcgen05 with the A operands in TMEM, head_dim 32 or 64)
 int attention_forward_ts(cudaStream_t st, int B, int S, int h, int d, const float* qkv, const int32_t* x,
                          const int32_t* fnp, float* ctx, float* lse);
@@ -251,6 +246,10 @@ size_t layernorm_backward_scratch_floats(int E);
 int softmax_xent_rows(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V, float inv,
                       float* dlogits, int64_t ldd, float* row_loss, int32_t* err = nullptr);
 int row_loss_mean(cudaStream_t st, const float* row_loss, int64_t rows, float* loss);
+// device-side evaluation bookkeeping of the driver loop (utils/train.py:51-75, 86-88, 143-163)
+int eval_accumulate(cudaStream_t st, const float* row_loss, int64_t rows, float* accum);
+int eval_finish(cudaStream_t st, float* accum, float* sched);
+int topk_softmax(cudaStream_t st, const float* logits, int V, int k, float* work, int32_t* out_idx, float* out_prob);
 int softmax_xent_stats(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
                        float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss, const float2* rowstat,
                        int32_t* err = nullptr);

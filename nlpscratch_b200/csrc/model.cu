@@ -1331,6 +1331,40 @@ int nlps_dropout_mask(nlps_model* m, int layer, int which, int64_t step, int64_t
   return dropout_mask(m->stream, d, n, d_out);
 }
 
+// ---- evaluation pass of the driver loop without host synchronisation (utils/train.py:51-75) ------------------------
+int nlps_eval_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_t,
+                         const int32_t* d_y, float* d_accum) {
+  NLPS_REQUIRE(m && c && d_x && d_t && d_y && d_accum, "nlps_eval_last_token: null argument");
+  const bool was_training = m->training;
+  m->training = false;                                    // model.eval(): dropout off (utils/train.py:54)
+  const int rc = nlps_forward(m, c, d_x, xs, 1, nullptr, 0);
+  m->training = was_training;
+  if (rc != 0) return rc;
+  const int B = c->B, E = m->E;
+  const float* h_final = m->L > 0 ? c->layers.back().y2 : c->h0;
+  const int64_t off_h = round_up((int64_t)B, kAlign);
+  const int64_t off_l = off_h + round_up((int64_t)B * E, kAlign);
+  NLPS_TRY(ensure_rows_tmp(m, off_l + (int64_t)B * m->ldV));
+  float* h_last = m->rows_tmp + off_h;
+  float* logits = m->rows_tmp + off_l;
+  NLPS_TRY(gather_last(m->stream, B, c->S, E, h_final, d_t, h_last));
+  GemmArgs g = gemm_nn(B, m->V, E, h_last, E, m->P + m->off_Wvocab, m->ldV, logits, m->ldV);
+  g.bias = m->P + m->off_bvocab;
+  NLPS_TRY(gemm_dispatch(m->stream, m->precision, g));
+  NLPS_TRY(softmax_xent_rows(m->stream, logits, m->ldV, d_y, B, m->V, 1.f, logits, m->ldV, m->rows_tmp, m->err_flag));
+  return eval_accumulate(m->stream, m->rows_tmp, B, d_accum);
+}
+
+int nlps_eval_finish(nlps_model* m, float* d_accum, float* d_sched) {
+  NLPS_REQUIRE(m && d_accum && d_sched, "nlps_eval_finish: null argument");
+  return eval_finish(m->stream, d_accum, d_sched);
+}
+
+int nlps_topk_softmax(void* stream, const float* d_logits, int V, int k, float* d_work, int32_t* d_idx, float* d_prob) {
+  NLPS_REQUIRE(d_logits && d_work && d_idx && d_prob, "nlps_topk_softmax: null argument");
+  return topk_softmax((cudaStream_t)stream, d_logits, V, k, d_work, d_idx, d_prob);
+}
+
 int nlps_launch_count(nlps_model*, int64_t* launches, int reset) {
   const long long n = launch_count(reset != 0);
   if (launches) *launches = n;

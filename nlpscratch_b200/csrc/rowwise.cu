@@ -608,11 +608,98 @@ int softmax_xent_stats(cudaStream_t st, const float* logits, int64_t ld, const i
 }
 
 namespace {
+// ---- device-side evaluation bookkeeping of the driver loop (utils/train.py:51-75, 86-88, 143-163) ----
+// accum[0] += sum of the batch's per-row losses, accum[1] += rows: one CTA, fixed tree => deterministic
+__global__ void __launch_bounds__(1024) eval_accumulate_kernel(const float* __restrict__ row_loss, int64_t rows,
+                                                               float* __restrict__ accum) {
+  __shared__ float sm[32];
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < rows; i += 1024) acc += row_loss[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = warp_sum(sm[threadIdx.x]);
+    if (threadIdx.x == 0) { accum[0] += v; accum[1] += (float)rows; }
+  }
+}
+// sched = {previous eval loss, evaluations so far, learning rate, halved-this-time flag, this eval loss}: the mean loss of
+// the pass, and the reference's schedule "halve the learning rate when the loss went up" (utils/train.py:86-88)
+__global__ void eval_finish_kernel(float* __restrict__ accum, float* __restrict__ sched) {
+  const float eval = accum[0] / fmaxf(accum[1], 1.f);
+  const bool worse = sched[1] > 0.f && eval > sched[0];
+  if (worse) sched[2] *= 0.5f;
+  sched[0] = eval; sched[1] += 1.f; sched[3] = worse ? 1.f : 0.f; sched[4] = eval;
+  accum[0] = 0.f; accum[1] = 0.f;
+}
+// softmax probabilities of one logits row and its k most probable ids (descending; ties: the higher id first, like
+// argsort()[-k:][::-1]).  One CTA; `work` is a V-float scratch that ends up holding the probabilities with the winners removed.
+__global__ void __launch_bounds__(256) topk_softmax_kernel(const float* __restrict__ logits, int V, int k, float* __restrict__ work,
+                                                           int32_t* __restrict__ out_idx, float* __restrict__ out_prob) {
+  __shared__ float red[8];
+  __shared__ int redi[8];
+  __shared__ float bc[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float m = -INFINITY;
+  for (int c = tid; c < V; c += 256) m = fmaxf(m, logits[c]);
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (tid == 0) { float t = red[0]; for (int w = 1; w < 8; ++w) t = fmaxf(t, red[w]); bc[0] = t; }
+  __syncthreads();
+  m = bc[0];
+  float s = 0.f;
+  for (int c = tid; c < V; c += 256) { const float e = expf(logits[c] - m); work[c] = e; s += e; }
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += red[w]; bc[1] = t; }
+  __syncthreads();
+  const float inv = 1.f / bc[1];
+  for (int j = 0; j < k; ++j) {
+    float best = -1.f; int bi = -1;
+    for (int c = tid; c < V; c += 256) { const float v = work[c]; if (v > best || (v == best && c > bi)) { best = v; bi = c; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi > bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { red[warp] = best; redi[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      float b = red[0]; int i = redi[0];
+      for (int w = 1; w < 8; ++w) if (red[w] > b || (red[w] == b && redi[w] > i)) { b = red[w]; i = redi[w]; }
+      out_idx[j] = i; out_prob[j] = b * inv;
+      if (i >= 0) work[i] = -1.f;
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void dropout_mask_kernel(DropoutParams d, int64_t n, float* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = dropout_one(d, (uint64_t)i, 1.f) != 0.f ? 1.f : 0.f;
 }
 }  // namespace
+
+int eval_accumulate(cudaStream_t st, const float* row_loss, int64_t rows, float* accum) {
+  if (rows <= 0) return 0;
+  eval_accumulate_kernel<<<1, 1024, 0, st>>>(row_loss, rows, accum);
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+int eval_finish(cudaStream_t st, float* accum, float* sched) {
+  eval_finish_kernel<<<1, 1, 0, st>>>(accum, sched);
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+int topk_softmax(cudaStream_t st, const float* logits, int V, int k, float* work, int32_t* out_idx, float* out_prob) {
+  NLPS_REQUIRE(V > 0 && k > 0 && k <= V, "topk_softmax: need 0 < k <= V (k=%d, V=%d)", k, V);
+  topk_softmax_kernel<<<1, 256, 0, st>>>(logits, V, k, work, out_idx, out_prob);
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
 
 int dropout_mask(cudaStream_t st, const DropoutParams& d, int64_t n, float* out) {
   if (n <= 0) return 0;

@@ -1,5 +1,5 @@
 // tcgen05 / TMEM / TMA / mbarrier PTX wrappers and the host-side tensor-map encoder shared by the
-// tensor-core kernels (gemm_tcgen05.cu, attention_tc.cu).  sm_100a only.
+// tensor-core kernels (gemm_tcgen05.cu, attention_ts.cu, tf32_peak.cu).  sm_100a only.
 #pragma once
 #include "common.cuh"
 #include <cuda.h>

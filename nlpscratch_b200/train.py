@@ -3,7 +3,10 @@
 clip / evaluation-and-LR-halving schedule / progress prints, but each training iteration is ONE fused
 library call (``Transformer.train_step_last_token``) and the loop performs no device synchronisation
 per step: sequence lengths are computed once on the host, the shuffle is a device gather, and the
-running loss is read back only when it is printed.
+running loss is read back only when it is printed.  The evaluation pass accumulates its loss on the
+device (``eval_batch_last_token``) and is read back ONCE per pass together with the learning rate the
+device-side schedule decided (``eval_finish``: halve when the loss went up); the top-k sampling block
+runs its softmax and selection on the device (``topk_next``).
 
 The unmodified reference loop also runs against ``nlpscratch_b200.Transformer`` (that is the drop-in
 contract); this module is the fast path for the same job.
@@ -31,32 +34,25 @@ def train_transformer(model, x_train, y_train, learning_rate=0.01, nepoch=100, e
     N = len(y_host)
     stats = {"steps": 0, "tokens": 0, "train_seconds": 0.0}
 
-    def compute_eval_loss():                                      # utils/train.py:51-75
-        total_loss, total_count = 0.0, 0
-        model.eval()
+    accum = DeviceArray.from_host(np.zeros(2, np.float32))
+    sched = DeviceArray.from_host(np.array([0.0, 0.0, learning_rate, 0.0, 0.0], np.float32))   # prev, passes, lr, halved, eval
+
+    def compute_eval_loss():                                      # utils/train.py:51-75: one read-back per pass
         for i in range(0, N, batch_size):
             lens = lens_host[i:i + batch_size]
             if lens.size == 0:
                 continue
             s_max = int(lens.max())
-            xb, yb = x_dev[i:i + batch_size][:, :s_max], y_dev[i:i + batch_size]
-            H, _ = model.forward(xb, return_hidden_only=True)
-            H_last = H[npb.arange(len(lens)), npb.array(lens - 1), :]
-            logits_last = H_last @ model.W_vocab + model.b_vocab
-            loss, _ = model.calculate_loss_dlogits(logits_last, yb)
-            total_loss += float(loss) * len(lens)
-            total_count += len(lens)
-        model.train()
-        return total_loss / max(1, total_count)
+            model.eval_batch_last_token(x_dev[i:i + batch_size][:, :s_max], y_dev[i:i + batch_size], accum, lens=lens)
+        return model.eval_finish(accum, sched)                    # (loss, lr after the schedule, halved)
 
     for epoch in range(nepoch):
         if epoch % evaluation_loss_after == 0:
-            eval_loss = compute_eval_loss()
+            eval_loss, learning_rate, halved = compute_eval_loss()
             losses.append((seen_examples, eval_loss))
             log(f"Eval loss={eval_loss:.6f} | ppl={np.exp(eval_loss):.2f} | seen={seen_examples} | epoch={epoch} | "
                 f"{time.time() - start_time:.1f}s")
-            if len(losses) > 1 and eval_loss > losses[-2][1]:
-                learning_rate *= 0.5
+            if halved:                                             # utils/train.py:86-88, decided on the device
                 log(f"Learning rate decreased to: {learning_rate}")
         perm = np.random.permutation(N)                           # same generator as utils/train.py:98
         x_dev, y_dev = x_dev[npb.array(perm)], y_dev[npb.array(perm)]
@@ -80,12 +76,7 @@ def train_transformer(model, x_train, y_train, learning_rate=0.01, nepoch=100, e
         if idx_to_word is not None and sample_prompts:            # utils/train.py:143-163
             log("\nSamples:")
             for prompt in sample_prompts:
-                seq = npb.array(prompt, dtype=npb.int32)[None, :]
-                H, _ = model.forward(seq, return_hidden_only=True)
-                next_logits = H[0, -1] @ model.W_vocab + model.b_vocab
-                probs = npb.exp(next_logits - next_logits.max())
-                probs /= probs.sum()
-                top_idx = np.array(npb.asnumpy(probs)).argsort()[-topk:][::-1]
+                top_idx, _ = model.topk_next(prompt, topk)
                 log("  -> " + " ".join(idx_to_word.get(int(j), "<UNK>") for j in top_idx))
     log(f"Training completed in {time.time() - start_time:.2f} sec")
     stats["losses"] = losses

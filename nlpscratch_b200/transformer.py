@@ -530,6 +530,53 @@ class Transformer:
         object.__setattr__(self, "_last_y", (yd, t))
         return DeviceScalar(loss, self)
 
+    # ---- evaluation / schedule / sampling of the driver loop without per-batch synchronisation -----------
+    def eval_batch_last_token(self, xb, yb, accum: DeviceArray, lens=None):
+        """One batch of ``compute_eval_loss`` (utils/train.py:51-75): adds the batch's summed last-token loss and its
+        row count to the 2-float device accumulator ``accum``; nothing is read back."""
+        xd = self._ids_to_device(xb)
+        yd = yb if isinstance(yb, DeviceArray) else DeviceArray.from_host(np.asarray(yb), np.int32)
+        B, S = xd.shape
+        if lens is None:
+            t = b200np.sum(xd != 0, axis=1) - 1
+        elif isinstance(lens, DeviceArray):
+            t = lens - 1
+        else:
+            t = DeviceArray.from_host(np.asarray(lens, dtype=np.int64) - 1, np.int32)
+        t, yd = t.contiguous(), yd.contiguous()
+        ch = C.c_void_p()
+        _lib.call("nlps_cache_create", self._h, C.c_int(B), C.c_int(S), C.byref(ch))
+        cache = Cache(self, ch, B, S, xd)
+        _lib.call("nlps_eval_last_token", self._h, ch, _lib.vp(xd.ptr), C.c_int64(xd.strides[0] if B > 1 else S),
+                  _lib.vp(t.ptr), _lib.vp(yd.ptr), _lib.vp(accum.ptr))
+        object.__setattr__(self, "_last_cache", cache)
+        object.__setattr__(self, "_last_y", (yd, t))
+
+    def eval_finish(self, accum: DeviceArray, sched: DeviceArray):
+        """Close an evaluation pass on the device: mean loss, "halve the learning rate if the loss went up"
+        (utils/train.py:86-88).  Returns (eval_loss, learning_rate, halved) -- the one read-back of the pass."""
+        _lib.call("nlps_eval_finish", self._h, _lib.vp(accum.ptr), _lib.vp(sched.ptr))
+        prev, n, lr, halved, loss = (float(v) for v in sched.get())
+        self._check_errors()
+        return loss, lr, bool(halved)
+
+    def topk_next(self, prompt, k: int = 5):
+        """The sampling block of the driver (utils/train.py:143-163) for one prompt: ids of the k most probable next
+        tokens, most probable first, and their probabilities -- softmax and selection on the device."""
+        seq = DeviceArray.from_host(np.asarray(prompt, dtype=np.int32)[None, :], np.int32)
+        was = self.training
+        self.training = False
+        try:
+            H, _ = self.forward(seq, return_hidden_only=True)
+        finally:
+            self.training = was
+        logits = (H[0, -1] @ self.W_vocab + self.b_vocab).contiguous()
+        V = self.vocab_size
+        work, idx, prob = DeviceArray.empty((V,), np.float32), DeviceArray.empty((k,), np.int32), DeviceArray.empty((k,), np.float32)
+        _lib.call("nlps_topk_softmax", _lib.stream_ptr(), _lib.vp(logits.ptr), C.c_int(V), C.c_int(int(k)), _lib.vp(work.ptr),
+                  _lib.vp(idx.ptr), _lib.vp(prob.ptr))
+        return idx.get(), prob.get()
+
     def apply_update(self, learning_rate, clip_grad_norm: Optional[float] = 1.0):
         """Second half of a deferred ``train_step`` (after the data-parallel all-reduce)."""
         if clip_grad_norm:

@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 900 python bench.py --workload c4 --steps 20 --warmup 5 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/bench_c4.json
-timeout 300 python tools/attn_bench.py 64 512 8 64 20 > gpurun_out/attention_c4.txt 2>&1; timeout 300 python tools/attn_bench.py 8 2048 12 64 10 >> gpurun_out/attention_c4.txt 2>&1; timeout 300 python tools/attn_bench.py 16 320 8 32 20 >> gpurun_out/attention_c4.txt 2>&1; NLPS_ATTN=ss timeout 300 python tools/attn_bench.py 64 512 8 64 20 | sed 's/^/first-generation (operands in shared memory): /' >> gpurun_out/attention_c4.txt 2>&1; cat gpurun_out/attention_c4.txt; bash tools/gpu_attn_split.sh > gpurun_out/attention_split_c4.txt 2>&1; cat gpurun_out/attention_split_c4.txt
+timeout 300 python tools/attn_bench.py 64 512 8 64 20 > gpurun_out/attention_c4.txt 2>&1; timeout 300 python tools/attn_bench.py 8 2048 12 64 10 >> gpurun_out/attention_c4.txt 2>&1; timeout 300 python tools/attn_bench.py 16 320 8 32 20 >> gpurun_out/attention_c4.txt 2>&1; cat gpurun_out/attention_c4.txt; bash tools/gpu_attn_split.sh > gpurun_out/attention_split_c4.txt 2>&1; cat gpurun_out/attention_split_c4.txt
 timeout 300 python tools/gemm_bench.py > gpurun_out/gemm_shapes.txt 2>&1; tail -3 gpurun_out/gemm_shapes.txt
 CMD="python bench.py --workload c4 --steps 2 --warmup 1 --quick"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_c4.csv $CMD > gpurun_out/ncu_c4.log 2>&1; echo "launch list rc=$?"
