@@ -635,7 +635,7 @@ def run_driver(args, wl):
             "config": {"workload": "c1: reference driver loop (nlpscratch_b200.train.train_transformer), last-token loss, "
                                    "%d prefixes x max_len %d (%d non-PAD tokens/epoch), B%d, host->device copy of the dataset "
                                    "and shuffles inside the timed region" % (len(Y), S, nonpad, B)},
-            "gpu_launches": model.launch_count(),
+            "gpu_launches": model.launch_count(), "graph_steps_eager_captured_replayed": list(model.graph_stats()),
             "e2e": {"value": tok_s, "unit": "non-pad tokens/s", "h2d_bytes_per_step": int(X.nbytes / max(1, stats["steps"])),
                     "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

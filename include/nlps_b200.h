@@ -172,6 +172,9 @@ int nlps_eval_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64
                          const int32_t* d_y, float* d_accum);
 int nlps_eval_finish(nlps_model* m, float* d_accum, float* d_sched);
 int nlps_topk_softmax(void* stream, const float* d_logits, int V, int k, float* d_work, int32_t* d_idx, float* d_prob);
+/* how the fused steps of this model ran so far: eagerly (first sighting of a signature, or not capturable), captured into a
+ * CUDA graph (second sighting), replayed */
+int nlps_graph_stats(nlps_model* m, int64_t* eager, int64_t* captured, int64_t* replayed);
 int nlps_launch_count(nlps_model* m, int64_t* launches, int reset);  /* kernels launched so far (process-wide counter) */
 
 /* ---- data-parallel exchange (the reference has no distributed code) -------------------------------------

@@ -110,6 +110,7 @@ struct nlps_model {
   // the setter that publishes the step's scalars (dropout counter, lr, Adam bias corrections) to device memory.
   struct StepGraph {
     const nlps_cache* cache; const int32_t* x; int64_t xs; const int32_t* y;
+    const int32_t* t;                  // last-token step: the (B,) index buffer; nullptr = full-sequence step
     float max_norm, grad_scale, dropout_p; int precision; bool training; bool deferred;
     unsigned long long epoch;
     int state;                         // 1 = signature seen once (ran eagerly), 2 = captured, 3 = not capturable
@@ -120,6 +121,7 @@ struct nlps_model {
     bool relu_bits_valid = false;
   };
   std::vector<StepGraph> graphs;
+  long long n_eager = 0, n_captured = 0, n_replayed = 0;   // how the fused steps ran (nlps_graph_stats)
   cudaStream_t own_stream = nullptr;   // created when the model would otherwise run on the legacy default stream
   float* hyper = nullptr;              // device {lr, bc1, bc2}
   bool in_graph_body = false;          // the per-call setters are replaced by the one setter node
@@ -221,6 +223,19 @@ DropoutParams drop_for(const nlps_model* m, const nlps_cache* c, int layer, int 
 }
 
 inline unsigned int* colsum_tickets_for(nlps_model* m, int64_t cols) { return ceil_div(cols, 128) <= 4096 ? m->colsum_tickets : nullptr; }
+
+// graphs that replay into a cache that is about to be freed
+void drop_graphs_of_cache(nlps_model* m, const nlps_cache* c) {
+  for (size_t i = 0; i < m->graphs.size();) {
+    if (m->graphs[i].cache == c) {
+      if (m->graphs[i].exec) cudaGraphExecDestroy(m->graphs[i].exec);
+      if (m->graphs[i].graph) cudaGraphDestroy(m->graphs[i].graph);
+      m->graphs.erase(m->graphs.begin() + i);
+    } else {
+      ++i;
+    }
+  }
+}
 
 void drop_step_graphs(nlps_model* m) {
   for (auto& g : m->graphs) {
@@ -747,9 +762,9 @@ int nlps_cache_create(nlps_model* m, int B, int S, nlps_cache** out) {
   if (e != cudaSuccess) {
     // out of memory: drop pooled caches and retry once
     cudaGetLastError();
-    for (nlps_cache* p : m->pool) { cudaFree(p->base); delete p; }
+    cudaStreamSynchronize(m->stream);
+    for (nlps_cache* p : m->pool) { drop_graphs_of_cache(m, p); cudaFree(p->base); delete p; }
     m->pool.clear();
-    bump_alloc_epoch();
     e = cudaMalloc(&c->base, c->bytes);
   }
   if (e != cudaSuccess) {
@@ -779,12 +794,12 @@ int nlps_cache_release(nlps_model* m, nlps_cache* c) {
   if (!c) return 0;
   NLPS_REQUIRE(m, "null model");
   c->valid = false;
-  if (m->pool.size() >= 6) {       // bound the pool: free the oldest entry
+  if (m->pool.size() >= 32) {      // bound the pool (one entry per batch shape; the driver loop has ~10 length buckets)
     nlps_cache* old = m->pool.front();
     m->pool.erase(m->pool.begin());
     cudaStreamSynchronize(m->stream);
+    drop_graphs_of_cache(m, old);          // only the graphs that replay into this cache; every other one stays valid
     cudaFree(old->base);
-    bump_alloc_epoch();
     delete old;
   }
   m->pool.push_back(c);
@@ -1041,8 +1056,16 @@ static int train_step_body(nlps_model* m, nlps_cache* c, const int32_t* d_x, int
   return nlps_step(m, lr, max_norm > 0.f ? 1 : 0);
 }
 
-static int train_step_graphed(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_y, float lr,
-                              float max_norm, float grad_scale, int defer_update, float* d_loss);
+static int train_step_graphed(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_t,
+                              const int32_t* d_y, float lr, float max_norm, float grad_scale, int defer_update, float* d_loss);
+static int last_token_body(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_t, const int32_t* d_y,
+                           float lr, float max_norm, float grad_scale, int defer_update, float* d_loss);
+// the eager form of either fused step: full-sequence objective (d_t == nullptr) or the driver's last-token objective
+static int run_body(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_t, const int32_t* d_y,
+                    float lr, float max_norm, float grad_scale, int defer_update, float* d_loss) {
+  if (d_t != nullptr) return last_token_body(m, c, d_x, xs, d_t, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
+  return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
+}
 
 int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_y, float lr,
                     float max_norm, float grad_scale, int defer_update, float* d_loss) {
@@ -1050,20 +1073,20 @@ int nlps_train_step(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs
   // with a communicator attached (nlps_comm_init) the undeferred step is the data-parallel step: the gradient buckets are
   // summed over ranks on the communication stream as backward completes them, and clip + update wait for the sums
   m->comm_active = m->comm != nullptr && !defer_update;
-  const int rc = train_step_graphed(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
+  const int rc = train_step_graphed(m, c, d_x, xs, nullptr, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
   m->comm_active = false;
   return rc;
 }
 
-static int train_step_graphed(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_y, float lr,
-                              float max_norm, float grad_scale, int defer_update, float* d_loss) {
+static int train_step_graphed(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_t,
+                              const int32_t* d_y, float lr, float max_norm, float grad_scale, int defer_update, float* d_loss) {
   // CUDA graph path, every arithmetic mode (the 3xTF32 operands live in a grow-only per-stream workspace).  First sighting
   // of a signature runs eagerly (it sizes every workspace), the second one is captured, later ones are replayed with one
   // patched node.
   static const bool dp_graph = [] { const char* e = getenv("NLPS_GRAPH_DP"); return !(e && e[0] == '0'); }();
   const bool graphable = m->graph_mode == 1 && (!defer_update || dp_graph) && m->stream != nullptr;
   const bool deferred = defer_update != 0;
-  if (!graphable) return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
+  if (!graphable) { m->n_eager++; return run_body(m, c, d_x, xs, d_t, d_y, lr, max_norm, grad_scale, defer_update, d_loss); }
   NLPS_CUDA(cudaSetDevice(m->device));
   const float drop_p = (m->training && m->dropout_p > 0.f) ? m->dropout_p : 0.f;
   nlps_model::StepGraph* e = nullptr;
@@ -1075,25 +1098,26 @@ static int train_step_graphed(nlps_model* m, nlps_cache* c, const int32_t* d_x, 
       m->graphs.erase(m->graphs.begin() + i);
       continue;
     }
-    if (g.cache == c && g.x == d_x && g.xs == xs && g.y == d_y && g.max_norm == max_norm && g.grad_scale == grad_scale &&
+    if (g.cache == c && g.x == d_x && g.xs == xs && g.y == d_y && g.t == d_t && g.max_norm == max_norm && g.grad_scale == grad_scale &&
         g.dropout_p == drop_p && g.precision == m->precision && g.training == m->training && g.deferred == deferred) e = &g;
     ++i;
   }
   if (e == nullptr) {
-    const int rc = train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
+    m->n_eager++;
+    const int rc = run_body(m, c, d_x, xs, d_t, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
     if (rc != 0) return rc;
-    if (m->graphs.size() >= 8) {               // bounded: forget the oldest signature
+    if (m->graphs.size() >= 48) {              // bounded: forget the oldest signature (the driver loop has one per length bucket)
       if (m->graphs.front().exec) cudaGraphExecDestroy(m->graphs.front().exec);
       if (m->graphs.front().graph) cudaGraphDestroy(m->graphs.front().graph);
       m->graphs.erase(m->graphs.begin());
     }
     nlps_model::StepGraph g{};
-    g.cache = c; g.x = d_x; g.xs = xs; g.y = d_y; g.max_norm = max_norm; g.grad_scale = grad_scale; g.dropout_p = drop_p;
+    g.cache = c; g.x = d_x; g.xs = xs; g.y = d_y; g.t = d_t; g.max_norm = max_norm; g.grad_scale = grad_scale; g.dropout_p = drop_p;
     g.precision = m->precision; g.training = m->training; g.deferred = deferred; g.epoch = alloc_epoch(); g.state = 1;
     m->graphs.push_back(g);
     return 0;
   }
-  if (e->state == 3) return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
+  if (e->state == 3) { m->n_eager++; return run_body(m, c, d_x, xs, d_t, d_y, lr, max_norm, grad_scale, defer_update, d_loss); }
   // this step's scalars
   const uint32_t step = m->fwd_counter;
   float bc1 = 1.f, bc2 = 1.f;
@@ -1108,13 +1132,13 @@ static int train_step_graphed(nlps_model* m, nlps_cache* c, const int32_t* d_x, 
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
       cudaGetLastError();
       e->state = 3;
-      return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
+      return run_body(m, c, d_x, xs, d_t, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
     }
     m->in_graph_body = true;
     m->graph_external_events = deferred;
     set_step_scalars_kernel<<<1, 1, 0, st>>>(a_slot, a_step, a_hyper, a_lr, a_bc1, a_bc2);
     count_launch();
-    const int rc = train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, loss_slot);
+    const int rc = run_body(m, c, d_x, xs, d_t, d_y, lr, max_norm, grad_scale, defer_update, loss_slot);
     m->in_graph_body = false;
     m->graph_external_events = false;
     cudaGraph_t graph = nullptr;
@@ -1144,10 +1168,11 @@ static int train_step_graphed(nlps_model* m, nlps_cache* c, const int32_t* d_x, 
       if (graph) cudaGraphDestroy(graph);
       if (rc == 0) { m->fwd_counter -= 1; if (m->cfg.use_adam && !deferred) m->adam_t -= 1; }
       // e may dangle if the vector changed: look the entry up again
-      for (auto& g : m->graphs) if (g.cache == c && g.x == d_x && g.y == d_y && g.state == 1) g.state = 3;
-      return train_step_body(m, c, d_x, xs, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
+      for (auto& g : m->graphs) if (g.cache == c && g.x == d_x && g.y == d_y && g.t == d_t && g.state == 1) g.state = 3;
+      return run_body(m, c, d_x, xs, d_t, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
     }
     e->graph = graph; e->exec = exec; e->setter = setter; e->state = 2;
+    m->n_captured++;
     e->launches = launch_count(false) - launches_before;
     e->relu_bits_valid = c->relu_bits_valid;
     // nothing has executed yet: this step's work is the first launch of the graph
@@ -1161,6 +1186,7 @@ static int train_step_graphed(nlps_model* m, nlps_cache* c, const int32_t* d_x, 
     kp.func = (void*)set_step_scalars_kernel;
     kp.gridDim = dim3(1, 1, 1); kp.blockDim = dim3(1, 1, 1); kp.sharedMemBytes = 0;
     kp.kernelParams = setter_args; kp.extra = nullptr;
+    m->n_replayed++;
     NLPS_CUDA(cudaGraphExecKernelNodeSetParams(e->exec, e->setter, &kp));
     NLPS_CUDA(cudaGraphLaunch(e->exec, m->stream));
     if (d_loss != nullptr) NLPS_CUDA(cudaMemcpyAsync(d_loss, loss_slot, sizeof(float), cudaMemcpyDeviceToDevice, m->stream));
@@ -1181,12 +1207,21 @@ int nlps_train_step_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x,
                                const int32_t* d_y, float lr, float max_norm, float grad_scale, int defer_update,
                                float* d_loss) {
   NLPS_REQUIRE(m && c && d_x && d_t && d_y, "nlps_train_step_last_token: null argument");
+  // like nlps_train_step: data-parallel when a communicator is attached, replayed as a CUDA graph from the third sighting
+  // of a (cache, x, t, y) signature on (the driver loop stages its batches into fixed buffers per length bucket)
+  m->comm_active = m->comm != nullptr && !defer_update;
+  const int rc = train_step_graphed(m, c, d_x, xs, d_t, d_y, lr, max_norm, grad_scale, defer_update, d_loss);
+  m->comm_active = false;
+  return rc;
+}
+
+static int last_token_body(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_t, const int32_t* d_y,
+                           float lr, float max_norm, float grad_scale, int defer_update, float* d_loss) {
   NLPS_TRY(nlps_forward(m, c, d_x, xs, 1, nullptr, 0));
   const int B = c->B, E = m->E;
   const float* h_final = m->L > 0 ? c->layers.back().y2 : c->h0;
-  // H_last (B,E) then logits_last (B,ldV) live at the head of the cache's logits buffer (N*ldV >= B*(E+ldV)
-  // does not hold for tiny vocabularies, so use the row scratch)
-  const int64_t off_h = round_up(2 * (int64_t)B * E + B, kAlign);          // after backward_last_token's own use
+  // H_last (B,E) then logits_last (B,ldV) live in the row scratch, behind backward_last_token's own use of it
+  const int64_t off_h = round_up(2 * (int64_t)B * E + B, kAlign);
   const int64_t off_l = off_h + round_up((int64_t)B * E, kAlign);
   NLPS_TRY(ensure_rows_tmp(m, off_l + (int64_t)B * m->ldV));
   float* h_last = m->rows_tmp + off_h;
@@ -1200,12 +1235,9 @@ int nlps_train_step_last_token(nlps_model* m, nlps_cache* c, const int32_t* d_x,
   float* loss = d_loss ? d_loss : m->scalars + 3;
   // row-loss scratch: the first B floats of rows_tmp are free until backward_last_token runs
   NLPS_TRY(softmax_xent(m->stream, logits, m->ldV, d_y, B, m->V, grad_scale, loss, logits, m->ldV, m->rows_tmp, m->err_flag));
-  m->comm_active = m->comm != nullptr && !defer_update;
-  int rc = nlps_backward_last_token(m, c, d_t, logits, m->ldV);
-  if (rc == 0 && m->comm_active) rc = comm_join(m);
-  m->comm_active = false;
-  if (rc != 0) return rc;
+  NLPS_TRY(nlps_backward_last_token(m, c, d_t, logits, m->ldV));
   if (defer_update) return 0;
+  if (m->comm_active) NLPS_TRY(comm_join(m));
   if (max_norm > 0.f) NLPS_TRY(nlps_clip_compute(m, max_norm));
   return nlps_step(m, lr, max_norm > 0.f ? 1 : 0);
 }
@@ -1363,6 +1395,14 @@ int nlps_eval_finish(nlps_model* m, float* d_accum, float* d_sched) {
 int nlps_topk_softmax(void* stream, const float* d_logits, int V, int k, float* d_work, int32_t* d_idx, float* d_prob) {
   NLPS_REQUIRE(d_logits && d_work && d_idx && d_prob, "nlps_topk_softmax: null argument");
   return topk_softmax((cudaStream_t)stream, d_logits, V, k, d_work, d_idx, d_prob);
+}
+
+int nlps_graph_stats(nlps_model* m, int64_t* eager, int64_t* captured, int64_t* replayed) {
+  NLPS_REQUIRE(m, "null model");
+  if (eager) *eager = m->n_eager;
+  if (captured) *captured = m->n_captured;
+  if (replayed) *replayed = m->n_replayed;
+  return 0;
 }
 
 int nlps_launch_count(nlps_model*, int64_t* launches, int reset) {

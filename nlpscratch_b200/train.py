@@ -34,6 +34,17 @@ def train_transformer(model, x_train, y_train, learning_rate=0.01, nepoch=100, e
     N = len(y_host)
     stats = {"steps": 0, "tokens": 0, "train_seconds": 0.0}
 
+    def bucket(lens):
+        # utils/train.py:108-110 trims a batch to its longest sequence; here the trim is rounded up to the next multiple of
+        # 8 columns so that an epoch has ~10 batch shapes (one activation cache and one CUDA graph each) instead of ~60.
+        # The extra columns hold PAD ids: masked keys contribute exact zeros and their (zero) gradients add exact zeros.
+        # (An all-PAD row -- never produced by the prefix datasets -- reads position s_max-1 through t = -1, so a batch
+        # that holds one keeps the exact trim.)
+        s_max = int(lens.max())
+        if int(lens.min()) >= 1:
+            s_max = min(x_host.shape[1], (s_max + 7) // 8 * 8)
+        return s_max
+
     accum = DeviceArray.from_host(np.zeros(2, np.float32))
     sched = DeviceArray.from_host(np.array([0.0, 0.0, learning_rate, 0.0, 0.0], np.float32))   # prev, passes, lr, halved, eval
 
@@ -42,7 +53,7 @@ def train_transformer(model, x_train, y_train, learning_rate=0.01, nepoch=100, e
             lens = lens_host[i:i + batch_size]
             if lens.size == 0:
                 continue
-            s_max = int(lens.max())
+            s_max = bucket(lens)
             model.eval_batch_last_token(x_dev[i:i + batch_size][:, :s_max], y_dev[i:i + batch_size], accum, lens=lens)
         return model.eval_finish(accum, sched)                    # (loss, lr after the schedule, halved)
 
@@ -57,13 +68,14 @@ def train_transformer(model, x_train, y_train, learning_rate=0.01, nepoch=100, e
         perm = np.random.permutation(N)                           # same generator as utils/train.py:98
         x_dev, y_dev = x_dev[npb.array(perm)], y_dev[npb.array(perm)]
         lens_host = lens_host[perm]
+        t_dev = npb.array(lens_host - 1)                          # the epoch's last-token indices: one copy, sliced below
         t0 = time.time()
         token_done, last_loss = 0, None
         for bi, i in enumerate(range(0, N, batch_size)):
             lens = lens_host[i:i + batch_size]
-            s_max = int(lens.max())
+            s_max = bucket(lens)
             xb, yb = x_dev[i:i + batch_size][:, :s_max], y_dev[i:i + batch_size]
-            last_loss = model.train_step_last_token(xb, yb, lens=lens, learning_rate=learning_rate,
+            last_loss = model.train_step_last_token(xb, yb, t_index=t_dev[i:i + batch_size], learning_rate=learning_rate,
                                                     clip_grad_norm=clip_grad_norm)
             seen_examples += len(lens)
             token_done += int(lens.sum())

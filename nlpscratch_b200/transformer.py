@@ -499,11 +499,12 @@ class Transformer:
         return sx, sy
 
     def train_step_last_token(self, xb, yb, lens=None, learning_rate=1e-4, clip_grad_norm: Optional[float] = 1.0,
-                              grad_scale: float = 1.0, defer_update: bool = False) -> DeviceScalar:
+                              grad_scale: float = 1.0, defer_update: bool = False, t_index=None) -> DeviceScalar:
         """One iteration of the reference driver's hot loop (utils/train.py:104-131) as a single call:
         forward on the (already trimmed) batch, last-real-token vocab head, loss, backward_last_token,
         clip, Adam -- with no host synchronisation.  ``lens`` = non-PAD length per row (host or device
-        int array); computed on the device when omitted."""
+        int array); computed on the device when omitted; ``t_index`` (device int32, = lens - 1) wins over both.
+        Batches are staged into fixed buffers per shape, so the library replays the step as a CUDA graph."""
         xd = self._ids_to_device(xb)
         yd = yb if isinstance(yb, DeviceArray) else DeviceArray.from_host(np.asarray(yb), np.int32)
         B, S = xd.shape
@@ -511,13 +512,17 @@ class Transformer:
             raise ValueError("yb %s must have shape (%d,)" % (yd.shape, B))
         if yd.bounds is not None and not (-self.vocab_size <= yd.bounds[0] and yd.bounds[1] < self.vocab_size):
             raise IndexError("target id out of bounds for %d classes" % self.vocab_size)
-        if lens is None:
+        if t_index is not None:
+            t = t_index
+        elif lens is None:
             t = b200np.sum(xd != 0, axis=1) - 1
         elif isinstance(lens, DeviceArray):
             t = lens - 1
         else:
             t = DeviceArray.from_host(np.asarray(lens, dtype=np.int64) - 1, np.int32)
-        t, yd = t.contiguous(), yd.contiguous()
+        if t.shape != (B,):
+            raise ValueError("t_index / lens must have shape (%d,)" % B)
+        xd, t, yd = self._static_inputs_last(xd, t, yd)
         ch = C.c_void_p()
         _lib.call("nlps_cache_create", self._h, C.c_int(B), C.c_int(S), C.byref(ch))
         cache = Cache(self, ch, B, S, xd)
@@ -529,6 +534,27 @@ class Transformer:
         object.__setattr__(self, "_last_cache", cache)
         object.__setattr__(self, "_last_y", (yd, t))
         return DeviceScalar(loss, self)
+
+    def _static_inputs_last(self, xd: DeviceArray, t: DeviceArray, yd: DeviceArray):
+        """Staging buffers per batch shape for the last-token step (see ``_static_inputs``): the driver loop hands over a
+        fresh strided slice every iteration; copied into fixed (B,S) / (B,) buffers, every batch of a shape replays one graph."""
+        if _STATIC_INPUTS_OFF:
+            return (xd if xd.strides[1] == 1 or xd.shape[1] <= 1 else xd.copy()), t.contiguous(), yd.contiguous()
+        stages = self.__dict__.get("_stage_last")
+        if stages is None:
+            stages = {}
+            object.__setattr__(self, "_stage_last", stages)
+        st = stages.get(xd.shape)
+        if st is None:
+            B, S = xd.shape
+            st = (DeviceArray.empty((B, S), np.int32), DeviceArray.empty((B,), np.int32), DeviceArray.empty((B,), np.int32))
+            stages[xd.shape] = st
+        sx, st_t, sy = st
+        _array._strided_copy(xd, sx)
+        _array._strided_copy(t, st_t)
+        _array._strided_copy(yd, sy)
+        sx.bounds, sy.bounds, st_t.bounds = xd.bounds, yd.bounds, t.bounds
+        return sx, st_t, sy
 
     # ---- evaluation / schedule / sampling of the driver loop without per-batch synchronisation (SURVEY 8f #2) -----------
     def eval_batch_last_token(self, xb, yb, accum: DeviceArray, lens=None):
@@ -582,6 +608,12 @@ class Transformer:
         if clip_grad_norm:
             _lib.call("nlps_clip_compute", self._h, C.c_float(float(clip_grad_norm)))
         _lib.call("nlps_step", self._h, C.c_float(float(learning_rate)), C.c_int(1 if clip_grad_norm else 0))
+
+    def graph_stats(self):
+        """(eager, captured, replayed) counts of the fused steps: how often the CUDA-graph path really served them."""
+        e, c, r = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.call("nlps_graph_stats", self._h, C.byref(e), C.byref(c), C.byref(r))
+        return e.value, c.value, r.value
 
     def launch_count(self, reset=False) -> int:
         n = C.c_int64()
