@@ -84,6 +84,14 @@ int nlps_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
 int nlps_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream);
 int nlps_memset(void* d_dst, int value, size_t bytes, void* stream);
 int nlps_stream_sync(void* stream);
+/* read-back without stalling the GPU: asynchronous copy into PINNED host memory, ordered by an event the host waits on
+ * later (a training loop reads step i's loss while step i+1 runs; utils/train.py:138 reads it at once) */
+int nlps_memcpy_d2h_async(void* h_pinned, const void* d_src, size_t bytes, void* stream);
+int nlps_event_create(void** event);
+int nlps_event_record(void* event, void* stream);
+int nlps_event_synchronize(void* event);
+int nlps_event_destroy(void* event);
+int nlps_model_stream(nlps_model* m, void** stream);              /* the cudaStream_t the model's work is ordered on */
 int nlps_host_alloc_pinned(void** h_ptr, size_t bytes);
 int nlps_host_free_pinned(void* h_ptr);
 

@@ -8,7 +8,7 @@ behind ``libnlps_b200.so`` (``include/nlps_b200.h``); importing the package neve
 """
 from . import _lib
 from .array import DeviceArray, b200np, matmul
-from .transformer import PARAM_NAMES, Cache, DeviceScalar, Transformer
+from .transformer import PARAM_NAMES, Cache, DeviceScalar, HostScalarSlot, Transformer
 
-__all__ = ["Transformer", "DeviceArray", "DeviceScalar", "Cache", "b200np", "matmul", "PARAM_NAMES", "_lib"]
+__all__ = ["Transformer", "DeviceArray", "DeviceScalar", "HostScalarSlot", "Cache", "b200np", "matmul", "PARAM_NAMES", "_lib"]
 __version__ = "0.1.0"

@@ -246,6 +246,12 @@ size_t layernorm_backward_scratch_floats(int E);
 int softmax_xent_rows(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V, float inv,
                       float* dlogits, int64_t ldd, float* row_loss, int32_t* err = nullptr);
 int row_loss_mean(cudaStream_t st, const float* row_loss, int64_t rows, float* loss);
+// cross-entropy whose pass also leaves the column-sum partials of dlogits (the vocabulary-bias gradient) behind
+int64_t xent_colsum_partial_rows(int64_t rows);
+bool xent_colsum_fusable(const float* logits, int64_t ld, const float* dlogits, int64_t ldd, int V);
+int softmax_xent_colsum(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
+                        float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss, float* partial,
+                        int64_t ld_partial, int32_t* err);
 // device-side evaluation bookkeeping of the driver loop (utils/train.py:51-75, 86-88, 143-163)
 int eval_accumulate(cudaStream_t st, const float* row_loss, int64_t rows, float* accum);
 int eval_finish(cudaStream_t st, float* accum, float* sched);

@@ -77,6 +77,8 @@ struct nlps_model {
   int64_t ws_N = 0;
   float *g0 = nullptr, *g1 = nullptr, *gdrop = nullptr, *dctx = nullptr, *dqkv = nullptr, *dhid = nullptr;
   float* colsum32 = nullptr;                  // [ceil(N/32)][F] column-sum partials written by the dz GEMM epilogue
+  float* dbv_partial = nullptr;               // [ceil(N/16)][ldV] column-sum partials of dlogits left by the fused cross-entropy
+  int64_t dbv_partial_rows = 0;               // > 0: the next nlps_backward takes db_vocab from them
   float *g1b = nullptr, *gdropb = nullptr;    // LayerNorm-2 backward outputs (own buffers so that the weight-gradient stream may lag)
   // weight-gradient stream: dW2, dW1, dWo, dWqkv and dW_vocab are off the critical path of backward; on a second stream
   // they fill the tensor pipe while the main stream runs its bandwidth-bound kernels (LayerNorm backward, column sums,
@@ -180,7 +182,8 @@ int ensure_workspace(nlps_model* m, int B, int S) {
   if (N <= m->ws_N) return 0;
   NLPS_CUDA(cudaStreamSynchronize(m->stream));
   if (m->wstream) NLPS_CUDA(cudaStreamSynchronize(m->wstream));
-  float** bufs[] = {&m->g0, &m->g1, &m->gdrop, &m->dctx, &m->dqkv, &m->dhid, &m->delta, &m->row_loss, &m->colsum32, &m->g1b, &m->gdropb};
+  float** bufs[] = {&m->g0, &m->g1, &m->gdrop, &m->dctx, &m->dqkv, &m->dhid, &m->delta, &m->row_loss, &m->colsum32, &m->g1b, &m->gdropb,
+                    &m->dbv_partial};
   for (float** b : bufs) { if (*b) cudaFree(*b); *b = nullptr; }
   bump_alloc_epoch();
   if (m->iscratch) { cudaFree(m->iscratch); m->iscratch = nullptr; }
@@ -194,6 +197,7 @@ int ensure_workspace(nlps_model* m, int B, int S) {
   NLPS_CUDA(cudaMalloc(&m->dqkv, sizeof(float) * N * 3 * E));
   NLPS_CUDA(cudaMalloc(&m->dhid, sizeof(float) * N * F));
   NLPS_CUDA(cudaMalloc(&m->colsum32, sizeof(float) * ceil_div(N, 32) * F));
+  NLPS_CUDA(cudaMalloc(&m->dbv_partial, sizeof(float) * xent_colsum_partial_rows(N) * m->ldV));
   NLPS_CUDA(cudaMalloc(&m->delta, sizeof(float) * N * m->h));
   NLPS_CUDA(cudaMalloc(&m->row_loss, sizeof(float) * N));
   NLPS_CUDA(cudaMalloc(&m->iscratch, sizeof(int32_t) * embed_backward_scratch_ints(N, m->V)));
@@ -523,6 +527,35 @@ int nlps_stream_sync(void* stream) {
   NLPS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
 }
+// asynchronous read-back into PINNED host memory + events, so that a loop can read step i's loss while step i+1 runs
+int nlps_memcpy_d2h_async(void* h_pinned, const void* d, size_t bytes, void* stream) {
+  if (bytes) NLPS_CUDA(cudaMemcpyAsync(h_pinned, d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
+}
+int nlps_event_create(void** event) {
+  NLPS_REQUIRE(event, "nlps_event_create: null argument");
+  cudaEvent_t e;
+  NLPS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *event = e;
+  return 0;
+}
+int nlps_event_record(void* event, void* stream) {
+  NLPS_CUDA(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+  return 0;
+}
+int nlps_event_synchronize(void* event) {
+  NLPS_CUDA(cudaEventSynchronize((cudaEvent_t)event));
+  return 0;
+}
+int nlps_event_destroy(void* event) {
+  if (event) NLPS_CUDA(cudaEventDestroy((cudaEvent_t)event));
+  return 0;
+}
+int nlps_model_stream(nlps_model* m, void** stream) {
+  NLPS_REQUIRE(m && stream, "null argument");
+  *stream = m->stream;
+  return 0;
+}
 int nlps_host_alloc_pinned(void** h_ptr, size_t bytes) {
   NLPS_CUDA(cudaMallocHost(h_ptr, bytes ? bytes : 4));
   return 0;
@@ -616,7 +649,7 @@ int nlps_destroy(nlps_model* m) {
   for (nlps_cache* c : m->pool) { if (c->base) cudaFree(c->base); delete c; }
   float* bufs[] = {m->P, m->G, m->M, m->Vv, m->pe, m->g0, m->g1, m->gdrop, m->dctx, m->dqkv, m->dhid, m->delta,
                    m->row_loss, m->rows_tmp, m->ln_partial, m->colsum_scratch, m->sumsq_scratch, m->scalars, m->colsum32,
-                   m->g1b, m->gdropb};
+                   m->g1b, m->gdropb, m->dbv_partial};
   for (float* b : bufs) if (b) cudaFree(b);
   if (m->iscratch) cudaFree(m->iscratch);
   if (m->err_flag) cudaFree(m->err_flag);
@@ -844,6 +877,7 @@ int nlps_forward(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, i
   c->drop_p = (m->training && m->dropout_p > 0.f) ? m->dropout_p : 0.f;
   c->drop_step = m->fwd_counter++;
   c->has_logits = false;
+  m->dbv_partial_rows = 0;             // column-sum partials of an earlier (possibly failed) step are not this step's
   if (!m->in_graph_body && c->drop_p > 0.f) {
     set_step_scalars_kernel<<<1, 1, 0, st>>>(c->dev_step, c->drop_step, nullptr, 0.f, 0.f, 0.f);
     NLPS_LAUNCH_CHECK();
@@ -932,7 +966,11 @@ int nlps_backward(nlps_model* m, nlps_cache* c, const float* d_dlogits, int64_t 
     NLPS_TRY(wgrad_fork(m, &ws));                      // off the critical path: weight-gradient stream
     NLPS_TRY(gemm_dispatch(ws, m->precision, g));
     NLPS_TRY(wgrad_done(m, W_VOCAB));
-    NLPS_TRY(colsum(st, N, m->V, d_dlogits, ldd, m->G + m->off_bvocab, m->colsum_scratch, colsum_tickets_for(m, m->V)));
+    if (m->dbv_partial_rows > 0)     // the cross-entropy pass already summed 16-row slabs of these dlogits
+      NLPS_TRY(colsum(st, m->dbv_partial_rows, m->V, m->dbv_partial, m->ldV, m->G + m->off_bvocab, m->colsum_scratch, colsum_tickets_for(m, m->V)));
+    else
+      NLPS_TRY(colsum(st, N, m->V, d_dlogits, ldd, m->G + m->off_bvocab, m->colsum_scratch, colsum_tickets_for(m, m->V)));
+    m->dbv_partial_rows = 0;
   }
   {  // dH = dlogits W_vocab^T                                          (:355)
     GemmArgs g = gemm_nn(N, E, m->V, d_dlogits, ldd, m->P + m->off_Wvocab, m->ldV, m->g0, E);
@@ -1044,8 +1082,20 @@ static int train_step_body(nlps_model* m, nlps_cache* c, const int32_t* d_x, int
   // dlogits overwrite the logits in place: 8V bytes of HBM traffic per token for the loss
   NLPS_CUDA(cudaSetDevice(m->device));
   NLPS_TRY(ensure_rows_tmp(m, c->N));
-  NLPS_TRY(softmax_xent_stats(m->stream, c->logits, m->ldV, d_y, c->N, m->V, grad_scale, d_loss ? d_loss : m->scalars + 3, c->logits,
-                              m->ldV, m->rows_tmp, c->rowstat_valid ? c->rowstat : nullptr, m->err_flag));
+  // NLPS_FUSE_DBV=1: the vocabulary-bias gradient rides on the cross-entropy pass.  OPT-IN: same-box A/B at c4 measured it
+  // SLOWER (13.65 vs 13.50 ms/step) -- a CTA that walks 16 rows with two block barriers per row hides less latency than
+  // 16 one-row CTAs, which costs the bandwidth-bound pass more than the saved 1.07 GB column-sum read returns
+  static int fuse_dbv = -1;
+  if (fuse_dbv < 0) { const char* e = getenv("NLPS_FUSE_DBV"); fuse_dbv = (e && e[0] == '1') ? 1 : 0; }
+  if (fuse_dbv && !c->rowstat_valid && xent_colsum_fusable(c->logits, m->ldV, c->logits, m->ldV, m->V)) {
+    NLPS_TRY(ensure_workspace(m, c->B, c->S));
+    NLPS_TRY(softmax_xent_colsum(m->stream, c->logits, m->ldV, d_y, c->N, m->V, grad_scale, d_loss ? d_loss : m->scalars + 3,
+                                 c->logits, m->ldV, m->rows_tmp, m->dbv_partial, m->ldV, m->err_flag));
+    m->dbv_partial_rows = xent_colsum_partial_rows(c->N);
+  } else {
+    NLPS_TRY(softmax_xent_stats(m->stream, c->logits, m->ldV, d_y, c->N, m->V, grad_scale, d_loss ? d_loss : m->scalars + 3, c->logits,
+                                m->ldV, m->rows_tmp, c->rowstat_valid ? c->rowstat : nullptr, m->err_flag));
+  }
   }
   c->has_logits = false;
   c->rowstat_valid = false;

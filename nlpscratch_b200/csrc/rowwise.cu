@@ -335,6 +335,80 @@ __global__ void __launch_bounds__(256) xent_kernel(const float* logits, int64_t 
   }
 }
 
+// Cross-entropy with the vocabulary-bias gradient riding along (db_vocab = column sums of dlogits, transformer.py:353):
+// a CTA walks kXentRows consecutive rows with the arithmetic of xent_kernel and keeps, per thread, the running column sums
+// of the dlogits it writes (thread t owns columns 4t + 1024k); at the end it stores one partial row.  The column-sum pass
+// over the (N, V) dlogits (1.07 GB at c4) becomes a column-sum pass over the (N/16, V) partials.  Fixed order: deterministic.
+constexpr int kXentRows = 16;
+constexpr int kXentMaxChunks = 16;      // V <= 16384
+template <int CHUNKS>
+__global__ void __launch_bounds__(256) xent_colsum_kernel(const float* logits, int64_t ld, const int32_t* __restrict__ y, int V,
+                                                          int64_t rows, float inv_rows_scaled, float* dlogits, int64_t ldd,
+                                                          float* __restrict__ row_loss, float* __restrict__ partial,
+                                                          int64_t ld_partial, int32_t* err) {
+  __shared__ float sm_m[8], sm_s[8];
+  __shared__ float bc[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * kXentRows, r1 = min(rows, r0 + kXentRows);
+  float4 acc[CHUNKS];
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t row = r0; row < r1; ++row) {
+    const float* z = logits + row * ld;
+    float* dz = dlogits + row * ldd;
+    float m = -INFINITY, s = 0.f;
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+      const int c = tid * 4 + k * 1024;
+      if (c < V) {
+        const float4 v = *reinterpret_cast<const float4*>(z + c);
+        const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        if (mx > m) { s *= expf(m - mx); m = mx; }
+        s += (expf(v.x - m) + expf(v.y - m)) + (expf(v.z - m) + expf(v.w - m));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      if (m2 > -INFINITY) { if (m > -INFINITY) online_merge(m, s, m2, s2); else { m = m2; s = s2; } }
+    }
+    if (lane == 0) { sm_m[warp] = m; sm_s[warp] = s; }
+    __syncthreads();
+    if (tid == 0) {
+      float M = sm_m[0], S = sm_s[0];
+      for (int w = 1; w < 8; ++w)
+        if (sm_m[w] > -INFINITY) { if (M > -INFINITY) online_merge(M, S, sm_m[w], sm_s[w]); else { M = sm_m[w]; S = sm_s[w]; } }
+      bc[0] = M; bc[1] = S;
+      const int t = xent_target(y, row, V, err);
+      row_loss[row] = -(z[t] - M - logf(S));
+    }
+    __syncthreads();
+    const float M = bc[0], invS = 1.f / bc[1];
+    const int target = xent_target(y, row, V, nullptr);
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+      const int c = tid * 4 + k * 1024;
+      if (c < V) {
+        const float4 v = *reinterpret_cast<const float4*>(z + c);
+        float4 o;
+        o.x = (expf(v.x - M) * invS - (c + 0 == target ? 1.f : 0.f)) * inv_rows_scaled;
+        o.y = (expf(v.y - M) * invS - (c + 1 == target ? 1.f : 0.f)) * inv_rows_scaled;
+        o.z = (expf(v.z - M) * invS - (c + 2 == target ? 1.f : 0.f)) * inv_rows_scaled;
+        o.w = (expf(v.w - M) * invS - (c + 3 == target ? 1.f : 0.f)) * inv_rows_scaled;
+        *reinterpret_cast<float4*>(dz + c) = o;
+        acc[k].x += o.x; acc[k].y += o.y; acc[k].z += o.z; acc[k].w += o.w;
+      }
+    }
+    __syncthreads();          // bc / sm_* are rewritten by the next row
+  }
+  float* prow = partial + (int64_t)blockIdx.x * ld_partial;
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) {
+    const int c = tid * 4 + k * 1024;
+    if (c < V) *reinterpret_cast<float4*>(prow + c) = acc[k];
+  }
+}
+
 // out[0] = scale * sum(x[0..n)) with a fixed tree: one CTA, deterministic
 __global__ void __launch_bounds__(1024) sum_to_scalar_kernel(const float* __restrict__ x, int64_t n, float scale,
                                                              float* __restrict__ out) {
@@ -572,6 +646,30 @@ int softmax_xent(cudaStream_t st, const float* logits, int64_t ld, const int32_t
   const int vec_ok = (V % 4 == 0 && ld % 4 == 0 && ldd % 4 == 0 && aligned16(logits) && aligned16(dlogits)) ? 1 : 0;
   const float inv = (float)((double)grad_scale / (double)rows);
   xent_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, ld, y, V, inv, dlogits, ldd, row_loss, vec_ok, err);
+  NLPS_LAUNCH_CHECK();
+  sum_to_scalar_kernel<<<1, 1024, 0, st>>>(row_loss, rows, (float)(1.0 / (double)rows), loss);
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+
+int64_t xent_colsum_partial_rows(int64_t rows) { return ceil_div(rows, (int64_t)kXentRows); }
+bool xent_colsum_fusable(const float* logits, int64_t ld, const float* dlogits, int64_t ldd, int V) {
+  return V % 4 == 0 && V <= 1024 * kXentMaxChunks && ld % 4 == 0 && ldd % 4 == 0 && aligned16(logits) && aligned16(dlogits);
+}
+// softmax_xent that also leaves the (ceil(rows/16), V) column-sum partials of dlogits in `partial` (row stride ld_partial)
+int softmax_xent_colsum(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V,
+                        float grad_scale, float* loss, float* dlogits, int64_t ldd, float* row_loss, float* partial,
+                        int64_t ld_partial, int32_t* err) {
+  NLPS_REQUIRE(rows > 0 && V > 0, "softmax_xent: empty input");
+  NLPS_REQUIRE(xent_colsum_fusable(logits, ld, dlogits, ldd, V) && ld_partial % 4 == 0 && aligned16(partial),
+               "softmax_xent_colsum: operands not fusable");
+  const float inv = (float)((double)grad_scale / (double)rows);
+  const unsigned grid = (unsigned)xent_colsum_partial_rows(rows);
+  const int chunks = (int)ceil_div(V, 1024);
+#define NLPS_XC(C) xent_colsum_kernel<C><<<grid, 256, 0, st>>>(logits, ld, y, V, rows, inv, dlogits, ldd, row_loss, partial, ld_partial, err)
+  if (chunks <= 1) NLPS_XC(1); else if (chunks <= 2) NLPS_XC(2); else if (chunks <= 4) NLPS_XC(4);
+  else if (chunks <= 8) NLPS_XC(8); else NLPS_XC(16);
+#undef NLPS_XC
   NLPS_LAUNCH_CHECK();
   sum_to_scalar_kernel<<<1, 1024, 0, st>>>(row_loss, rows, (float)(1.0 / (double)rows), loss);
   NLPS_LAUNCH_CHECK();

@@ -129,6 +129,47 @@ class DeviceScalar:
     def __gt__(self, o): return float(self) > self._f(o)
 
 
+class HostScalarSlot:
+    """A pinned 4-byte host slot + event for reading a device scalar (a step's loss) WITHOUT stalling the GPU:
+    ``slot.fetch(loss)`` enqueues the copy behind the step that produces the value and returns at once; ``slot.value()``
+    waits for that copy only.  A loop that fetches step i's loss and reads step i-1's keeps the GPU busy back to back --
+    what the reference's ``float(loss)`` every iteration (utils/train.py:138) cannot do."""
+
+    def __init__(self, model: "Transformer"):
+        self._model = model
+        self._host = C.c_void_p()
+        _lib.call("nlps_host_alloc_pinned", C.byref(self._host), C.c_size_t(4))
+        self._event = C.c_void_p()
+        _lib.call("nlps_event_create", C.byref(self._event))
+        self._pending = False
+
+    def fetch(self, scalar: "DeviceScalar"):
+        st = C.c_void_p()
+        _lib.call("nlps_model_stream", self._model._h, C.byref(st))
+        _lib.call("nlps_memcpy_d2h_async", self._host, _lib.vp(scalar._arr.ptr), C.c_size_t(4), st)
+        _lib.call("nlps_event_record", self._event, st)
+        self._keep = scalar                       # the device value must outlive the copy
+        self._pending = True
+
+    def value(self) -> float:
+        if not self._pending:
+            raise RuntimeError("HostScalarSlot.value() before fetch()")
+        _lib.call("nlps_event_synchronize", self._event)
+        return float(C.cast(self._host, C.POINTER(C.c_float))[0])
+
+    def close(self):
+        if self._event:
+            _lib.load().nlps_event_destroy(self._event)
+            _lib.load().nlps_host_free_pinned(self._host)
+            self._event = self._host = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _lecun_host(shape, fan_in):
     """U(-1/sqrt(fan_in), +1/sqrt(fan_in)) from NumPy's GLOBAL generator, drawn in the reference's
     order (transformer.py:34-54,596-598) so ``np.random.seed(k)`` gives the reference's weights."""

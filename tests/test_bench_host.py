@@ -84,6 +84,11 @@ class FakeModel:
     def close(self): pass
     def synchronize(self): pass
 nlpscratch_b200.Transformer = FakeModel
+class FakeSlot:
+    def __init__(self, m): self.v = None
+    def fetch(self, l): self.v = float(l)
+    def value(self): return self.v
+nlpscratch_b200.HostScalarSlot = FakeSlot
 ctypes.memmove = lambda *a: None
 import importlib.util
 spec = importlib.util.spec_from_file_location("bench", %r); b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)

@@ -86,3 +86,29 @@ def test_topk_sampling_matches_numpy(V, k):
     assert np.array_equal(idx, want), (idx, want)
     assert np.allclose(prob, p[want], rtol=1e-4, atol=1e-7)
     m.close()
+
+
+def test_pipelined_loss_read_back_returns_every_steps_loss():
+    """HostScalarSlot: step i's loss is copied to a pinned slot behind the step and read while step i+1 runs; the values
+    are the ones a synchronous float(loss) returns (same steps, fresh model)."""
+    from nlpscratch_b200 import HostScalarSlot
+    cfg = (97, 32, 4, 64, 2, 20)
+    rng = np.random.default_rng(0)
+    x = rng.integers(1, 97, (4, 20)).astype(np.int32)
+    y = rng.integers(0, 97, (4, 20)).astype(np.int32)
+    got, want = [], []
+    for mode in ("pipelined", "sync"):
+        np.random.seed(5)
+        m = Transformer(*cfg, dropout_p=0.1, precision="fp32", seed=9)
+        if mode == "sync":
+            want = [float(m.train_step(x, y, 1e-3, 1.0)) for _ in range(6)]
+        else:
+            slots = [HostScalarSlot(m), HostScalarSlot(m)]
+            for i in range(6):
+                slots[i % 2].fetch(m.train_step(x, y, 1e-3, 1.0))
+                if i:
+                    got.append(slots[(i - 1) % 2].value())
+            got.append(slots[5 % 2].value())
+            m.synchronize()
+        m.close()
+    assert got == want
