@@ -745,6 +745,43 @@ __global__ void __launch_bounds__(256) splitk_reduce_vec_kernel(const KernelArgs
   }
 }
 
+// reducer WITH the fused epilogue (bias -> ReLU -> float gate -> dropout -> residual -> accumulate) on float4 lanes: the
+// forward / dgrad products of the 3xTF32 mode whose K exceeds one chunk end here.  Same order of operations per element as
+// gemm_epilogue_one, same split order as the scalar kernel => same bits.
+__global__ void __launch_bounds__(256) splitk_reduce_epi_vec_kernel(const KernelArgs ka) {
+  const GemmArgs& g = ka.g;
+  const int n4 = g.N >> 2;
+  const int64_t total = (int64_t)g.M * n4;
+  const int64_t sstride = (int64_t)g.M * ka.ws_ld;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / n4), col = (int)(i - (int64_t)row * n4) * 4;
+    const float* src = ka.ws + (int64_t)row * ka.ws_ld + col;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    for (; s + 2 <= ka.splits; s += 2) {
+      const float4 a = *reinterpret_cast<const float4*>(src + (s + 0) * sstride);
+      const float4 b = *reinterpret_cast<const float4*>(src + (s + 1) * sstride);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+      acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+    }
+    for (; s < ka.splits; ++s) {
+      const float4 a = *reinterpret_cast<const float4*>(src + s * sstride);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    if (g.bias) { const float4 b = *reinterpret_cast<const float4*>(g.bias + col); acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w; }
+    if (g.relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    if (g.gate) {
+      const float4 t = *reinterpret_cast<const float4*>(g.gate + (int64_t)row * g.ldg + col);
+      acc.x = t.x > 0.f ? acc.x : 0.f; acc.y = t.y > 0.f ? acc.y : 0.f; acc.z = t.z > 0.f ? acc.z : 0.f; acc.w = t.w > 0.f ? acc.w : 0.f;
+    }
+    if (g.drop.p > 0.f) dropout_four(g.drop, (uint64_t)row * (uint64_t)g.N + (uint64_t)col, acc);
+    if (g.residual) { const float4 t = *reinterpret_cast<const float4*>(g.residual + (int64_t)row * g.ldr + col); acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+    float4* dst = reinterpret_cast<float4*>(g.C + (int64_t)row * g.ldc + col);
+    if (g.accumulate) { const float4 o = *dst; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+    *dst = acc;
+  }
+}
+
 // 3xTF32 operand: hi = round-to-nearest TF32 of x (low 13 mantissa bits zero), lo = x - hi (exact in FP32), written side by
 // side ALONG K into one buffer with segment stride Kp (a multiple of the 32-float k-block; the gap is zero-filled):
 //   k_cols != 0 (K is the contiguous axis, source rows x K):  out[r][k] = hi, out[r][Kp + k] = lo,        ldo >= 2*Kp
@@ -971,9 +1008,15 @@ int gemm_tf32_impl(cudaStream_t st, const GemmArgs& g, bool round_tf32, bool x3 
     const int64_t total = (int64_t)g.M * g.N;
     const bool plain = !g.bias && !g.relu && !g.gate && !g.gate_bits && !g.relu_bits_out && g.drop.p <= 0.f && !g.residual &&
                        g.N % 4 == 0 && ka.ws_ld % 4 == 0 && g.ldc % 4 == 0 && aligned16(g.C) && aligned16(ka.ws);
+    const bool vec_epi = !g.gate_bits && !g.relu_bits_out && g.N % 4 == 0 && ka.ws_ld % 4 == 0 && g.ldc % 4 == 0 && aligned16(g.C) &&
+                         aligned16(ka.ws) && (!g.bias || aligned16(g.bias)) && (!g.gate || (aligned16(g.gate) && g.ldg % 4 == 0)) &&
+                         (!g.residual || (aligned16(g.residual) && g.ldr % 4 == 0));
     if (plain) {
       const int rgrid = (int)std::min<int64_t>(ceil_div(total / 4, 256), kNumSMs * 8);
       splitk_reduce_vec_kernel<<<rgrid, 256, 0, st>>>(ka);
+    } else if (vec_epi) {
+      const int rgrid = (int)std::min<int64_t>(ceil_div(total / 4, 256), kNumSMs * 16);
+      splitk_reduce_epi_vec_kernel<<<rgrid, 256, 0, st>>>(ka);
     } else {
       const int rgrid = (int)std::min<int64_t>(ceil_div(total, 256), kNumSMs * 8);
       splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(ka);

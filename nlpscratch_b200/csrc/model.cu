@@ -41,7 +41,8 @@ struct nlps_cache {
   float* h0 = nullptr;
   struct L { float *qkv, *ctx, *lse, *r1, *mean1, *rstd1, *y1, *hid, *r2, *mean2, *rstd2, *y2; uint32_t* relu_bits; };
   std::vector<L> layers;
-  float* logits = nullptr;
+  float* logits = nullptr;            // (N, ldV) logits / dlogits + the rowstat block: allocated on first use (ensure_cache_logits) --
+  char* logits_base = nullptr;        // the fused vocabulary path (NLPS_FUSE_VOCAB) never needs them
   uint32_t* dev_step = nullptr;       // drop_step on the device: what the kernels of this cache read (graph-replayable)
   float2* rowstat = nullptr;          // [N][ceil(V/32)] softmax statistics left by the vocab-head GEMM epilogue
   bool rowstat_valid = false;
@@ -77,6 +78,8 @@ struct nlps_model {
   int64_t ws_N = 0;
   float *g0 = nullptr, *g1 = nullptr, *gdrop = nullptr, *dctx = nullptr, *dqkv = nullptr, *dhid = nullptr;
   float* colsum32 = nullptr;                  // [ceil(N/32)][F] column-sum partials written by the dz GEMM epilogue
+  float* vchunk = nullptr;                    // fused vocabulary path: (vchunk_rows, ldV) logits -> dlogits of one row chunk
+  int64_t vchunk_rows = 0;
   float* dbv_partial = nullptr;               // [ceil(N/16)][ldV] column-sum partials of dlogits left by the fused cross-entropy
   int64_t dbv_partial_rows = 0;               // > 0: the next nlps_backward takes db_vocab from them
   float *g1b = nullptr, *gdropb = nullptr;    // LayerNorm-2 backward outputs (own buffers so that the weight-gradient stream may lag)
@@ -461,6 +464,17 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
   return 0;
 }
 
+// the (N, ldV) logits / dlogits buffer (+ the softmax-statistics block) of a cache, allocated when a call first needs it
+int ensure_cache_logits(nlps_model* m, nlps_cache* c) {
+  if (c->logits != nullptr) return 0;
+  const int64_t n_logits = round_up(c->N * m->ldV, kAlign);
+  const int64_t n_stat = round_up(2 * c->N * ((m->V + 31) / 32), kAlign);
+  NLPS_CUDA(cudaMalloc(&c->logits_base, sizeof(float) * (size_t)(n_logits + n_stat)));
+  c->logits = reinterpret_cast<float*>(c->logits_base);
+  c->rowstat = reinterpret_cast<float2*>(c->logits + n_logits);
+  return 0;
+}
+
 int check_cache(const nlps_model* m, const nlps_cache* c) {
   NLPS_REQUIRE(m && c, "null model or cache");
   NLPS_REQUIRE(c->valid, "cache does not hold a forward pass");
@@ -646,10 +660,10 @@ int nlps_destroy(nlps_model* m) {
   if (!m) return 0;
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
-  for (nlps_cache* c : m->pool) { if (c->base) cudaFree(c->base); delete c; }
+  for (nlps_cache* c : m->pool) { if (c->base) cudaFree(c->base); if (c->logits_base) cudaFree(c->logits_base); delete c; }
   float* bufs[] = {m->P, m->G, m->M, m->Vv, m->pe, m->g0, m->g1, m->gdrop, m->dctx, m->dqkv, m->dhid, m->delta,
                    m->row_loss, m->rows_tmp, m->ln_partial, m->colsum_scratch, m->sumsq_scratch, m->scalars, m->colsum32,
-                   m->g1b, m->gdropb, m->dbv_partial};
+                   m->g1b, m->gdropb, m->dbv_partial, m->vchunk};
   for (float* b : bufs) if (b) cudaFree(b);
   if (m->iscratch) cudaFree(m->iscratch);
   if (m->err_flag) cudaFree(m->err_flag);
@@ -788,15 +802,13 @@ int nlps_cache_create(nlps_model* m, int B, int S, nlps_cache** out) {
     q.hid = carve(N * F); q.r2 = carve(N * E); q.mean2 = carve(N); q.rstd2 = carve(N); q.y2 = carve(N * E);
     q.bits = carve(N * ((F + 31) / 32));
   }
-  const int64_t o_logits = carve(N * m->ldV);
-  const int64_t o_rowstat = carve(2 * N * ((m->V + 31) / 32));
   c->bytes = (size_t)cur * sizeof(float);
   cudaError_t e = cudaMalloc(&c->base, c->bytes);
   if (e != cudaSuccess) {
     // out of memory: drop pooled caches and retry once
     cudaGetLastError();
     cudaStreamSynchronize(m->stream);
-    for (nlps_cache* p : m->pool) { drop_graphs_of_cache(m, p); cudaFree(p->base); delete p; }
+    for (nlps_cache* p : m->pool) { drop_graphs_of_cache(m, p); cudaFree(p->base); if (p->logits_base) cudaFree(p->logits_base); delete p; }
     m->pool.clear();
     e = cudaMalloc(&c->base, c->bytes);
   }
@@ -817,8 +829,6 @@ int nlps_cache_create(nlps_model* m, int B, int S, nlps_cache** out) {
                     f + q.hid, f + q.r2, f + q.mean2, f + q.rstd2, f + q.y2,
                     reinterpret_cast<uint32_t*>(f + q.bits)};
   }
-  c->logits = f + o_logits;
-  c->rowstat = reinterpret_cast<float2*>(f + o_rowstat);
   *out = c;
   return 0;
 }
@@ -833,6 +843,7 @@ int nlps_cache_release(nlps_model* m, nlps_cache* c) {
     cudaStreamSynchronize(m->stream);
     drop_graphs_of_cache(m, old);          // only the graphs that replay into this cache; every other one stays valid
     cudaFree(old->base);
+    if (old->logits_base) cudaFree(old->logits_base);
     delete old;
   }
   m->pool.push_back(c);
@@ -861,6 +872,7 @@ int nlps_cache_layer_ptr(nlps_model* m, nlps_cache* c, int layer, int which, voi
 
 int nlps_cache_logits_ptr(nlps_cache* c, void** p, int64_t* ld) {
   NLPS_REQUIRE(c && p, "null argument");
+  NLPS_REQUIRE(c->logits != nullptr, "this cache holds no logits (hidden-only forward or fused vocabulary path)");
   *p = c->logits;
   (void)ld;
   return 0;
@@ -920,6 +932,7 @@ int nlps_forward(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, i
     x_in = a.y2;
   }
   if (!hidden_only) {  // logits = H W_vocab + b_vocab                 (:191)
+    NLPS_TRY(ensure_cache_logits(m, c));
     GemmArgs g = gemm_nn(N, m->V, E, x_in, E, m->P + m->off_Wvocab, m->ldV, c->logits, m->ldV);
     g.bias = m->P + m->off_bvocab;
     // NLPS_FUSE_CE=1: softmax statistics come out of this product's epilogue and the loss skips its first pass over
@@ -1045,39 +1058,97 @@ int nlps_adam_t(nlps_model* m, int64_t* t, int set, int64_t value) {
   return 0;
 }
 
+// Fused vocabulary head + cross-entropy + vocabulary backward that never materialises the (N, V) logits / dlogits (SURVEY 8f #1;
+// transformer.py:191, 515-549, 352-355).  The rows are walked in chunks small enough for the chunk's logits to stay in L2:
+//   logits_c = H_c W_vocab + b_vocab  ->  dlogits_c in place (per-row losses aside)  ->  db partial_c = column sums,
+//   dW_vocab (+)= H_c^T dlogits_c,  dH_c = dlogits_c W_vocab^T
+// so the 5 passes over an (N, V) matrix that the materialising path pays in HBM (write logits, read + write in the loss,
+// read for dW_vocab, read for dH) happen in L2, and the activation cache loses its largest tensor (1.07 GB at c4, 4.3 GB
+// at V = 32768).  Same kernels and the same per-row arithmetic as the materialising path; dW_vocab and db_vocab are summed
+// chunk by chunk in a fixed order (deterministic; not the bits of the one-shot sums).
+static int vocab_chunk_rows(const nlps_model* m, int64_t N) {
+  static int64_t mb = -1;
+  if (mb < 0) { const char* e = getenv("NLPS_VOCAB_CHUNK_MB"); mb = e ? std::max(1, atoi(e)) : 48; }
+  int64_t rows = (mb << 20) / (m->ldV * 4);
+  rows = std::max<int64_t>(256, rows / 256 * 256);
+  return (int)std::min<int64_t>(rows, N);
+}
+
+static int fused_vocab_head(nlps_model* m, nlps_cache* c, const int32_t* d_y, float grad_scale, float* d_loss) {
+  NLPS_CUDA(cudaSetDevice(m->device));
+  NLPS_TRY(ensure_workspace(m, c->B, c->S));
+  NLPS_TRY(ensure_rows_tmp(m, c->N));
+  const int64_t N = c->N, E = m->E;
+  const int rows = vocab_chunk_rows(m, N);
+  if (m->vchunk_rows < rows) {
+    NLPS_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->vchunk) cudaFree(m->vchunk);
+    bump_alloc_epoch();
+    m->vchunk = nullptr;
+    NLPS_CUDA(cudaMalloc(&m->vchunk, sizeof(float) * (size_t)rows * m->ldV));
+    m->vchunk_rows = rows;
+  }
+  cudaStream_t st = m->stream;
+  const float* h_final = m->L > 0 ? c->layers.back().y2 : c->h0;
+  const float inv = (float)((double)grad_scale / (double)N);
+  int k = 0;
+  for (int64_t r0 = 0; r0 < N; r0 += rows, ++k) {
+    const int n = (int)std::min<int64_t>(rows, N - r0);
+    const float* h_c = h_final + r0 * E;
+    {  // logits_c = H_c W_vocab + b_vocab                                 (transformer.py:191)
+      GemmArgs g = gemm_nn(n, m->V, (int)E, h_c, E, m->P + m->off_Wvocab, m->ldV, m->vchunk, m->ldV);
+      g.bias = m->P + m->off_bvocab;
+      NLPS_TRY(gemm_dispatch(st, m->precision, g));
+    }
+    // dlogits_c in place, per-row losses aside                          (:515-549)
+    NLPS_TRY(softmax_xent_rows(st, m->vchunk, m->ldV, d_y + r0, n, m->V, inv, m->vchunk, m->ldV, m->rows_tmp + r0, m->err_flag));
+    // db_vocab partial of this chunk                                    (:353)
+    NLPS_TRY(colsum(st, n, m->V, m->vchunk, m->ldV, m->dbv_partial + (int64_t)k * m->ldV, m->colsum_scratch, colsum_tickets_for(m, m->V)));
+    {  // dW_vocab (+)= H_c^T dlogits_c                                    (:352)
+      GemmArgs g = gemm_nn((int)E, m->V, n, h_c, E, m->vchunk, m->ldV, m->G + m->off_Wvocab, m->ldV);
+      g.trans_a = true;
+      g.accumulate = k > 0;
+      NLPS_TRY(gemm_dispatch(st, m->precision, g));
+    }
+    {  // dH_c = dlogits_c W_vocab^T                                       (:355)
+      GemmArgs g = gemm_nn(n, (int)E, m->V, m->vchunk, m->ldV, m->P + m->off_Wvocab, m->ldV, m->g0 + r0 * E, E);
+      g.trans_b = true;
+      NLPS_TRY(gemm_dispatch(st, m->precision, g));
+    }
+  }
+  NLPS_TRY(row_loss_mean(st, m->rows_tmp, N, d_loss ? d_loss : m->scalars + 3));
+  NLPS_TRY(colsum(st, k, m->V, m->dbv_partial, m->ldV, m->G + m->off_bvocab, m->colsum_scratch, colsum_tickets_for(m, m->V)));
+  NLPS_TRY(record_bucket(m, 0));
+  return 0;
+}
+
+// NLPS_FUSE_VOCAB=1 selects the fused vocabulary path.  OPT-IN: it removes the (N, V) tensor from memory (1.07 GB at c4,
+// 4.3 GB at V = 32768) but same-box A/Bs measured it slower at every configuration -- c3 2.00 -> 2.32 ms, c4 13.18 -> 13.49,
+// c4 with V 32768 20.2 -> 22.3, c5 27.2 -> 27.5 with 96 MB chunks, worse with 64 / 32 MB chunks that do stay in L2: what the
+// chunks cost (partial waves of the 256x256 tiles on 1-3 k rows, split-K for the short dH products, the dW_vocab
+// accumulator read and written once per chunk) exceeds what the L2-resident passes save.
+static bool fused_vocab_wanted(const nlps_model*, const nlps_cache*) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NLPS_FUSE_VOCAB"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 // the fused step as it always ran: forward, loss (dlogits in place), backward, clip, update
 static int train_step_body(nlps_model* m, nlps_cache* c, const int32_t* d_x, int64_t xs, const int32_t* d_y, float lr,
                            float max_norm, float grad_scale, int defer_update, float* d_loss) {
-  // Row-chunked vocabulary head (needs the second stream): the cross-entropy of chunk k (bandwidth-bound, in place) runs on
-  // the second stream while the tensor pipe forms the logits of chunk k+1.  Rows are independent in both kernels and the
-  // loss is reduced over all rows afterwards, so the bits equal the one-shot form.  OPT-IN (NLPS_VOCAB_CHUNKS=4): same-box
-  // A/B at c4 and c3 showed no gain (13.17 vs 13.17 ms; 2, 4, 8 chunks) -- the K = 512 vocabulary product already writes
-  // 2.4 TB/s, so the cross-entropy next to it only trades places with it on the memory system.
-  static int want_chunks = -1;
-  if (want_chunks < 0) { const char* e = getenv("NLPS_VOCAB_CHUNKS"); want_chunks = e ? std::max(1, atoi(e)) : 1; }
   static int fuse_ce_on = -1;
   if (fuse_ce_on < 0) { const char* e = getenv("NLPS_FUSE_CE"); fuse_ce_on = (e && e[0] == '1') ? 1 : 0; }
-  const int64_t chunk_rows = round_up(ceil_div(c->N, (int64_t)want_chunks), 256);
-  if (m->wstream != nullptr && want_chunks > 1 && !fuse_ce_on && chunk_rows < c->N) {
+  if (fused_vocab_wanted(m, c) && !fuse_ce_on && c->N > 0) {
     NLPS_TRY(nlps_forward(m, c, d_x, xs, 1, nullptr, 0));
-    NLPS_CUDA(cudaSetDevice(m->device));
-    NLPS_TRY(ensure_rows_tmp(m, c->N));
-    const float* h_final = m->L > 0 ? c->layers.back().y2 : c->h0;
-    const float inv = (float)((double)grad_scale / (double)c->N);
-    for (int64_t r0 = 0; r0 < c->N; r0 += chunk_rows) {
-      const int64_t n = std::min<int64_t>(chunk_rows, c->N - r0);
-      float* lg = c->logits + r0 * m->ldV;
-      GemmArgs g = gemm_nn((int)n, m->V, m->E, h_final + r0 * m->E, m->E, m->P + m->off_Wvocab, m->ldV, lg, m->ldV);
-      g.bias = m->P + m->off_bvocab;                                     // logits = H W_vocab + b_vocab  (:191)
-      NLPS_TRY(gemm_dispatch(m->stream, m->precision, g));
-      cudaStream_t ws = m->stream;
-      NLPS_TRY(wgrad_fork(m, &ws));
-      NLPS_TRY(softmax_xent_rows(ws, lg, m->ldV, d_y + r0, n, m->V, inv, lg, m->ldV, m->rows_tmp + r0, m->err_flag));
-    }
-    NLPS_TRY(wgrad_done(m, W_XENT));
-    NLPS_TRY(wgrad_need(m, W_XENT));                                     // the second stream is in order: this covers every chunk
-    NLPS_TRY(row_loss_mean(m->stream, m->rows_tmp, c->N, d_loss ? d_loss : m->scalars + 3));
-  } else {
+    NLPS_TRY(fused_vocab_head(m, c, d_y, grad_scale, d_loss));
+    c->has_logits = false;
+    c->rowstat_valid = false;
+    NLPS_TRY(backward_stack(m, c));
+    if (defer_update) return 0;
+    if (m->comm_active) NLPS_TRY(comm_join(m));
+    if (max_norm > 0.f) NLPS_TRY(nlps_clip_compute(m, max_norm));
+    return nlps_step(m, lr, max_norm > 0.f ? 1 : 0);
+  }
   NLPS_TRY(nlps_forward(m, c, d_x, xs, 0, nullptr, 0));
   // dlogits overwrite the logits in place: 8V bytes of HBM traffic per token for the loss
   NLPS_CUDA(cudaSetDevice(m->device));
@@ -1095,7 +1166,6 @@ static int train_step_body(nlps_model* m, nlps_cache* c, const int32_t* d_x, int
   } else {
     NLPS_TRY(softmax_xent_stats(m->stream, c->logits, m->ldV, d_y, c->N, m->V, grad_scale, d_loss ? d_loss : m->scalars + 3, c->logits,
                                 m->ldV, m->rows_tmp, c->rowstat_valid ? c->rowstat : nullptr, m->err_flag));
-  }
   }
   c->has_logits = false;
   c->rowstat_valid = false;

@@ -599,3 +599,52 @@ def test_resume_checkpoint_restores_parameters_and_adam_state(tmp_path):
     assert b.adam_t == 0
     assert float(np.abs(b.m["We"].get()).max()) == 0.0
     a.close(); b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_fused_vocabulary_path_matches_the_materialising_one_and_the_oracle(precision, tmp_path):
+    """NLPS_FUSE_VOCAB=1: vocabulary head, cross-entropy and vocabulary backward walk the rows in L2-sized
+    chunks and never materialise the (N, V) logits / dlogits.  Same kernels and per-row arithmetic as the materialising path;
+    only dW_vocab / db_vocab are summed chunk by chunk.  Four chunks here (the last one ragged), odd vocabulary, PAD tail,
+    dropout on; compared with the materialising path (same Philox masks) and, with dropout off, with the oracle."""
+    import subprocess, sys, os, json
+    code = r"""
+import json, sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from nlpscratch_b200 import Transformer
+from oracle.transformer_oracle import OracleTransformer, full_sequence_step
+cfg = (641, 128, 4, 256, 2, 160)
+rng = np.random.default_rng(0)
+x = rng.integers(1, 641, (6, 160)).astype(np.int32); x[1, 100:] = 0
+y = rng.integers(0, 641, (6, 160)).astype(np.int32)
+out = {}
+for p in (0.1, 0.0):
+    np.random.seed(3)
+    oracle = OracleTransformer(*cfg, dropout_p=0.0)
+    m = Transformer(*cfg, dropout_p=p, precision=%r, seed=5)
+    m.load_params(oracle.params)
+    losses = [float(m.train_step(x, y, learning_rate=1e-3, clip_grad_norm=1.0)) for _ in range(4)]
+    params = m.get_params()
+    out[str(p)] = {"losses": losses, "W_vocab": params["W_vocab"].astype(np.float64).ravel()[::97].tolist(),
+                   "b_vocab": params["b_vocab"].astype(np.float64).tolist(), "We": params["We"].astype(np.float64).ravel()[::131].tolist()}
+    if p == 0.0:
+        want = [full_sequence_step(oracle, x, y, lr=1e-3, clip=1.0)[0] for _ in range(4)]
+        out["oracle"] = {"losses": want, "b_vocab": oracle.params["b_vocab"].astype(np.float64).tolist()}
+    m.close()
+print(json.dumps(out))
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), precision)
+    res = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, NLPS_FUSE_VOCAB=flag, NLPS_VOCAB_CHUNK_MB="1")
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-3000:]
+        res[flag] = json.loads(r.stdout.strip().splitlines()[-1])
+    tol = 2e-5 if precision == "fp32" else 2e-3
+    for p in ("0.1", "0.0"):
+        a, b = res["0"][p], res["1"][p]
+        assert np.allclose(a["losses"], b["losses"], rtol=tol, atol=0), (p, a["losses"], b["losses"])
+        for k in ("W_vocab", "b_vocab", "We"):
+            assert np.max(np.abs(np.array(a[k]) - np.array(b[k]))) <= (1e-6 if precision == "fp32" else 2.5e-3 * 4), (p, k)
+    o = res["1"]["oracle"]
+    assert np.allclose(res["1"]["0.0"]["losses"], o["losses"], rtol=1e-5 if precision == "fp32" else 2e-3, atol=0)
