@@ -97,6 +97,21 @@ global_norm_clip([grads[k] for k in grads], 1.0); model.step(grads, 1e-3)
 global_norm_clip([g[k] for k in g], 1.0); ref.step(g, 1e-3)
 for k in g:
     assert np.allclose(model.params[k], ref.params[k], rtol=0, atol=2e-6), k
+# save_checkpoint_rank0 (SURVEY 8f #4): rank 0 alone writes, every rank returns only after the file is complete
+from nlpscratch_b200.dp import save_checkpoint_rank0
+import pickle, types
+class _Model:
+    def save_checkpoint(self, filename):
+        import time
+        time.sleep(0.3)                                    # a slow writer: the barrier must cover it
+        with open(filename, "wb") as fh:
+            pickle.dump({"params": {k: v for k, v in model.params.items()}, "adam_t": model.adam_t}, fh)
+ck = os.path.join(os.environ["CKDIR"], "ck.pkl")
+save_checkpoint_rank0(types.SimpleNamespace(rank=rank, model=_Model(), _dist=dist, group=None), ck)
+with open(ck, "rb") as fh:                                 # readable on EVERY rank right after the call
+    state = pickle.load(fh)
+assert state["adam_t"] == 1 and all(np.array_equal(state["params"][k], model.params[k]) for k in model.params)
+assert os.path.getsize(ck) > 0 and len([f for f in os.listdir(os.environ["CKDIR"]) if f.endswith(".pkl")]) == 1
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok", worst)
 '''
@@ -106,7 +121,7 @@ def test_two_rank_gloo_data_parallel_identity(tmp_path):
     script = os.path.join(tmp_path, "worker.py")
     with open(script, "w") as fh:
         fh.write(WORKER)
-    env = dict(os.environ, REPO=ROOT, OMP_NUM_THREADS="2", OPENBLAS_NUM_THREADS="2")
+    env = dict(os.environ, REPO=ROOT, OMP_NUM_THREADS="2", OPENBLAS_NUM_THREADS="2", CKDIR=str(tmp_path))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29533", script]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=280)
