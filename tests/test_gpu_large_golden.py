@@ -5,7 +5,8 @@ public API: reference-default model (full-sequence and the driver's last-token p
 In `tf32` mode these shapes run the kernels the benchmark times (asserted through nlps_kernel_stats): the CTA-pair
 tcgen05 GEMM and the persistent tcgen05 attention.  Tolerances (norm-wise relative on deterministic samples, and on f64 norms):
   fp32, tf32x3 : 1e-4 logits / hidden / loss / every gradient tensor; updated weights 1e-4
-  tf32         : 5e-3 logits / hidden, 2e-3 loss, 5e-2 gradients (10-bit operand mantissas: the reference's own cuBLAS TF32 mode),
+  tf32         : 2e-3 logits / hidden, 2e-4 loss, 4e-2 gradients, per-tensor gradient norms within the same bound
+                 (10-bit operand mantissas: the reference's own cuBLAS TF32 mode; observed 4.8e-4 / 1.2e-5 / 2.0e-2),
                  updated weights within 2.5*lr*steps (Adam's first steps are +-lr*sign(g)); the same bound replaces the 1e-4 one
                  in the FP32-faithful modes when a near-zero ReLU gate flipped (next paragraph): the flip perturbs the
                  gradients below it by ~1e-4, which turns the Adam sign of a few near-zero gradient elements (2*lr each)
@@ -38,7 +39,7 @@ from oracle.transformer_oracle import OracleTransformer  # noqa: E402
 
 TOL = {"fp32": dict(act=1e-4, grad=1e-4, loss=1e-5, param=1e-4),
        "tf32x3": dict(act=1e-4, grad=1e-4, loss=1e-5, param=1e-4),
-       "tf32": dict(act=5e-3, grad=5e-2, loss=2e-3, param=None)}
+       "tf32": dict(act=2e-3, grad=4e-2, loss=2e-4, param=None)}     # observed: 4.8e-4 / 2.0e-2 / 1.2e-5 (profiles/r02_parity_large.json)
 REPORT = {}
 
 
