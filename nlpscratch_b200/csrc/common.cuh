@@ -240,7 +240,10 @@ int layernorm_backward(cudaStream_t st, int64_t rows, int E, const float* dy, co
                        const float* mean, const float* rstd, const float* gamma, float* dx,
                        float* dx_dropped, const DropoutParams* drop,
                        float* dgamma, float* dbeta, float* partial_scratch,
-                       float* dbias = nullptr);   // optional: column sums of the branch gradient leaving the kernel (dx_dropped, else dx)
+                       float* dbias = nullptr,    // optional: column sums of the branch gradient leaving the kernel (dx_dropped, else dx)
+                       bool defer_finish = false);   // true: the partial sums stay in partial_scratch for layernorm_backward_finish
+int layernorm_backward_finish(cudaStream_t st, int64_t rows, int E, const float* partial, float* dgamma, float* dbeta,
+                              float* dbias = nullptr);
 size_t layernorm_backward_scratch_floats(int E);
 // rowstat != nullptr: per-32-column {max, sum exp} blocks from the vocab-head GEMM epilogue (see GemmArgs::rowstat_out)
 int softmax_xent_rows(cudaStream_t st, const float* logits, int64_t ld, const int32_t* y, int64_t rows, int V, float inv,

@@ -95,6 +95,7 @@ struct nlps_model {
   int64_t rows_tmp_cap = 0;
   // fixed scratch
   float *ln_partial = nullptr, *colsum_scratch = nullptr, *sumsq_scratch = nullptr;
+  float* colsum_scratch_w = nullptr;          // column sums issued on the weight-gradient stream use their own scratch + tickets
   unsigned int* colsum_tickets = nullptr;     // 4096 self-resetting counters: one per 128-column group of a colsum
   float* scalars = nullptr;          // [0]=sumsq [1]=clip scale [2]=norm [3]=loss
   int32_t* err_flag = nullptr;
@@ -230,6 +231,15 @@ DropoutParams drop_for(const nlps_model* m, const nlps_cache* c, int layer, int 
 }
 
 inline unsigned int* colsum_tickets_for(nlps_model* m, int64_t cols) { return ceil_div(cols, 128) <= 4096 ? m->colsum_tickets : nullptr; }
+// NLPS_SIDE_SUMS=0 keeps the reductions nobody waits for (LayerNorm parameter-gradient finish, db1, db_vocab) on the main
+// stream as in round 1 (A/B); default: they ride on the weight-gradient stream
+inline bool side_sums() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NLPS_SIDE_SUMS"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+// column sums issued on the weight-gradient stream may run next to main-stream ones: own counters
+inline unsigned int* colsum_tickets_w(nlps_model* m, int64_t cols) { return ceil_div(cols, 128) <= 4096 ? m->colsum_tickets + 4096 : nullptr; }
 
 // graphs that replay into a cache that is about to be freed
 void drop_graphs_of_cache(nlps_model* m, const nlps_cache* c) {
@@ -369,14 +379,18 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
     // LN2 backward (+ dropout backward of the FFN branch)
     DropoutParams dpf = drop_for(m, c, l, 1);
     NLPS_TRY(wgrad_need(m, W_DW2));                    // the layer above read d_f from these buffers
+    float* part2 = m->ln_partial + (size_t)(2 * l + 1) * layernorm_backward_scratch_floats(E);
+    float* part1 = m->ln_partial + (size_t)(2 * l) * layernorm_backward_scratch_floats(E);
     NLPS_TRY(layernorm_backward(st, N, E, m->g0, a.r2, a.mean2, a.rstd2, m->P + o.ln2g, g1b,
                                 dropping ? gdropb : nullptr, dropping ? &dpf : nullptr, m->G + o.ln2g,
-                                m->G + o.ln2b, m->ln_partial, m->G + o.b2));     // db2 = column sums of d_f ride along
+                                m->G + o.ln2b, part2, m->G + o.b2, /*defer_finish=*/true));   // db2 = column sums of d_f ride along
     const float* d_f = dropping ? gdropb : g1b;
     {  // dW2 = hid^T d_f ; db2
       GemmArgs g = gemm_nn(F, E, N, a.hid, F, d_f, E, m->G + o.w2, E);
       g.trans_a = true;
       NLPS_TRY(wgrad_fork(m, &ws));
+      // the LayerNorm parameter gradients (and db2) are nobody's input: their final sum leaves the critical path
+      NLPS_TRY(layernorm_backward_finish(side_sums() ? ws : st, N, E, part2, m->G + o.ln2g, m->G + o.ln2b, m->G + o.b2));
       NLPS_TRY(gemm_dispatch(ws, prec, g));
       NLPS_TRY(wgrad_done(m, W_DW2));
     }
@@ -398,9 +412,16 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
       g.trans_a = true;
       NLPS_TRY(wgrad_fork(m, &ws));
       NLPS_TRY(gemm_dispatch(ws, prec, g));
+      // db1 on the same stream, before the event that guards dhid / the epilogue partials against the next layer's dz product
+      {
+        const bool side = side_sums();
+        cudaStream_t cs = side ? ws : st;
+        float* scratch = side ? m->colsum_scratch_w : m->colsum_scratch;
+        unsigned int* tickets = side ? colsum_tickets_w(m, F) : colsum_tickets_for(m, F);
+        if (db1_fused) NLPS_TRY(colsum(cs, ceil_div(N, 32), F, m->colsum32, F, m->G + o.b1, scratch, tickets));
+        else NLPS_TRY(colsum(cs, N, F, m->dhid, F, m->G + o.b1, scratch, tickets));
+      }
       NLPS_TRY(wgrad_done(m, W_DW1));
-      if (db1_fused) NLPS_TRY(colsum(st, ceil_div(N, 32), F, m->colsum32, F, m->G + o.b1, m->colsum_scratch, colsum_tickets_for(m, F)));
-      else NLPS_TRY(colsum(st, N, F, m->dhid, F, m->G + o.b1, m->colsum_scratch, colsum_tickets_for(m, F)));
     }
     {  // d(y1) = dz W1^T + d_r2
       GemmArgs g = gemm_nn(N, E, F, m->dhid, F, m->P + o.w1, F, m->g0, E);
@@ -413,12 +434,13 @@ int backward_stack(nlps_model* m, nlps_cache* c) {
     NLPS_TRY(wgrad_need(m, W_DWO));                    // the layer above read d_a from these buffers
     NLPS_TRY(layernorm_backward(st, N, E, m->g0, a.r1, a.mean1, a.rstd1, m->P + o.ln1g, m->g1,
                                 dropping ? m->gdrop : nullptr, dropping ? &dpa : nullptr, m->G + o.ln1g,
-                                m->G + o.ln1b, m->ln_partial));
+                                m->G + o.ln1b, part1, nullptr, /*defer_finish=*/true));
     const float* d_a = dropping ? m->gdrop : m->g1;
     {  // dWo = ctx^T d_a
       GemmArgs g = gemm_nn(E, E, N, a.ctx, E, d_a, E, m->G + o.wo, E);
       g.trans_a = true;
       NLPS_TRY(wgrad_fork(m, &ws));
+      NLPS_TRY(layernorm_backward_finish(side_sums() ? ws : st, N, E, part1, m->G + o.ln1g, m->G + o.ln1b));
       NLPS_TRY(gemm_dispatch(ws, prec, g));
       NLPS_TRY(wgrad_done(m, W_DWO));
     }
@@ -618,10 +640,13 @@ int nlps_create(const nlps_config* cfg, int device, nlps_model** out) {
       }
     NLPS_CUDA(cudaMemcpy(m->pe, pe.data(), sizeof(float) * pe.size(), cudaMemcpyHostToDevice));
   }
-  NLPS_CUDA(cudaMalloc(&m->ln_partial, sizeof(float) * layernorm_backward_scratch_floats(m->E)));
+  // one slice per LayerNorm of the stack: the partial sums of a backward are finished on the weight-gradient stream and
+  // must survive until then
+  NLPS_CUDA(cudaMalloc(&m->ln_partial, sizeof(float) * layernorm_backward_scratch_floats(m->E) * (size_t)std::max(1, 2 * m->L)));
   NLPS_CUDA(cudaMalloc(&m->colsum_scratch, sizeof(float) * colsum_scratch_floats(std::max<int64_t>(std::max(m->E, m->F), m->ldV))));
-  NLPS_CUDA(cudaMalloc(&m->colsum_tickets, sizeof(unsigned int) * 4096));
-  NLPS_CUDA(cudaMemset(m->colsum_tickets, 0, sizeof(unsigned int) * 4096));
+  NLPS_CUDA(cudaMalloc(&m->colsum_scratch_w, sizeof(float) * colsum_scratch_floats(std::max<int64_t>(std::max(m->E, m->F), m->ldV))));
+  NLPS_CUDA(cudaMalloc(&m->colsum_tickets, sizeof(unsigned int) * 8192));
+  NLPS_CUDA(cudaMemset(m->colsum_tickets, 0, sizeof(unsigned int) * 8192));
   NLPS_CUDA(cudaMalloc(&m->sumsq_scratch, sizeof(float) * sumsq_scratch_floats()));
   NLPS_CUDA(cudaMalloc(&m->hyper, sizeof(float) * 4));
   NLPS_CUDA(cudaMemset(m->hyper, 0, sizeof(float) * 4));
@@ -663,7 +688,7 @@ int nlps_destroy(nlps_model* m) {
   for (nlps_cache* c : m->pool) { if (c->base) cudaFree(c->base); if (c->logits_base) cudaFree(c->logits_base); delete c; }
   float* bufs[] = {m->P, m->G, m->M, m->Vv, m->pe, m->g0, m->g1, m->gdrop, m->dctx, m->dqkv, m->dhid, m->delta,
                    m->row_loss, m->rows_tmp, m->ln_partial, m->colsum_scratch, m->sumsq_scratch, m->scalars, m->colsum32,
-                   m->g1b, m->gdropb, m->dbv_partial, m->vchunk};
+                   m->g1b, m->gdropb, m->dbv_partial, m->vchunk, m->colsum_scratch_w};
   for (float* b : bufs) if (b) cudaFree(b);
   if (m->iscratch) cudaFree(m->iscratch);
   if (m->err_flag) cudaFree(m->err_flag);
@@ -977,13 +1002,20 @@ int nlps_backward(nlps_model* m, nlps_cache* c, const float* d_dlogits, int64_t 
     g.trans_a = true;
     cudaStream_t ws = st;
     NLPS_TRY(wgrad_fork(m, &ws));                      // off the critical path: weight-gradient stream
+    // db_vocab first: a bandwidth-bound pass over the dlogits that now runs next to the tensor-bound dH product
+    {
+      const bool side = side_sums();
+      cudaStream_t cs = side ? ws : st;
+      float* scratch = side ? m->colsum_scratch_w : m->colsum_scratch;
+      unsigned int* tickets = side ? colsum_tickets_w(m, m->V) : colsum_tickets_for(m, m->V);
+      if (m->dbv_partial_rows > 0)     // the cross-entropy pass already summed 16-row slabs of these dlogits
+        NLPS_TRY(colsum(cs, m->dbv_partial_rows, m->V, m->dbv_partial, m->ldV, m->G + m->off_bvocab, scratch, tickets));
+      else
+        NLPS_TRY(colsum(cs, N, m->V, d_dlogits, ldd, m->G + m->off_bvocab, scratch, tickets));
+    }
+    m->dbv_partial_rows = 0;
     NLPS_TRY(gemm_dispatch(ws, m->precision, g));
     NLPS_TRY(wgrad_done(m, W_VOCAB));
-    if (m->dbv_partial_rows > 0)     // the cross-entropy pass already summed 16-row slabs of these dlogits
-      NLPS_TRY(colsum(st, m->dbv_partial_rows, m->V, m->dbv_partial, m->ldV, m->G + m->off_bvocab, m->colsum_scratch, colsum_tickets_for(m, m->V)));
-    else
-      NLPS_TRY(colsum(st, N, m->V, d_dlogits, ldd, m->G + m->off_bvocab, m->colsum_scratch, colsum_tickets_for(m, m->V)));
-    m->dbv_partial_rows = 0;
   }
   {  // dH = dlogits W_vocab^T                                          (:355)
     GemmArgs g = gemm_nn(N, E, m->V, d_dlogits, ldd, m->P + m->off_Wvocab, m->ldV, m->g0, E);

@@ -600,9 +600,22 @@ int layernorm_forward(cudaStream_t st, int64_t rows, int E, const float* x, cons
 
 size_t layernorm_backward_scratch_floats(int E) { return (size_t)kLnPartials * 3 * E; }
 
+// second half of layernorm_backward when it was called with defer_finish: the fixed-order sum of the per-CTA partials
+// (the parameter gradients are off the critical path of backward: the model runs this on its weight-gradient stream)
+int layernorm_backward_finish(cudaStream_t st, int64_t rows, int E, const float* partial, float* dgamma, float* dbeta,
+                              float* dbias) {
+  if (rows <= 0) return 0;
+  const int grid = (int)std::min<int64_t>(kLnPartials, ceil_div(rows, kLnWarps));
+  const int nsum = dbias != nullptr ? 3 : 2;
+  ln_bwd_finish_kernel<<<(unsigned)ceil_div(nsum * E, 32), 256, 0, st>>>(grid, E, nsum, partial, dgamma, dbeta, dbias);
+  NLPS_LAUNCH_CHECK();
+  return 0;
+}
+
 int layernorm_backward(cudaStream_t st, int64_t rows, int E, const float* dy, const float* x, const float* mean,
                        const float* rstd, const float* gamma, float* dx, float* dx_dropped,
-                       const DropoutParams* drop, float* dgamma, float* dbeta, float* partial, float* dbias) {
+                       const DropoutParams* drop, float* dgamma, float* dbeta, float* partial, float* dbias,
+                       bool defer_finish) {
   if (rows <= 0) return 0;
   const int grid = (int)std::min<int64_t>(kLnPartials, ceil_div(rows, kLnWarps));
   const int use_drop = (drop != nullptr && drop->p > 0.f && dx_dropped != nullptr) ? 1 : 0;
@@ -635,6 +648,7 @@ int layernorm_backward(cudaStream_t st, int64_t rows, int E, const float* dy, co
   }
 #undef NLPS_LN_BWD
   NLPS_LAUNCH_CHECK();
+  if (defer_finish) return 0;
   ln_bwd_finish_kernel<<<(unsigned)ceil_div(nsum * E, 32), 256, 0, st>>>(grid, E, nsum, partial, dgamma, dbeta, dbias);
   NLPS_LAUNCH_CHECK();
   return 0;
