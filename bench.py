@@ -9,9 +9,12 @@ clip, Adam) over one batch of synthetic token ids.  Default workload = BASELINE.
 configuration the metric is quoted on; weak scaling (per-GPU batch fixed).
 
 Prints ONE JSON line (rank 0).  `value` = device-resident tokens/s; `e2e` = the same metric through
-the public API with pinned-host -> device copies of x,y and a device -> host read of the loss inside
-every timed step.  `--impl reference` times the reference's CPU algorithm (the NumPy oracle port;
-the reference itself is not on the GPU box) on a bounded sample of the same workload.
+the public API with pinned-host -> device copies of x,y and a device -> host read of every step's loss
+inside the timed region.  `roofline` = the dominant kernel (tcgen05 FFN GEMM) against the tcgen05 TF32
+peak measured in the same run; `cpu_baseline` = the unmodified reference (baseline/_ref, installed by
+tools/install_reference.py; the NumPy oracle port only if it is absent) on the host cores; `other` = the
+FP32-faithful arithmetic modes and the other BASELINE.json configurations, a few steps each.
+`--impl reference` times that CPU implementation alone, on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
