@@ -461,11 +461,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // instead of 48 KB -- shared-memory bandwidth, not the tensor pipe, is what bounds the FP32-operand
 // (TF32) GEMM.  Each CTA keeps its own 128 accumulator rows in its TMEM and runs its own epilogue.
 constexpr int kPairStages = 6;
+constexpr int kPairThreads = kThreads + 32;                      // + warp 10: the second TMA producer (B operand)
 constexpr int kPairStageBytes = 2 * BM * BK * 4;                 // A half + B half, 16 KB each
 constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kEpiWarps * kEpiStageFloats * 4 + 256 + 1024;
 
 template <bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ KernelArgs ka) {
   constexpr int BN = 256, BMP = 256;
@@ -506,9 +507,13 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0) {
-    // ===================== TMA producer (one per CTA) =====================
+  if (warp == 0 || warp == 2 + kEpiWarps) {
+    // ===================== TMA producers (two per CTA: warp 0 loads A, warp 10 loads B) =====================
+    // An MN-major operand needs four 32-row boxes per k-block (the 128-B swizzle span holds 32 floats), so a weight-gradient
+    // product (both operands MN-major) issues 8 TMA instructions per stage; one thread issuing all of them could not keep
+    // up with the 512-clk k-block of the MMA (measured main-loop ceiling 555 TF against 750 for the 2- and 5-box products).
     if (lane == 0) {
+      const bool load_a = warp == 0;
       int stage = 0; uint32_t phase = 0;
       for (int item = pair; item < items; item += num_pairs) {
         const int split = item / tiles;
@@ -522,20 +527,23 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           const uint32_t a_dst = base + stage * kPairStageBytes;
           const uint32_t b_dst = a_dst + BM * BK * 4;
           const uint32_t lead_full = mapa_rank(full_bar(stage), 0);
-          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * kPairStageBytes);   // both CTAs' bytes land here
           int ka0 = kb * BK, kb0k = ka0;
           if (ka.x3_kb) x3_coords(kb, ka.x3_kb, ka.x3_cb, ka0, kb0k);
-          if (A_MN) {
+          if (load_a) {
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * kPairStageBytes);   // both CTAs' A and B bytes land here
+            if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_2d_pair(a_dst + j * 4096, &map_a, lead_full, m0 + 32 * j, ka0);
+              for (int j = 0; j < 4; ++j) tma_load_2d_pair(a_dst + j * 4096, &map_a, lead_full, m0 + 32 * j, ka0);
+            } else {
+              tma_load_2d_pair(a_dst, &map_a, lead_full, ka0, m0);
+            }
           } else {
-            tma_load_2d_pair(a_dst, &map_a, lead_full, ka0, m0);
-          }
-          if (B_MN) {
+            if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_2d_pair(b_dst + j * 4096, &map_b, lead_full, n0 + 32 * j, kb0k);
-          } else {
-            tma_load_2d_pair(b_dst, &map_b, lead_full, kb0k, n0);
+              for (int j = 0; j < 4; ++j) tma_load_2d_pair(b_dst + j * 4096, &map_b, lead_full, n0 + 32 * j, kb0k);
+            } else {
+              tma_load_2d_pair(b_dst, &map_b, lead_full, kb0k, n0);
+            }
           }
           if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
         }
@@ -903,7 +911,7 @@ int launch_pair_one(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& m
     NLPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     attr_set = true;
   }
-  kern<<<grid, kThreads, kPairSmemBytes, st>>>(ma, mb, ka);
+  kern<<<grid, kPairThreads, kPairSmemBytes, st>>>(ma, mb, ka);
   NLPS_LAUNCH_CHECK();
   return 0;
 }
