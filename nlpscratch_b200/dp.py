@@ -89,6 +89,8 @@ class DataParallel:
         self.rank = dist.get_rank(group)
         self._torch, self._dist, self._lib, self._C = torch, dist, _lib, C
         self.backend = backend or os.environ.get("NLPS_DP_BACKEND", "native")
+        if "NLPS_DP_BUCKET" in os.environ:                       # A/B: floats per coalesced exchange
+            min_bucket_floats = int(os.environ["NLPS_DP_BUCKET"])
         if self.backend not in ("native", "torch"):
             raise ValueError("backend must be 'native' or 'torch'")
         if self.backend == "native":
